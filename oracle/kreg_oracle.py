@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY -- Python face of the CPU oracle (oracle/kreg_oracle.c).
+
+The oracle restates the reference's KREG algorithm (mlatom/fortran/KREG.f90 and the
+Gaussian/RE/unpermuted branch of mlatom/MLatomF_src/A_KRR_kernel.f90, A_KRR.f90) on the
+CPU.  It is pinned against the reference's own compiled library (oracle/_ref/KREG.so, see
+oracle/ref_kreg.py) by tests/test_oracle_vs_ref.py and by the golden vectors in
+tests/golden/ (generated from that library by tools/make_golden.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this
+module; the product package mlatom_b200 never does.
+
+The linear solve is LAPACK dpotrf/dpotrs('U') exactly as mlatom/fortran/mathUtils.f90:65,79,
+through SciPy (OpenBLAS).  The reference links MKL; no reference test pins alpha at that
+boundary, so alpha parity is *unpinned* (checked through residuals and fixed-alpha
+predictions instead).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_double, c_int, c_long
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libkreg_oracle.so")
+_lib = None
+_DP = POINTER(c_double)
+
+
+def build(force: bool = False) -> None:
+    src = os.path.join(_HERE, "kreg_oracle.c")
+    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libkreg_oracle.so"], stdout=subprocess.DEVNULL)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.kro_num_threads.restype = c_int
+    return _lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_DP)
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def set_threads(n: int) -> None:
+    load().kro_set_num_threads(c_int(int(n)))
+
+
+def num_threads() -> int:
+    return int(load().kro_num_threads())
+
+
+def ac2d(nat: int) -> np.ndarray:
+    out = np.zeros((nat, nat), dtype=np.int32)
+    load().kro_ac2d(c_int(nat), out.ctypes.data_as(POINTER(c_int)))
+    return out
+
+
+def xeq(req: np.ndarray) -> np.ndarray:
+    req = _c(req)
+    nat = req.shape[0]
+    out = np.zeros(nat * (nat - 1) // 2)
+    load().kro_xeq(c_int(nat), _d(req), _d(out))
+    return out
+
+
+def descriptors(xyz: np.ndarray, xeq_: np.ndarray) -> np.ndarray:
+    xyz = _c(xyz)
+    n, nat, _ = xyz.shape
+    out = np.zeros((n, nat * (nat - 1) // 2))
+    load().kro_descriptors(c_int(nat), c_long(n), _d(xyz), _d(_c(xeq_)), _d(out))
+    return out
+
+
+def kernel_matrix(xyz, x, sigma, ntrval, ntrgr, factored=False) -> np.ndarray:
+    xyz, x = _c(xyz), _c(x)
+    n, nat, _ = xyz.shape
+    m = ntrval + ntrgr
+    k = np.zeros((m, m))
+    fn = load().kro_kernel_matrix_factored if factored else load().kro_kernel_matrix
+    fn(c_int(nat), c_int(n), c_int(ntrval), c_int(ntrgr), _d(xyz), _d(x), c_double(sigma), _d(k))
+    return k
+
+
+def solve(k: np.ndarray, y: np.ndarray, ntrval: int, ntrgr: int, lambdav: float, lambdag: float):
+    """calcAlpha (KREG.f90:598-627): copy K, shift the two diagonal blocks, dpotrf/dpotrs 'U'."""
+    from scipy.linalg import cho_factor, cho_solve
+
+    a = np.array(k, dtype=np.float64, order="F", copy=True)
+    load().kro_add_lambda(c_int(ntrval), c_int(ntrgr), c_double(lambdav), c_double(lambdag), _d(a))
+    c, low = cho_factor(a, lower=False, overwrite_a=True, check_finite=False)
+    return cho_solve((c, low), _c(y), check_finite=False)
+
+
+def ytrain(y=None, ygrad=None, prior=0.0) -> np.ndarray:
+    """kreg_api.py:51-72: [Y - prior ; gradients flattened (point, atom, xyz)]."""
+    parts = []
+    if y is not None:
+        parts.append(np.asarray(y, dtype=np.float64) - prior)
+    if ygrad is not None:
+        parts.append(np.asarray(ygrad, dtype=np.float64).reshape(-1))
+    return np.concatenate(parts)
+
+
+def predict_kregf90(xyz_tr, x_tr, alpha, sigma, ntrval, ntrgr, xyz_te, x_te, calc_val=True, calc_grad=True):
+    xyz_tr, x_tr, xyz_te, x_te, alpha = map(_c, (xyz_tr, x_tr, xyz_te, x_te, alpha))
+    ntr, nat, _ = xyz_tr.shape
+    npred = xyz_te.shape[0]
+    e = np.zeros(npred)
+    g = np.zeros((npred, nat, 3))
+    load().kro_predict_kregf90(
+        c_int(nat), c_int(ntr), c_int(ntrval), c_int(ntrgr), _d(xyz_tr), _d(x_tr), _d(alpha.reshape(-1)),
+        c_double(sigma), c_long(npred), _d(xyz_te), _d(x_te), c_int(calc_val), c_int(calc_grad), _d(e), _d(g),
+    )
+    return e, g
+
+
+def predict_mlatomf(xyz_tr, x_tr, alpha, sigma, prior, ntrval, ntrgr, xyz_te, x_te, calc_val=True, calc_grad=True):
+    xyz_tr, x_tr, xyz_te, x_te, alpha = map(_c, (xyz_tr, x_tr, xyz_te, x_te, alpha))
+    ntr, nat, _ = xyz_tr.shape
+    npred = xyz_te.shape[0]
+    e = np.zeros(npred)
+    g = np.zeros((npred, nat, 3))
+    load().kro_predict_mlatomf(
+        c_int(nat), c_int(ntr), c_int(ntrval), c_int(ntrgr), _d(xyz_tr), _d(x_tr), _d(alpha.reshape(-1)),
+        c_double(sigma), c_double(prior), c_long(npred), _d(xyz_te), _d(x_te), c_int(calc_val),
+        c_int(calc_grad), _d(e), _d(g),
+    )
+    return e, g
+
+
+def precompute_v(xyz_tr, x_tr, alpha_g):
+    xyz_tr, x_tr = _c(xyz_tr), _c(x_tr)
+    ntr, nat, _ = xyz_tr.shape
+    ag = _c(alpha_g).reshape(ntr, nat, 3)
+    v = np.zeros_like(x_tr)
+    load().kro_precompute_v(c_int(nat), c_int(ntr), _d(xyz_tr), _d(x_tr), _d(ag), _d(v))
+    return v
+
+
+def predict_factored(x_tr, alpha_v, v, sigma, prior, xyz_te, x_te, calc_grad=True, want_scale=False):
+    x_tr, xyz_te, x_te = _c(x_tr), _c(xyz_te), _c(x_te)
+    ntr = x_tr.shape[0]
+    npred, nat, _ = xyz_te.shape
+    av = None if alpha_v is None else _c(alpha_v).reshape(-1)
+    vv = None if v is None else _c(v)
+    e = np.zeros(npred)
+    g = np.zeros((npred, nat, 3))
+    s = np.zeros(npred) if want_scale else None
+    load().kro_predict_factored(
+        c_int(nat), c_int(ntr), _d(x_tr), _d(av), _d(vv), c_double(sigma), c_double(prior), c_long(npred),
+        _d(xyz_te), _d(x_te), c_int(calc_grad), _d(e), _d(g), _d(s),
+    )
+    return (e, g, s) if want_scale else (e, g)
