@@ -1,0 +1,155 @@
+/*
+ * kreg_b200.h -- C ABI of libkreg_b200.so: the B200-native (sm_100a) KREG hot path.
+ *
+ * This is the drop-in boundary for the reference's native KREG layer.  Every entry point
+ * replaces one routine of the reference's f2py module `KREG` (mlatom/fortran/KREG.f90, called
+ * from mlatom/kreg_api.py) or of MLatomF's KRR engine (mlatom/MLatomF_src/A_KRR*.f90); the
+ * replaced interface is cited at each declaration.  INTEGRATION.md shows the binding a
+ * maintainer would put in mlatom/kreg_api.py.
+ *
+ * Conventions
+ *  - All array arguments are DEVICE pointers to fp64 unless the name ends in `_host`.
+ *    The caller owns every buffer (PyTorch tensors in the Python host layer).  No entry point
+ *    allocates device memory; scratch space is passed in and its size is queried first.
+ *  - Layouts are C order and byte-identical to the reference's Fortran arrays:
+ *      xyz[p][a][t]   == Fortran XYZ(t,a,p)  (3,Nat,N)      (KREG.f90:299)
+ *      X[p][d]        == Fortran X(d,p)      (D,N)          (KREG.f90:300)
+ *      K[i*ldk + j]   == Fortran K(j,i) == K(i,j)           (KREG.f90:301; symmetric)
+ *      alpha / y      : values first, then gradients in (point, atom, xyz) order, xyz fastest
+ *                       (KREG.f90:273-291 get_itrgrxyz; kreg_api.py:51-72)
+ *    D = Nat(Nat-1)/2; descriptor index of atom pair a<b (0-based): (2Nat-a-1)a/2 + (b-a) - 1
+ *    (KREG.f90:48).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    asynchronous with respect to the host unless stated otherwise, re-entrant per stream.
+ *  - Return value: 0 = ok; <0 = argument / capability error (see KREG_E_*); >0 = numerical
+ *    failure reported by the factorisation (LAPACK `info`, kreg_solve only).  The library never
+ *    calls exit()/abort() (the reference's stopKREG does: mlatom/fortran/stopper.f90:13).
+ *  - There is no CPU fallback anywhere: every function needs an sm_100 device.
+ */
+#ifndef KREG_B200_H
+#define KREG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KREG_OK 0
+#define KREG_E_BADARG (-1)      /* null pointer, negative size, inconsistent counts */
+#define KREG_E_UNSUPPORTED (-2) /* Natoms outside the compiled range, wrong device arch */
+#define KREG_E_WORKSPACE (-3)   /* scratch buffer too small */
+#define KREG_E_CUDA (-4)        /* a CUDA runtime / cuSOLVER call failed (see kreg_last_error) */
+
+#define KREG_MIN_NATOMS 2
+#define KREG_MAX_NATOMS 24
+
+/* kreg_build_kernel_matrix `fill` argument: which part of the symmetric K is written */
+#define KREG_FILL_LOWER 0 /* K[i][j], j <= i (row-major lower == column-major upper, potrf 'U') */
+#define KREG_FILL_FULL 1  /* both triangles, as the reference does (KREG.f90:317-318)        */
+
+/* kreg_predict `flags` */
+#define KREG_PREDICT_ENERGY 1
+#define KREG_PREDICT_GRADIENT 2
+
+/* Library / device information ------------------------------------------------------- */
+
+int kreg_abi_version(void);
+/* Text of the last CUDA/cuSOLVER error seen by the calling thread ("" if none). */
+const char *kreg_last_error(void);
+/* 0 if the current CUDA device can run the kernels (compute capability 10.x). */
+int kreg_device_check(void);
+
+/* FP64 issue-rate probe used as the roofline denominator for the prediction kernel
+ * (MEASURED_PEAKS.json holds no FP64 figure).  kind: 0 = DFMA, 1 = DMMA (mma.sync m8n8k4 f64).
+ * Synchronous; writes TFLOP/s (best of `reps` launches of ~`ms_target` ms each). */
+int kreg_measure_fp64_peak(int kind, int reps, double ms_target, double *tflops_host);
+
+/* Descriptors -------------------------------------------------------------------------- */
+
+/* Replaces KREG.kreg.get_xeq (KREG.f90:223-239): equilibrium pair distances.
+ * req[Nat][3] -> xeq[D]. */
+int kreg_xeq(int natoms, const double *req, double *xeq, void *stream);
+
+/* Replaces KREG.kreg.calc_re_descriptors (KREG.f90:241-271; D_rel2eq.f90:17-83):
+ * X[p][d] = xeq[d] / R_d(p).  Bit-identical to the reference (IEEE sqrt and divide, no FMA
+ * contraction in R).  Needed for the model file; the assembly and prediction kernels below
+ * build descriptors on the fly and never read X. */
+int kreg_descriptors(int natoms, int64_t npoints, const double *xyz, const double *xeq, double *X,
+                     void *stream);
+
+/* Kernel-matrix assembly ------------------------------------------------------------------ */
+
+/* Scratch bytes needed by kreg_build_kernel_matrix. */
+size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr);
+
+/* Replaces KREG.kreg.calc_kernel_matrix + the diagonal shift of calcAlpha
+ * (KREG.f90:293-346 and :616-622; A_KRR_kernel.f90:130-188, A_KRR.f90:905-918).
+ * Builds rows [row_begin,row_end) of  K + diag(lambdav*1_NtrVal, lambdagradxyz*1_NtrGrXYZ)
+ * directly from Cartesian coordinates (descriptor build fused into the call).
+ *   ntrval  in {0, ntrain}; ntrgr in {0, 3*natoms*ntrain}  (kreg_api.py:52-72); M = ntrval+ntrgr.
+ *   K points at element (0,0) of an M x ldk row-major matrix (ldk >= M); only rows in the range
+ *   are touched, so ranks can assemble disjoint row slabs of one matrix.
+ *   fill = KREG_FILL_LOWER writes j <= i only; KREG_FILL_FULL mirrors as the reference does. */
+int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrval, int64_t ntrgr,
+                             const double *xyz_train, const double *xeq, double sigma,
+                             double lambdav, double lambdagradxyz, int64_t row_begin,
+                             int64_t row_end, int fill, double *K, int64_t ldk, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
+/* Rectangular value-value kernel block between two geometry sets (validation kernels for the
+ * hyper-parameter search; MLatomF calc_Kvalidate, A_KRR_kernel.f90:190-223):
+ * Kout[i][j] = k(X(xyz_a[i]), X(xyz_b[j])), row-major na x ldk. */
+int kreg_kernel_block(int natoms, int64_t na, const double *xyz_a, int64_t nb, const double *xyz_b,
+                      const double *xeq, double sigma, double *Kout, int64_t ldk, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* Linear solve ------------------------------------------------------------------------------ */
+
+/* Device / pinned-host scratch needed by kreg_solve for an m x m system. */
+int kreg_solve_workspace_bytes(int64_t m, size_t *device_bytes, size_t *host_bytes);
+
+/* Replaces mathUtils.solveSysLinEqs (mlatom/fortran/mathUtils.f90:8-104: dpotrf('U') +
+ * dpotrs): in-place Cholesky of the matrix produced by kreg_build_kernel_matrix
+ * (KREG_FILL_LOWER or _FULL) and solve for one right-hand side.  y is overwritten with alpha.
+ * The only library call on the path (cuSOLVER potrf/potrs); timed separately by bench.py.
+ * Synchronises the stream to read `info`.  Returns info (>0: leading minor not positive
+ * definite; K is destroyed) or a negative error. */
+int kreg_solve(int64_t m, double *K, int64_t ldk, double *y_inout, void *device_workspace,
+               size_t device_bytes, void *host_workspace, size_t host_bytes, void *stream);
+
+/* Prediction -------------------------------------------------------------------------------- */
+
+/* Replaces nothing one-to-one: hoists the training-set half of the reference's gradient terms
+ * out of the prediction loop:  v[j][d] = sum_{(a,t)} J_j[d,(a,t)] *
+ * alpha_grad[j][a][t], J = descriptor Jacobian (KREG.f90:121,146). */
+int kreg_precompute_v(int natoms, int64_t ntrain, const double *xyz_train, const double *xeq,
+                      const double *alpha_grad, double *V, void *stream);
+
+/* Size in bytes of the packed model consumed by kreg_predict. */
+size_t kreg_packed_model_bytes(int natoms, int64_t ntrain, int has_gradient_terms);
+
+/* Packs a trained model into the tensor-core fragment order the prediction kernel streams
+ * through shared memory.  alpha_val may be NULL (gradient-only model: NtrVal = 0) and V may be
+ * NULL (values-only model).  `center[D]` is written with the descriptor mean that is
+ * subtracted from train and test descriptors alike (the kernel is invariant to it). */
+int kreg_pack_model(int natoms, int64_t ntrain, const double *xyz_train, const double *xeq,
+                    const double *alpha_val, const double *V, double sigma, double *center,
+                    void *packed, size_t packed_bytes, void *stream);
+
+/* Replaces KREG.kreg.predict (KREG.f90:534-596: Yest_KRR :348-366, YgradXYZest_KRR :368-391)
+ * and MLatomF calcEst_KRR (A_KRR.f90:985-1029; A_KRR_kernel.f90:225-245, :327-412):
+ *   E[i]       = prior + sum_j alpha_j k_ij + sum_j sum_bu alpha_j,bu dk_ij/dM_j,bu
+ *   G[i][a][t] = dE_i / d xyz[i][a][t]            (gradient, not force: kreg_api.py:126-131)
+ * for npoints geometries, energies and gradients in ONE pass over the training set.
+ * flags: KREG_PREDICT_ENERGY | KREG_PREDICT_GRADIENT; E or G may be NULL when not requested. */
+int kreg_predict(int natoms, int64_t ntrain, const void *packed, const double *center,
+                 const double *xeq, double sigma, double prior, int has_gradient_terms,
+                 int64_t npoints, const double *xyz, int flags, double *E, double *G,
+                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KREG_B200_H */

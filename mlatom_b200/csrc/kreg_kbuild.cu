@@ -1,0 +1,529 @@
+// kreg_kbuild.cu -- kernel-matrix assembly: values block on FP64 tensor cores, gradient-augmented
+// blocks as dense 3Nat x 3Nat tiles written at HBM rate.
+//
+// Replaces KREG.kreg.calc_kernel_matrix + the lambda shift of calcAlpha
+// (mlatom/fortran/KREG.f90:293-346, :616-622; MLatomF_src/A_KRR_kernel.f90:130-188).
+// Blocks (row-major K, M = Nv + Ng, Ng = 3 Nat Ntr, G3 = 3 Nat):
+//   K[i][j]                         = k_ij                                   (values, KREG.f90:314-320)
+//   K[Nv + p*G3 + q][i]             = (k_pi/s^2) (J_p^T (X_i - X_p))_q       (value-gradient, :326-331)
+//   K[Nv + i*G3 + q][Nv + j*G3 + r] = (k_ij/s^2) [J_i^T J_j - u_i u_j^T/s^2]_{qr},
+//                                     u_i = J_i^T D, u_j = J_j^T D, D = X_j - X_i (grad-grad, :337-343)
+// J[d,(a,t)] = X_d (x_c - x_a)_t / R_ac^2 for d = (a,c) is the descriptor Jacobian (KREG.f90:121,146); the
+// bracket is the O(D) expansion of the reference's (Nat-1)^2-term double loop.
+#include "kreg_common.cuh"
+#include "kreg_internal.h"
+
+namespace kreg {
+
+// =================================================================================================
+// Values block / rectangular value-value block:  S = XA . XB^T on DMMA.8x8x4, then exp.
+// CTA tile 128 x 128, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 64 = 4 x 8 DMMA tiles.
+// =================================================================================================
+constexpr int kTile = 128;
+
+struct ValuesArgs {
+  const double *XA;  // [na][XS] centred descriptors, zero padded
+  const double *XB;  // [nb][XS]
+  const double *biasA;  // -c1 n_i / 2
+  const double *biasB;
+  int64_t na, nb;
+  int XS;       // row stride (doubles), multiple of 4*KC
+  int nchunks;  // XS / (4*KC)
+  double c1;
+  double lambda;  // added where i == j when `symmetric`
+  int symmetric;  // 1: XA == XB (K build): exact 1+lambda on the diagonal, tiles with tj > ti skipped unless `all_cols`
+  int all_cols;   // 1: compute every column tile directly (row-slab FULL mode / rectangular block)
+  int mirror;     // 1: also write K[j][i] for off-diagonal tiles (whole-matrix FULL mode)
+  int64_t row_begin, row_end;  // rows of A to produce
+  double *K;
+  int64_t ldk;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(256) values_tile_kernel(const ValuesArgs a) {
+  constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);  // stride = 4 mod 8 doubles: conflict-free LDS.64 fragments
+  extern __shared__ __align__(16) double sm[];
+  double *As = sm;                    // [128][XSP]
+  double *Bs = As + kTile * XSP;      // [128][XSP]
+  double *bA = Bs + kTile * XSP;      // [128]
+  double *bB = bA + kTile;            // [128]
+  double *tab = bB + kTile;           // [64]
+
+  const int64_t ti = (int64_t)blockIdx.y + a.row_begin / kTile;
+  const int64_t tj = blockIdx.x;
+  if (a.symmetric && !a.all_cols && tj > ti) return;
+  const int64_t i0 = ti * kTile, j0 = tj * kTile;
+  if (i0 >= a.na || j0 >= a.nb) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wi = warp >> 1, wj = warp & 1;
+
+  fill_exp_table(tab, tid, 256);
+  if (tid < kTile) {
+    bA[tid] = (i0 + tid < a.na) ? a.biasA[i0 + tid] : 0.0;
+    bB[tid] = (j0 + tid < a.nb) ? a.biasB[j0 + tid] : 0.0;
+  }
+
+  double S[4][8][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
+
+  for (int ch = 0; ch < a.nchunks; ch++) {
+    if (ch) __syncthreads();
+    // stage the K-chunk of both tiles (16-byte vector loads; rows past the end read as zero)
+    for (int e = tid; e < kTile * KC * 2; e += 256) {
+      const int r = e / (KC * 2), c2 = e % (KC * 2);
+      double2 va = make_double2(0.0, 0.0), vb = va;
+      if (i0 + r < a.na) va = *reinterpret_cast<const double2 *>(a.XA + (i0 + r) * a.XS + ch * KC * 4 + c2 * 2);
+      if (j0 + r < a.nb) vb = *reinterpret_cast<const double2 *>(a.XB + (j0 + r) * a.XS + ch * KC * 4 + c2 * 2);
+      *reinterpret_cast<double2 *>(As + r * XSP + c2 * 2) = va;
+      *reinterpret_cast<double2 *>(Bs + r * XSP + c2 * 2) = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < KC; ks++) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) af[mt] = As[(wi * 32 + mt * 8 + g) * XSP + ks * 4 + q];
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) bf[nt] = Bs[(wj * 64 + nt * 8 + g) * XSP + ks * 4 + q];
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) dmma884(S[mt][nt], af[mt], bf[nt]);
+    }
+  }
+
+  // epilogue: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly 1 + lambda, coalesced 16-byte stores
+  const bool diag_tile = a.symmetric && ti == tj;
+  const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int ri = wi * 32 + mt * 8 + g;
+    const int64_t i = i0 + ri;
+    const bool row_ok = i < a.na && i >= a.row_begin && i < a.row_end;
+    const double bi = bA[ri];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int cj = wj * 64 + nt * 8 + 2 * q;
+      const int64_t j = j0 + cj;
+      double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bB[cj]), 0.0), tab);
+      double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bB[cj + 1]), 0.0), tab);
+      if (a.symmetric) {
+        if (i == j) k0 = 1.0 + a.lambda;
+        if (i == j + 1) k1 = 1.0 + a.lambda;
+      }
+      if (row_ok) {
+        double *dst = a.K + i * a.ldk + j;
+        const bool w0 = j < a.nb && (!lower_only || j <= i);
+        const bool w1 = j + 1 < a.nb && (!lower_only || j + 1 <= i);
+        if (w0 && w1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          *reinterpret_cast<double2 *>(dst) = make_double2(k0, k1);
+        } else {
+          if (w0) dst[0] = k0;
+          if (w1) dst[1] = k1;
+        }
+      }
+      if (a.mirror && !diag_tile && i < a.na) {
+        if (j < a.nb) a.K[j * a.ldk + i] = k0;
+        if (j + 1 < a.nb) a.K[(j + 1) * a.ldk + i] = k1;
+      }
+    }
+  }
+}
+
+template <int KC>
+static int launch_values_kc(const ValuesArgs &a, cudaStream_t st) {
+  constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
+  const size_t smem = (size_t)(2 * kTile * XSP + 2 * kTile + 64) * sizeof(double);
+  auto kern = values_tile_kernel<KC>;
+  KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t r1 = a.row_end < a.na ? a.row_end : a.na;
+  if (r1 <= a.row_begin) return KREG_OK;
+  const int64_t ti0 = a.row_begin / kTile, ti1 = (r1 - 1) / kTile;
+  dim3 grid((unsigned)((a.nb + kTile - 1) / kTile), (unsigned)(ti1 - ti0 + 1));
+  kern<<<grid, 256, smem, st>>>(a);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
+// k-steps per staged chunk for a descriptor of KS k-steps: at most 12, as even as possible
+static void chunking(int KS, int *KC, int *nchunks) {
+  *nchunks = (KS + 11) / 12;
+  *KC = (KS + *nchunks - 1) / *nchunks;
+}
+
+static int launch_values(ValuesArgs a, int KC, cudaStream_t st) {
+  switch (KC) {
+#define KREG_KC(N) \
+  case N:          \
+    return launch_values_kc<N>(a, st);
+    KREG_KC(1) KREG_KC(2) KREG_KC(3) KREG_KC(4) KREG_KC(5) KREG_KC(6) KREG_KC(7) KREG_KC(8) KREG_KC(9) KREG_KC(10)
+    KREG_KC(11) KREG_KC(12)
+#undef KREG_KC
+    default:
+      return KREG_E_UNSUPPORTED;
+  }
+}
+
+// Centred, zero-padded descriptors + exponent bias for one geometry set.
+__global__ void __launch_bounds__(256) prep_rows_kernel(int nat, int64_t n, const double *__restrict__ xyz,
+                                                        const double *__restrict__ xeq,
+                                                        const double *__restrict__ center, int XS, double c1,
+                                                        double *__restrict__ Xc, double *__restrict__ bias) {
+  const int D = descr_size(nat);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const double *m = xyz + p * nat * 3;
+    double *x = Xc + p * XS;
+    double nn = 0.0;
+    for (int a = 0; a < nat; a++)
+      for (int b = a + 1; b < nat; b++) {
+        int d = pair_index(nat, a, b);
+        double v = xeq[d] / sqrt(rij2_exact(m + 3 * a, m + 3 * b)) - center[d];
+        x[d] = v;
+        nn = fma(v, v, nn);
+      }
+    for (int d = D; d < XS; d++) x[d] = 0.0;
+    bias[p] = -0.5 * c1 * nn;
+  }
+}
+
+// =================================================================================================
+// Gradient-augmented blocks.  One CTA per (geometry i, block of TJ geometries j); thread = one matrix
+// column (j, b, u); it walks the 3 Nat rows (a, t) of geometry i, so every row segment it helps write is
+// TJ * 3 Nat contiguous doubles.  Per element: 2 shared loads + 3 FP64 ops -> HBM-write bound.
+// =================================================================================================
+struct GradArgs {
+  const double *xyz;     // [ntr][NAT][3]
+  const double *Xc;      // [ntr][XS] centred descriptors
+  const double *bias;    // [ntr]
+  const double *E;       // [ntr][NAT][NAT][3]  E(a,c)[t] = dX_{d_ac}/dx_{a,t} (zero for a == c)
+  int64_t ntr;
+  int64_t nv;            // 0 or ntr
+  int XS;
+  double c1, inv_s2, lambdag;
+  int fill;              // KREG_FILL_LOWER / KREG_FILL_FULL
+  int64_t row_begin, row_end;  // absolute row range of K to produce
+  double *K;
+  int64_t ldk;
+};
+
+// E(a,c)[t] = X_d (x_c - x_a)_t / R^2   (KREG.f90:121)
+__global__ void __launch_bounds__(128) jacobian_rows_kernel(int nat, int64_t n, const double *__restrict__ xyz,
+                                                            const double *__restrict__ xeq, double *__restrict__ E) {
+  const int64_t total = n * nat * nat;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = e / (nat * nat);
+    const int ac = (int)(e - p * nat * nat);
+    const int a = ac / nat, c = ac % nat;
+    double *out = E + e * 3;
+    if (a == c) {
+      out[0] = out[1] = out[2] = 0.0;
+      continue;
+    }
+    const double *m = xyz + p * nat * 3;
+    const int lo = a < c ? a : c, hi = a < c ? c : a;
+    const double r2 = rij2_exact(m + 3 * lo, m + 3 * hi);
+    const double x = xeq[pair_index(nat, lo, hi)] / sqrt(r2);
+    const double f = x / r2;
+    for (int t = 0; t < 3; t++) out[t] = f * (m[3 * c + t] - m[3 * a + t]);
+  }
+}
+
+template <int NAT>
+struct GradCfg {
+  static constexpr int G3 = 3 * NAT;
+  static constexpr int D = NAT * (NAT - 1) / 2;
+  static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);
+  static constexpr int THREADS = ((TJ * G3 + 31) / 32) * 32;
+};
+
+template <int NAT>
+__global__ void __launch_bounds__(GradCfg<NAT>::THREADS) grad_blocks_kernel(const GradArgs a) {
+  using C = GradCfg<NAT>;
+  constexpr int G3 = C::G3, D = C::D, TJ = C::TJ;
+  __shared__ double Xi[D];
+  __shared__ double Ei[NAT * NAT * 3];
+  __shared__ double dlt[TJ][D];   // X_j - X_i
+  __shared__ double ui[TJ][G3];   // J_i^T (X_j - X_i)
+  __shared__ double ks[TJ];       // k_ij / sigma^2
+  __shared__ double tab[64];
+
+  const int64_t i = blockIdx.y;
+  const int64_t jb = (int64_t)blockIdx.x * TJ;
+  const int64_t row_i = a.nv + i * G3;
+  // this CTA's rows: [row_i, row_i + G3)
+  if (row_i + G3 <= a.row_begin || row_i >= a.row_end) return;
+  const bool need_gg = jb <= i || a.fill == KREG_FILL_FULL;  // grad-grad columns wanted for this j block
+  if (!need_gg && a.nv == 0) return;
+
+  const int tid = threadIdx.x;
+  const int jl = tid / G3, col = tid % G3;  // column (j, b, u)
+  const int b = col / 3, u = col % 3;
+  const int64_t j = jb + jl;
+  const bool active = jl < TJ && j < a.ntr;
+
+  fill_exp_table(tab, tid, C::THREADS);
+  for (int e = tid; e < D; e += C::THREADS) Xi[e] = a.Xc[i * a.XS + e];
+  for (int e = tid; e < NAT * NAT * 3; e += C::THREADS) Ei[e] = a.E[i * (NAT * NAT * 3) + e];
+  __syncthreads();
+  for (int e = tid; e < TJ * D; e += C::THREADS) {
+    const int jj = e / D, d = e % D;
+    dlt[jj][d] = (jb + jj < a.ntr) ? a.Xc[(jb + jj) * a.XS + d] - Xi[d] : 0.0;
+  }
+  __syncthreads();
+  if (tid < TJ) {
+    double k = 0.0;
+    if (jb + tid < a.ntr) {
+      double d2 = 0.0;
+      for (int d = 0; d < D; d++) d2 = fma(dlt[tid][d], dlt[tid][d], d2);
+      k = (jb + tid == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
+    }
+    ks[tid] = k * a.inv_s2;
+  }
+  // u_i^{(j)}[(a,t)] = sum_c E_i(a,c)[t] * D_j[d_ac]   -- thread (jl, col) computes entry col of its j
+  double ej[NAT];  // E_j(b,c)[u] for all c (0 at c == b)
+  double ujs = 0.0;
+  if (active) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NAT; c++) {
+      if (c != b) {
+        const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
+        s = fma(Ei[(b * NAT + c) * 3 + u], dlt[jl][d], s);
+      }
+    }
+    ui[jl][col] = s;
+    double sj = 0.0;
+#pragma unroll
+    for (int c = 0; c < NAT; c++) {
+      ej[c] = a.E[(j * NAT * NAT + b * NAT + c) * 3 + u];
+      if (c != b) {
+        const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
+        sj = fma(ej[c], dlt[jl][d], sj);
+      }
+    }
+    ujs = sj * a.inv_s2;  // u_j[col] / sigma^2
+  }
+  __syncthreads();
+  if (!active) return;
+  const double kj = ks[jl];
+
+  // value-gradient block: K[row_i + q][j] = (k/s^2) (J_i^T (X_j - X_i))_q ; thread (jl, col) writes q = col
+  if (a.nv) {
+    const int64_t r = row_i + col;
+    if (r >= a.row_begin && r < a.row_end) {
+      const double v = kj * ui[jl][col];
+      a.K[r * a.ldk + j] = v;
+      if (a.fill == KREG_FILL_FULL) a.K[j * a.ldk + r] = v;  // mirrored value-gradient entry (value row j)
+    }
+  }
+  if (!need_gg) return;
+  if (a.fill != KREG_FILL_FULL && j > i) return;
+  // gradient-gradient block, rows (a,t) of geometry i, this thread's column (j,b,u)
+  double *dst = a.K + row_i * a.ldk + a.nv + j * G3 + col;
+#pragma unroll
+  for (int aa = 0; aa < NAT; aa++) {
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int q = aa * 3 + t;
+      double jj;
+      if (aa == b) {
+        jj = 0.0;
+#pragma unroll
+        for (int c = 0; c < NAT; c++) jj = fma(Ei[(b * NAT + c) * 3 + t], ej[c], jj);  // E(b,b) = 0
+      } else {
+        jj = Ei[(aa * NAT + b) * 3 + t] * ej[aa];  // E_i(a,b)[t] * E_j(b,a)[u]
+      }
+      double v = kj * fma(-ui[jl][q], ujs, jj);
+      if (j == i && q == col) v += a.lambdag;
+      const int64_t r = row_i + q;
+      if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * a.ldk] = v;
+    }
+  }
+}
+
+template <int NAT>
+static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
+  using C = GradCfg<NAT>;
+  dim3 grid((unsigned)((a.ntr + C::TJ - 1) / C::TJ), (unsigned)a.ntr);
+  grad_blocks_kernel<NAT><<<grid, C::THREADS, 0, st>>>(a);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
+static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
+  switch (nat) {
+#define KREG_CASE(N) \
+  case N:            \
+    return launch_grad_nat<N>(a, st);
+    KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9)
+    KREG_CASE(10) KREG_CASE(11) KREG_CASE(12) KREG_CASE(21)
+#undef KREG_CASE
+    default:
+      return KREG_E_UNSUPPORTED;
+  }
+}
+
+// workspace carve-up helpers ---------------------------------------------------------------
+struct BuildWs {
+  size_t off_center, off_X, off_bias, off_E, total;
+  int XS, KC, nchunks;
+};
+
+static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
+  BuildWs w;
+  const TcShape sh(nat);
+  chunking(sh.KS, &w.KC, &w.nchunks);
+  w.XS = w.KC * w.nchunks * 4;
+  size_t off = 0;
+  auto take = [&](size_t doubles) {
+    size_t o = off;
+    off += (doubles * sizeof(double) + 255) / 256 * 256;
+    return o;
+  };
+  w.off_center = take(sh.D);
+  w.off_X = take((size_t)n * w.XS);
+  w.off_bias = take((size_t)n);
+  w.off_E = with_grad ? take((size_t)n * nat * nat * 3) : off;
+  w.total = off;
+  return w;
+}
+
+}  // namespace kreg
+
+using namespace kreg;
+
+extern "C" size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain < 0) return 0;
+  return build_ws(natoms, ntrain, ntrgr > 0).total;
+}
+
+extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrval, int64_t ntrgr,
+                                        const double *xyz_train, const double *xeq, double sigma, double lambdav,
+                                        double lambdagradxyz, int64_t row_begin, int64_t row_end, int fill, double *K,
+                                        int64_t ldk, void *workspace, size_t workspace_bytes, void *stream) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  const int64_t G3 = 3 * (int64_t)natoms;
+  if (ntrain <= 0 || !xyz_train || !xeq || !K || !workspace || !(sigma > 0.0)) return KREG_E_BADARG;
+  if (!(ntrval == 0 || ntrval == ntrain) || !(ntrgr == 0 || ntrgr == G3 * ntrain) || ntrval + ntrgr == 0)
+    return KREG_E_BADARG;
+  const int64_t M = ntrval + ntrgr;
+  if (ldk < M || row_begin < 0 || row_end > M || row_begin > row_end) return KREG_E_BADARG;
+  if (fill != KREG_FILL_LOWER && fill != KREG_FILL_FULL) return KREG_E_BADARG;
+  // gradient models: the mirrored (FULL) layout is only produced for the whole matrix
+  if (fill == KREG_FILL_FULL && ntrgr > 0 && !(row_begin == 0 && row_end == M)) return KREG_E_BADARG;
+  const BuildWs w = build_ws(natoms, ntrain, ntrgr > 0);
+  if (workspace_bytes < w.total) return KREG_E_WORKSPACE;
+  if (row_begin == row_end) return KREG_OK;
+  cudaStream_t st = as_stream(stream);
+  char *ws = static_cast<char *>(workspace);
+  double *center = reinterpret_cast<double *>(ws + w.off_center);
+  double *Xc = reinterpret_cast<double *>(ws + w.off_X);
+  double *bias = reinterpret_cast<double *>(ws + w.off_bias);
+  const double inv_s2 = 1.0 / (sigma * sigma);
+  const double c1 = kExpScale * inv_s2;
+
+  int rc = launch_descriptor_mean(natoms, ntrain, xyz_train, xeq, center, st);
+  if (rc) return rc;
+  {
+    int blocks = (int)((ntrain + 255) / 256);
+    prep_rows_kernel<<<blocks, 256, 0, st>>>(natoms, ntrain, xyz_train, xeq, center, w.XS, c1, Xc, bias);
+    KREG_LAUNCH_CHECK();
+  }
+  if (ntrval > 0 && row_begin < ntrval) {
+    ValuesArgs a;
+    a.XA = a.XB = Xc;
+    a.biasA = a.biasB = bias;
+    a.na = a.nb = ntrain;
+    a.XS = w.XS;
+    a.nchunks = w.nchunks;
+    a.c1 = c1;
+    a.lambda = lambdav;
+    a.symmetric = 1;
+    const bool whole = row_begin == 0 && row_end >= ntrval;
+    a.all_cols = (fill == KREG_FILL_FULL && !whole) ? 1 : 0;
+    a.mirror = (fill == KREG_FILL_FULL && whole) ? 1 : 0;
+    a.row_begin = row_begin;
+    a.row_end = row_end < ntrval ? row_end : ntrval;
+    a.K = K;
+    a.ldk = ldk;
+    rc = launch_values(a, w.KC, st);
+    if (rc) return rc;
+  }
+  if (ntrgr > 0 && row_end > ntrval) {
+    double *E = reinterpret_cast<double *>(ws + w.off_E);
+    {
+      const int64_t total = ntrain * natoms * natoms;
+      int blocks = (int)((total + 127) / 128);
+      jacobian_rows_kernel<<<blocks, 128, 0, st>>>(natoms, ntrain, xyz_train, xeq, E);
+      KREG_LAUNCH_CHECK();
+    }
+    GradArgs g;
+    g.xyz = xyz_train;
+    g.Xc = Xc;
+    g.bias = bias;
+    g.E = E;
+    g.ntr = ntrain;
+    g.nv = ntrval;
+    g.XS = w.XS;
+    g.c1 = c1;
+    g.inv_s2 = inv_s2;
+    g.lambdag = lambdagradxyz;
+    g.fill = fill;
+    g.row_begin = row_begin;
+    g.row_end = row_end;
+    g.K = K;
+    g.ldk = ldk;
+    rc = launch_grad(natoms, g, st);
+    if (rc) return rc;
+  }
+  return KREG_OK;
+}
+
+extern "C" int kreg_kernel_block(int natoms, int64_t na, const double *xyz_a, int64_t nb, const double *xyz_b,
+                                 const double *xeq, double sigma, double *Kout, int64_t ldk, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  if (na < 0 || nb < 0 || !xeq || !(sigma > 0.0) || ldk < nb) return KREG_E_BADARG;
+  if (na == 0 || nb == 0) return KREG_OK;
+  if (!xyz_a || !xyz_b || !Kout || !workspace) return KREG_E_BADARG;
+  // workspace = build_ws(A) followed by build_ws(B); the centre is taken from set B (the training side)
+  const BuildWs wa = build_ws(natoms, na, false), wb = build_ws(natoms, nb, false);
+  if (workspace_bytes < wa.total + wb.total) return KREG_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char *ws = static_cast<char *>(workspace);
+  double *center = reinterpret_cast<double *>(ws + wa.total + wb.off_center);
+  double *XA = reinterpret_cast<double *>(ws + wa.off_X), *bA = reinterpret_cast<double *>(ws + wa.off_bias);
+  double *XB = reinterpret_cast<double *>(ws + wa.total + wb.off_X);
+  double *bB = reinterpret_cast<double *>(ws + wa.total + wb.off_bias);
+  const double c1 = kExpScale / (sigma * sigma);
+  int rc = launch_descriptor_mean(natoms, nb, xyz_b, xeq, center, st);
+  if (rc) return rc;
+  prep_rows_kernel<<<(int)((na + 255) / 256), 256, 0, st>>>(natoms, na, xyz_a, xeq, center, wa.XS, c1, XA, bA);
+  KREG_LAUNCH_CHECK();
+  prep_rows_kernel<<<(int)((nb + 255) / 256), 256, 0, st>>>(natoms, nb, xyz_b, xeq, center, wb.XS, c1, XB, bB);
+  KREG_LAUNCH_CHECK();
+  ValuesArgs a;
+  a.XA = XA;
+  a.XB = XB;
+  a.biasA = bA;
+  a.biasB = bB;
+  a.na = na;
+  a.nb = nb;
+  a.XS = wa.XS;
+  a.nchunks = wa.nchunks;
+  a.c1 = c1;
+  a.lambda = 0.0;
+  a.symmetric = 0;
+  a.all_cols = 1;
+  a.mirror = 0;
+  a.row_begin = 0;
+  a.row_end = na;
+  a.K = Kout;
+  a.ldk = ldk;
+  return launch_values(a, wa.KC, st);
+}

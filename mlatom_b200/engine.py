@@ -1,0 +1,252 @@
+"""Device-side KREG operations on PyTorch fp64 CUDA tensors.
+
+PyTorch is plumbing here (device memory, streams, pinned host buffers); every number is
+produced by the hand-written sm_100a kernels behind the C ABI in ``include/kreg_b200.h``.
+There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FILL_FULL, FILL_LOWER, PREDICT_ENERGY, PREDICT_GRADIENT, KregError, call
+
+F64 = torch.float64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dev(t, device=None) -> torch.Tensor:
+    """fp64, contiguous, on a CUDA device (host arrays are copied once)."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64))
+    if t.dtype != F64:
+        t = t.to(F64)
+    if not t.is_cuda:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def device_check() -> None:
+    call("kreg_device_check")
+
+
+def measure_fp64_peak(kind: str = "dmma", reps: int = 5, ms_target: float = 20.0) -> float:
+    """TFLOP/s of the FP64 pipe through DFMA or DMMA (roofline denominator of the prediction kernel)."""
+    out = ctypes.c_double(0.0)
+    call("kreg_measure_fp64_peak", 0 if kind == "dfma" else 1, reps, float(ms_target), ctypes.byref(out))
+    return out.value
+
+
+def xeq(req) -> torch.Tensor:
+    """Equilibrium pair distances (KREG.f90:223-239). req (Nat,3) -> (D,)."""
+    req = _dev(req)
+    nat = req.shape[0]
+    out = torch.empty(nat * (nat - 1) // 2, dtype=F64, device=req.device)
+    call("kreg_xeq", nat, _ptr(req), _ptr(out), _stream())
+    return out
+
+
+def descriptors(xyz, xeq_: torch.Tensor) -> torch.Tensor:
+    """RE descriptors (KREG.f90:241-271). xyz (N,Nat,3) -> (N,D); bit-identical to the reference."""
+    xyz = _dev(xyz, xeq_.device)
+    n, nat, _ = xyz.shape
+    out = torch.empty((n, nat * (nat - 1) // 2), dtype=F64, device=xyz.device)
+    call("kreg_descriptors", nat, n, _ptr(xyz), _ptr(xeq_), _ptr(out), _stream())
+    return out
+
+
+def build_kernel_matrix(
+    xyz: torch.Tensor,
+    xeq_: torch.Tensor,
+    sigma: float,
+    lambdav: float,
+    lambdagradxyz: float,
+    use_values: bool = True,
+    use_gradients: bool = False,
+    fill: int = FILL_LOWER,
+    rows: Optional[Tuple[int, int]] = None,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """K + diag(lambda) assembled on the device (KREG.f90:293-346 + :616-622).
+
+    Returns the (M, M) row-major matrix; with ``fill=FILL_LOWER`` only j <= i is defined.
+    ``rows=(r0, r1)`` restricts the assembly to a row slab of ``out`` (multi-GPU sharding).
+    """
+    xyz = _dev(xyz, xeq_.device)
+    ntr, nat, _ = xyz.shape
+    ntrval = ntr if use_values else 0
+    ntrgr = 3 * nat * ntr if use_gradients else 0
+    m = ntrval + ntrgr
+    if out is None:
+        out = torch.empty((m, m), dtype=F64, device=xyz.device)
+    assert out.is_cuda and out.dtype == F64 and out.shape[0] == m and out.stride(1) == 1
+    r0, r1 = (0, m) if rows is None else rows
+    ws_bytes = _lib.load().kreg_build_workspace_bytes(nat, ntr, ntrgr)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+    call(
+        "kreg_build_kernel_matrix", nat, ntr, ntrval, ntrgr, _ptr(xyz), _ptr(xeq_), float(sigma), float(lambdav),
+        float(lambdagradxyz), r0, r1, fill, _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream(),
+    )
+    return out
+
+
+def kernel_block(xyz_a: torch.Tensor, xyz_b: torch.Tensor, xeq_: torch.Tensor, sigma: float) -> torch.Tensor:
+    """Rectangular value-value kernel block k(X_a[i], X_b[j]) (A_KRR_kernel.f90:190-223)."""
+    xyz_a, xyz_b = _dev(xyz_a, xeq_.device), _dev(xyz_b, xeq_.device)
+    na, nat, _ = xyz_a.shape
+    nb = xyz_b.shape[0]
+    out = torch.empty((na, nb), dtype=F64, device=xyz_a.device)
+    lib = _lib.load()
+    ws_bytes = lib.kreg_build_workspace_bytes(nat, na, 0) + lib.kreg_build_workspace_bytes(nat, nb, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz_a.device)
+    call("kreg_kernel_block", nat, na, _ptr(xyz_a), nb, _ptr(xyz_b), _ptr(xeq_), float(sigma), _ptr(out),
+         out.stride(0), _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def solve(k: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """alpha = (K)^-1 y by in-place Cholesky (cuSOLVER potrf/potrs; mathUtils.f90:8-104).
+
+    ``k`` (row-major, lower triangle valid, lambda already on the diagonal) is DESTROYED;
+    returns alpha.  Raises KregError(code > 0) if K is not positive definite."""
+    m = k.shape[0]
+    alpha = y.detach().clone().to(F64).contiguous()
+    dbytes, hbytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    call("kreg_solve_workspace_bytes", m, ctypes.byref(dbytes), ctypes.byref(hbytes))
+    dws = torch.empty(max(dbytes.value, 16), dtype=torch.uint8, device=k.device)
+    hws = torch.empty(max(hbytes.value, 16), dtype=torch.uint8).pin_memory()
+    call("kreg_solve", m, _ptr(k), k.stride(0), _ptr(alpha), _ptr(dws), dbytes.value, hws.data_ptr(), hbytes.value,
+         _stream())
+    return alpha
+
+
+def precompute_v(xyz_tr: torch.Tensor, xeq_: torch.Tensor, alpha_grad: torch.Tensor) -> torch.Tensor:
+    """v_j = J_j alpha_grad,j. alpha_grad (Ntr, Nat, 3) -> (Ntr, D)."""
+    ntr, nat, _ = xyz_tr.shape
+    out = torch.empty((ntr, nat * (nat - 1) // 2), dtype=F64, device=xyz_tr.device)
+    call("kreg_precompute_v", nat, ntr, _ptr(xyz_tr), _ptr(xeq_), _ptr(alpha_grad.contiguous()), _ptr(out), _stream())
+    return out
+
+
+@dataclass
+class PackedModel:
+    """A trained KREG model resident in HBM in the fragment order the prediction kernel streams."""
+
+    natoms: int
+    ntrain: int
+    sigma: float
+    prior: float
+    has_gradient_terms: bool
+    xeq: torch.Tensor      # (D,)
+    center: torch.Tensor   # (D,)
+    packed: torch.Tensor   # uint8 blob
+
+    @property
+    def device(self):
+        return self.packed.device
+
+    @classmethod
+    def from_training_set(cls, xyz_tr, xeq_, alpha, sigma: float, prior: float, ntrval: int, ntrgr: int, device=None):
+        """alpha: (NtrVal + NtrGrXYZ,) in the reference order [values ; (point, atom, xyz)]."""
+        xeq_ = _dev(xeq_, device)
+        xyz_tr = _dev(xyz_tr, xeq_.device)
+        alpha = _dev(alpha, xeq_.device).reshape(-1)
+        ntr, nat, _ = xyz_tr.shape
+        assert alpha.numel() == ntrval + ntrgr
+        alpha_v = alpha[:ntrval].contiguous() if ntrval else None
+        v = None
+        if ntrgr:
+            v = precompute_v(xyz_tr, xeq_, alpha[ntrval:].reshape(ntr, nat, 3))
+        nbytes = _lib.load().kreg_packed_model_bytes(nat, ntr, 1 if v is not None else 0)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=xeq_.device)
+        center = torch.empty_like(xeq_)
+        call("kreg_pack_model", nat, ntr, _ptr(xyz_tr), _ptr(xeq_), _ptr(alpha_v), _ptr(v), float(sigma),
+             _ptr(center), _ptr(packed), nbytes, _stream())
+        return cls(nat, ntr, float(sigma), float(prior), v is not None, xeq_, center, packed)
+
+    def predict(self, xyz: torch.Tensor, energy: bool = True, gradient: bool = True, out_e=None, out_g=None):
+        """xyz (N, Nat, 3) cuda fp64 -> (E (N,) or None, dE/dxyz (N, Nat, 3) or None)."""
+        assert xyz.is_cuda and xyz.dtype == F64 and xyz.is_contiguous()
+        n = xyz.shape[0]
+        assert xyz.shape[1] == self.natoms
+        e = (out_e if out_e is not None else torch.empty(n, dtype=F64, device=xyz.device)) if energy else None
+        g = (out_g if out_g is not None else torch.empty((n, self.natoms, 3), dtype=F64, device=xyz.device)) if gradient else None
+        flags = (PREDICT_ENERGY if energy else 0) | (PREDICT_GRADIENT if gradient else 0)
+        call("kreg_predict", self.natoms, self.ntrain, _ptr(self.packed), _ptr(self.center), _ptr(self.xeq),
+             self.sigma, self.prior, 1 if self.has_gradient_terms else 0, n, _ptr(xyz), flags, _ptr(e), _ptr(g),
+             _stream())
+        return e, g
+
+    def predict_host(self, xyz_host: np.ndarray, energy: bool = True, gradient: bool = True, chunk: int = 65536):
+        """Host-buffer entry point: numpy (N, Nat, 3) in, numpy out.  Streams chunks through pinned
+        staging buffers with H2D copy / kernel / D2H copy overlapped on three streams."""
+        return HostPredictor(self, chunk).run(xyz_host, energy, gradient)
+
+
+class HostPredictor:
+    """Double-buffered host <-> device pipeline around PackedModel.predict."""
+
+    def __init__(self, model: PackedModel, chunk: int = 65536, nbuf: int = 3):
+        self.model, self.chunk, self.nbuf = model, int(chunk), nbuf
+        dev, nat = model.device, model.natoms
+        self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.d_xyz = [torch.empty((chunk, nat, 3), dtype=F64, device=dev) for _ in range(nbuf)]
+        self.d_e = [torch.empty(chunk, dtype=F64, device=dev) for _ in range(nbuf)]
+        self.d_g = [torch.empty((chunk, nat, 3), dtype=F64, device=dev) for _ in range(nbuf)]
+        self.ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+        self.ev_k = [torch.cuda.Event() for _ in range(nbuf)]
+        self.ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+
+    def run(self, xyz_host, energy=True, gradient=True, out_e=None, out_g=None):
+        m = self.model
+        xyz_t = xyz_host if torch.is_tensor(xyz_host) else torch.from_numpy(np.ascontiguousarray(xyz_host, dtype=np.float64))
+        n = xyz_t.shape[0]
+        if out_e is None and energy:
+            out_e = torch.empty(n, dtype=F64).pin_memory()
+        if out_g is None and gradient:
+            out_g = torch.empty((n, m.natoms, 3), dtype=F64).pin_memory()
+        with torch.cuda.device(m.device):
+            start = torch.cuda.current_stream()
+            for s in (self.s_in, self.s_k, self.s_out):
+                s.wait_stream(start)
+            for ci, lo in enumerate(range(0, n, self.chunk)):
+                hi = min(n, lo + self.chunk)
+                b = ci % self.nbuf
+                with torch.cuda.stream(self.s_in):
+                    if ci >= self.nbuf:
+                        self.s_in.wait_event(self.ev_k[b])  # kernel that read this input buffer is done
+                    self.d_xyz[b][: hi - lo].copy_(xyz_t[lo:hi], non_blocking=True)
+                    self.ev_in[b].record()
+                with torch.cuda.stream(self.s_k):
+                    self.s_k.wait_event(self.ev_in[b])
+                    if ci >= self.nbuf:
+                        self.s_k.wait_event(self.ev_out[b])  # previous results left this output buffer
+                    m.predict(self.d_xyz[b][: hi - lo], energy, gradient,
+                              out_e=self.d_e[b][: hi - lo] if energy else None,
+                              out_g=self.d_g[b][: hi - lo] if gradient else None)
+                    self.ev_k[b].record()
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(self.ev_k[b])
+                    if energy:
+                        out_e[lo:hi].copy_(self.d_e[b][: hi - lo], non_blocking=True)
+                    if gradient:
+                        out_g[lo:hi].copy_(self.d_g[b][: hi - lo], non_blocking=True)
+                    self.ev_out[b].record()
+            start.wait_stream(self.s_out)
+            start.wait_stream(self.s_k)
+            start.wait_stream(self.s_in)
+        return out_e, out_g

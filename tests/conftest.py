@@ -1,0 +1,43 @@
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    for k in ("natoms", "ntrain", "ntest", "ntrval", "ntrgr"):
+        d[k] = int(d[k])
+    for k in ("sigma", "lambdav", "lambdagradxyz", "prior"):
+        d[k] = float(d[k])
+    return d
+
+
+@pytest.fixture(params=golden_names())
+def golden(request):
+    return load_golden(request.param)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import kreg_oracle
+
+    kreg_oracle.load()
+    return kreg_oracle

@@ -1,0 +1,82 @@
+"""CPU: the C oracle (oracle/kreg_oracle.c) against the golden vectors produced by the reference's
+own compiled library (tools/make_golden.py), and against that library itself when oracle/_ref is
+present.  This is what pins the oracle (task rule 3)."""
+import numpy as np
+import pytest
+
+
+def test_index_map_and_descriptors_bit_exact(golden, oracle):
+    nat = golden["natoms"]
+    assert np.array_equal(oracle.ac2d(nat), golden["ac2d"])
+    xeq = oracle.xeq(golden["eq"])
+    assert np.array_equal(xeq, golden["xeq"])
+    assert np.array_equal(oracle.descriptors(golden["xyz_train"], xeq), golden["X_train"])
+    assert np.array_equal(oracle.descriptors(golden["xyz_test"], xeq), golden["X_test"])
+
+
+def test_kernel_matrix_literal_bit_exact(golden, oracle):
+    k = oracle.kernel_matrix(golden["xyz_train"], golden["X_train"], golden["sigma"], golden["ntrval"], golden["ntrgr"])
+    assert np.array_equal(k, golden["K"])
+    assert np.array_equal(k, k.T)
+    if golden["ntrval"]:
+        assert np.all(np.diag(k)[: golden["ntrval"]] == 1.0)
+
+
+def test_kernel_matrix_factored(golden, oracle):
+    k = oracle.kernel_matrix(golden["xyz_train"], golden["X_train"], golden["sigma"], golden["ntrval"], golden["ntrgr"], factored=True)
+    scale = np.abs(golden["K"]).max()
+    assert np.abs(k - golden["K"]).max() <= 1e-14 * scale
+
+
+def test_solve_residual(golden, oracle):
+    g = golden
+    alpha = oracle.solve(g["K"], g["ytrain"], g["ntrval"], g["ntrgr"], g["lambdav"], g["lambdagradxyz"])
+    a = g["K"].copy()
+    a[np.diag_indices_from(a)] += np.r_[np.full(g["ntrval"], g["lambdav"]), np.full(g["ntrgr"], g["lambdagradxyz"])]
+    res = np.linalg.norm(a @ alpha - g["ytrain"]) / np.linalg.norm(g["ytrain"])
+    assert res < 1e-9
+    # same LAPACK (OpenBLAS) as the fixture generator: alpha reproduces to rounding
+    assert np.abs(alpha - g["alpha"]).max() <= 1e-9 * np.abs(g["alpha"]).max()
+
+
+def test_predict_literal_bit_exact(golden, oracle):
+    g = golden
+    e, gr = oracle.predict_kregf90(g["xyz_train"], g["X_train"], g["alpha"], g["sigma"], g["ntrval"], g["ntrgr"], g["xyz_test"], g["X_test"])
+    assert np.array_equal(e, g["E_test"])
+    assert np.array_equal(gr, g["G_test"])
+
+
+def test_predict_mlatomf_and_factored(golden, oracle):
+    g = golden
+    nv = g["ntrval"]
+    e, gr = oracle.predict_mlatomf(g["xyz_train"], g["X_train"], g["alpha"], g["sigma"], g["prior"], nv, g["ntrgr"], g["xyz_test"], g["X_test"])
+    av = g["alpha"][:nv] if nv else None
+    v = oracle.precompute_v(g["xyz_train"], g["X_train"], g["alpha"][nv:]) if g["ntrgr"] else None
+    ef, gf, sc = oracle.predict_factored(g["X_train"], av, v, g["sigma"], g["prior"], g["xyz_test"], g["X_test"], want_scale=True)
+    ref_e = g["prior"] + g["E_test"]
+    for ee, gg in ((e, gr), (ef, gf)):
+        assert np.all(np.abs(ee - ref_e) <= 1e-13 * np.maximum(sc, np.abs(ref_e)))
+        assert np.abs(gg - g["G_test"]).max() <= 1e-11 * max(1.0, np.abs(g["G_test"]).max())
+
+
+def test_oracle_against_live_reference(oracle):
+    from oracle import ref_kreg
+
+    if not ref_kreg.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from mlatom_b200 import synthetic as S
+
+    nat = 7
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, 21, 11), S.geometries(eq, 9, 12)
+    xeq = ref_kreg.get_xeq(eq)
+    assert np.array_equal(xeq, oracle.xeq(eq))
+    X, Xte = ref_kreg.calc_re_descriptors(xtr, xeq), ref_kreg.calc_re_descriptors(xte, xeq)
+    assert np.array_equal(X, oracle.descriptors(xtr, xeq))
+    for nv, ng in ((21, 0), (21, 21 * 21), (0, 21 * 21)):
+        k = ref_kreg.calc_kernel_matrix(xtr, X, 1.4, nv, ng)
+        assert np.array_equal(k, oracle.kernel_matrix(xtr, X, 1.4, nv, ng))
+        alpha = np.random.default_rng(5).standard_normal(nv + ng)
+        e, g = ref_kreg.predict(xtr, X, xte, Xte, alpha, 1.4, nv, ng)
+        eo, go = oracle.predict_kregf90(xtr, X, alpha, 1.4, nv, ng, xte, Xte)
+        assert np.array_equal(e, eo) and np.array_equal(g, go)
