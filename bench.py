@@ -1,0 +1,348 @@
+#!/usr/bin/env python3
+"""bench.py -- KREG E+F prediction throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] -- KREG energies + gradients, 9-atom
+ethanol-shaped synthetic geometries, Ntrain = 10 000 (values-trained, alpha solved on the GPU
+before the timed region), Ntest = 1 000 000 geometries PER GPU (weak scaling: test batches are
+independent).  One "step" = one pass of the fused E + dE/dxyz prediction kernel over
+the rank's 1M-geometry batch.  Inputs + outputs of a step are 440 MB per GPU (> 126 MB L2), so no
+explicit L2 flush is needed between timed iterations.
+
+JSON keys beyond the base contract:
+  roofline     dominant kernel (predict_kernel) against the FP64 tensor pipe (DMMA) peak measured
+               live by kreg_measure_fp64_peak() -- MEASURED_PEAKS.json has no FP64 entry
+  kbuild       K-matrix assembly GB/s (values block, Ntrain=10k) and its two ceilings; potrf timed apart
+  cpu_baseline the oracle's port of MLatomF's prediction path on the host cores (bounded sample)
+  e2e          same metric through PackedModel.predict_host: pinned host xyz in, host E/G out, copies
+               inside the timed region
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NAT, NTRAIN, NTEST, SIGMA, LAMBDA = 9, 10000, 1000000, 1.0, 1e-6
+D = NAT * (NAT - 1) // 2
+METRIC = "KREG E+F predictions/s (9 atoms, Ntrain=10k, Ntest=1M per GPU)"
+UNIT = "geometries/s"
+WORKLOAD = "cfg2: KREG energies+forces prediction, 9 atoms, Ntrain=10000, Ntest=1000000 per GPU"
+# algorithmic work: E + dE/dxyz, values-trained
+FLOP_PER_STEP = float(NTEST) * NTRAIN * (5 * D + 4) + float(NTEST) * 30 * D
+
+
+def training_set():
+    from mlatom_b200 import synthetic as S
+
+    eq = S.equilibrium(NAT)
+    xyz = S.geometries(eq, NTRAIN, seed=1)
+    e, _ = S.pair_potential(xyz, eq)
+    return eq, xyz, e
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(eq, xyz_tr, alpha, prior, seconds=12.0, threads=None):
+    """The oracle's port of MLatomF's prediction path (A_KRR.f90:985-1029, A_KRR_kernel.f90:225-245,
+    :327-352) on the host cores, on a bounded sample of the same workload."""
+    from mlatom_b200 import synthetic as S
+    from oracle import kreg_oracle as O
+
+    threads = threads or os.cpu_count() or 1
+    O.set_threads(threads)
+    xeq = O.xeq(eq)
+    x_tr = O.descriptors(xyz_tr, xeq)
+
+    def run(n):
+        xte = S.geometries(eq, n, seed=2)
+        t0 = time.perf_counter()
+        x_te = O.descriptors(xte, xeq)  # descriptor build is part of the path
+        O.predict_mlatomf(xyz_tr, x_tr, alpha, SIGMA, prior, NTRAIN, 0, xte, x_te, True, True)
+        return time.perf_counter() - t0
+
+    n0 = 4 * threads
+    t = run(n0)
+    n = int(max(n0, min(NTEST, n0 * seconds / max(t, 1e-6))))
+    n = max(threads, n // threads * threads)
+    t = run(n)
+    return {"value": n / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} of {NTEST} test geometries, full Ntrain={NTRAIN}, {t:.1f} s wall"}, n, t
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host CPU (MLatomF itself cannot be built here:
+    no Fortran compiler, binary absent from the checkout)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import kreg_oracle as O
+
+    eq, xyz_tr, e_tr = training_set()
+    prior = float(e_tr.mean())
+    alpha = np.random.default_rng(0).standard_normal(NTRAIN) * 1e-3  # throughput does not depend on alpha
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    from mlatom_b200 import synthetic as S
+
+    _, n, _ = cpu_baseline(eq, xyz_tr, alpha, prior, seconds=per_step, threads=threads)  # calibrates the sample
+    xeq = O.xeq(eq)
+    x_tr = O.descriptors(xyz_tr, xeq)
+    xte = S.geometries(eq, n, seed=2)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        x_te = O.descriptors(xte, xeq)
+        O.predict_mlatomf(xyz_tr, x_tr, alpha, SIGMA, prior, NTRAIN, 0, xte, x_te, True, True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * len(times) / total
+    sample = f"{n} of {NTEST} test geometries per step, full Ntrain={NTRAIN}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "natoms": NAT, "ntrain": NTRAIN, "ntest_per_gpu": NTEST, "sigma": SIGMA,
+                   "note": "CPU only: MLatomF's optimised prediction loop restated in C/OpenMP (oracle/kreg_oracle.c), "
+                           "all host threads; geometries/s is independent of the sample size"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mlatom_b200 import engine, synthetic as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    engine.device_check()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    to_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+    # ---- model: assemble K and solve on rank 0's GPU, broadcast alpha (the only collective) ----
+    eq, xyz_tr, e_tr = training_set()
+    prior = float(e_tr.mean())
+    xeq = engine.xeq(to_dev(eq))
+    d_xyz_tr = to_dev(xyz_tr)
+    alpha = torch.empty(NTRAIN, dtype=torch.float64, device=dev)
+    extra = {}
+    if rank == 0:
+        k = torch.empty((NTRAIN, NTRAIN), dtype=torch.float64, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        kb = []
+        for it in range(6):
+            torch.cuda.synchronize()
+            ev[0].record()
+            engine.build_kernel_matrix(d_xyz_tr, xeq, SIGMA, LAMBDA, LAMBDA, out=k)
+            ev[1].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                kb.append(ev[0].elapsed_time(ev[1]))
+        tri_bytes = 4.0 * NTRAIN * (NTRAIN + 1)
+        kb_ms = float(np.mean(kb))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        alpha.copy_(engine.solve(k, to_dev(e_tr - prior)))
+        torch.cuda.synchronize()
+        extra["solve_ms"] = 1e3 * (time.perf_counter() - t0)
+        del k
+        extra["kbuild"] = {"ms": kb_ms, "bytes": tri_bytes, "layout": "lower triangle, 4*M*(M+1) bytes",
+                           "gb_per_s": tri_bytes / kb_ms * 1e-6,
+                           "flop": NTRAIN * (NTRAIN + 1) / 2 * (3 * D + 3)}
+    if world > 1:
+        dist.broadcast(alpha, src=0)
+    model = engine.PackedModel.from_training_set(d_xyz_tr, xeq, alpha, SIGMA, prior, NTRAIN, 0)
+
+    # ---- FP64 pipe peak, measured live (roofline denominator) ----
+    peak_dmma = engine.measure_fp64_peak("dmma", reps=5, ms_target=30.0)
+    peak_dfma = engine.measure_fp64_peak("dfma", reps=3, ms_target=30.0)
+
+    # ---- this rank's test batch, resident in HBM ----
+    xte_host = torch.from_numpy(S.geometries(eq, NTEST, seed=2 + rank)).pin_memory()
+    d_xte = xte_host.to(dev, non_blocking=True)
+    d_e = torch.empty(NTEST, dtype=torch.float64, device=dev)
+    d_g = torch.empty((NTEST, NAT, 3), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        model.predict(d_xte, True, True, out_e=d_e, out_g=d_g)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * NTEST * args.steps / (elapsed_ms * 1e-3)
+    kernel_ms = elapsed_ms / args.steps  # one kernel launch per step, back to back on one stream
+
+    # ---- end to end through the host-buffer API (copies inside the timed region) ----
+    host = engine.HostPredictor(model, chunk=65536)
+    out_e = torch.empty(NTEST, dtype=torch.float64).pin_memory()
+    out_g = torch.empty((NTEST, NAT, 3), dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        host.run(xte_host, True, True, out_e, out_g)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        host.run(xte_host, True, True, out_e, out_g)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
+    e2e_value = world * NTEST * e2e_steps / (e2e_ms * 1e-3)
+    checksum = float(out_e[:1000].sum())  # the device->host read of the step's result
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    achieved = FLOP_PER_STEP / (kernel_ms * 1e-3) * 1e-12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "natoms": NAT, "descriptor_size": D, "ntrain": NTRAIN, "ntest_per_gpu": NTEST,
+                   "sigma": SIGMA, "lambda": LAMBDA, "prior": "mean", "model": "values-trained, alpha solved by cuSOLVER potrf on rank 0",
+                   "parallelism": f"test batches sharded over {world} GPU(s), alpha broadcast once",
+                   "l2": "inputs+outputs 440 MB per step per GPU exceed the 126 MB L2; no flush needed"},
+        "clocks": clocks,
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "tensor", "pipe": "FP64 tensor core (DMMA.8x8x4); shares the FP64 pipe with DFMA",
+                     "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
+                     "traffic": None,
+                     "peak_source": "measured live by kreg_measure_fp64_peak(DMMA) (MEASURED_PEAKS.json has no FP64 figure)",
+                     "peak_dfma": peak_dfma, "algorithmic_flop_per_launch": FLOP_PER_STEP,
+                     "kernel": "kreg::predict_kernel<9,4,false,false,4,4>", "kernel_ms": kernel_ms},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NTEST * NAT * 3 * 8,
+                "d2h_bytes_per_step": NTEST * 8 + NTEST * NAT * 3 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "PackedModel.predict_host (pinned host xyz -> pinned host E, dE/dxyz; 64k-geometry chunks, 3 streams)",
+                "checksum": checksum},
+    }
+    if "kbuild" in extra:
+        kb = extra["kbuild"]
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        fp64_ms = kb["flop"] / (peak_dmma * 1e12) * 1e3
+        line["kbuild"] = {"metric": "K-matrix build GB/s (values block, Ntrain=10k, lower triangle)", "value": kb["gb_per_s"],
+                          "unit": "GB/s", "ms": kb["ms"], "bytes": kb["bytes"],
+                          "hbm_peak_gbs": hbm_peak if hbm_peak else 6650.0,
+                          "hbm_peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback",
+                          "frac_of_hbm": kb["gb_per_s"] / (hbm_peak if hbm_peak else 6650.0),
+                          "fp64_bound_ms": fp64_ms, "frac_of_fp64_bound": fp64_ms / kb["ms"],
+                          "note": "values-only K at D=36 is FP64-issue-bound, not HBM-bound (SURVEY.md App. D)",
+                          "potrf_potrs_ms_timed_separately": extra.get("solve_ms")}
+    if world == 1 and not args.no_cpu:
+        base, _, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
