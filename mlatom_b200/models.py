@@ -1,0 +1,337 @@
+"""``kreg`` -- drop-in for ``mlatom.models.kreg`` (reference: mlatom/models.py:343-552) running on the
+B200 KREG kernels.
+
+The constructor, ``train`` and ``predict`` signatures, the hyper-parameter objects, the ``.npz`` model
+file and the convention that predictions are written into the molecule objects (gradients, not forces)
+are those of the reference, so ``ml.md``, ``ml.optimize_geometry`` and the active-learning drivers can
+use this class in place of ``ml.models.kreg``.  ``ml_program`` is accepted for compatibility;
+'KREG_API' (default) and 'B200' select this backend, 'MLatomF' is refused (the Fortran program is not
+part of this package)."""
+from __future__ import annotations
+
+import json
+import os
+import uuid
+from typing import Any, Dict, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import data as _data
+from . import engine
+from ._lib import FILL_LOWER, KregError
+from .hyperparameters import hyperparameter, hyperparameters
+from .kreg_api import KREG_API, _as_database
+
+
+def rmse(a, b) -> float:
+    a, b = np.asarray(a, dtype=np.float64).reshape(-1), np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.sqrt(np.mean((a - b) ** 2)))
+
+
+def optimize_grid(func, grid):
+    """Minimum of ``func`` over the Cartesian product of ``grid`` visited in lexicographic order with the
+    first hyper-parameter outermost; ties keep the earliest point (same visiting order and strict '<'
+    as the reference's recursive optimize_grid, mlatom/model_cls.py:819-854)."""
+    best, best_params = None, None
+
+    def rec(prefix, rest):
+        nonlocal best, best_params
+        if not rest:
+            val = func(list(prefix))
+            if best is None or val < best:
+                best, best_params = val, list(prefix)
+            return
+        for p in rest[0]:
+            rec(prefix + [p], rest[1:])
+
+    rec([], [list(g) for g in grid])
+    return best_params, best
+
+
+class kreg:
+    """KREG model object (Gaussian kernel on the RE descriptor)."""
+
+    hyperparameters = hyperparameters({
+        "lambda": hyperparameter(value=2 ** -35, minval=2 ** -35, maxval=1.0, optimization_space="log", name="lambda"),
+        "sigma": hyperparameter(value=1.0, minval=2 ** -5, maxval=2 ** 9, optimization_space="log", name="sigma"),
+    })
+    nthreads = 0
+
+    def __init__(self, model_file: Optional[str] = None, ml_program: str = "KREG_API", equilibrium_molecule=None,
+                 prior: float = 0, nthreads: Optional[int] = None,
+                 hyperparameters: Union[Dict[str, Any], "hyperparameters"] = {}, device=None):
+        self.model_file = model_file
+        self.equilibrium_molecule = equilibrium_molecule
+        self.ml_program = ml_program
+        self.device = device
+        self.prior = prior
+        if ml_program.casefold() not in ("kreg_api", "b200"):
+            raise ValueError(f"ml_program={ml_program!r} is not available in mlatom_b200 (use 'KREG_API')")
+        if self.model_file is not None:
+            if self.model_file[-4:] != ".npz":
+                self.model_file += ".npz"
+            if os.path.exists(self.model_file):
+                self.kreg_api = KREG_API(device)
+                self.kreg_api.load_model(self.model_file)
+        self.hyperparameters = type(self).hyperparameters.copy()
+        self.hyperparameters.update(hyperparameters)
+        self.nthreads = nthreads
+
+    # -- small compat surface (mlatom/model_cls.py:20-38, 392-427) --------------------------------
+    def set_num_threads(self, nthreads=0):
+        if nthreads:
+            self.nthreads = nthreads
+
+    def reset(self):
+        if self.model_file and os.path.exists(self.model_file):
+            os.remove(self.model_file)
+
+    def generate_model_dict(self):
+        return {"type": "ml_model", "ml_model_type": "mlatom_b200.models.kreg",
+                "kwargs": {"model_file": os.path.abspath(self.model_file) if self.model_file else None,
+                           "ml_program": self.ml_program}, "nthreads": self.nthreads}
+
+    def dump(self, filename=None, format="json"):
+        model_dict = self.generate_model_dict()
+        if format == "dict":
+            return model_dict
+        with open(filename, "w") as f:
+            json.dump(model_dict, f, indent=4)
+
+    # -- equilibrium geometry (mlatom/models.py:439-457) ---------------------------------------------
+    def get_equilibrium_molecule(self, molecular_database=None):
+        first = molecular_database.molecules[0].__dict__
+        for name in ("energy", "y"):
+            if name in first:
+                values = molecular_database.get_properties(property_name=name)
+                return molecular_database.molecules[int(np.argmin(values))]
+        raise ValueError("equilibrium molecule is not provided and no energies are found in molecular database")
+
+    def get_equilibrium_distances(self, molecular_database=None):
+        if self.equilibrium_molecule is None:
+            self.equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=molecular_database)
+        x = np.asarray(self.equilibrium_molecule.xyz_coordinates)
+        dm = np.linalg.norm(x[:, None] - x[None], axis=-1)
+        return dm[np.triu_indices(len(x), 1)]
+
+    # -- train / predict (mlatom/models.py:459-552) ------------------------------------------------------
+    def _lambdas_and_prior(self, prior):
+        lam = self.hyperparameters["lambda"].value
+        lam_g = self.hyperparameters["lambdaGradXYZ"].value if "lambdaGradXYZ" in self.hyperparameters.keys() else lam
+        if "prior" in self.hyperparameters.keys():
+            prior = self.hyperparameters["prior"].value
+        return lam, lam_g, prior
+
+    def train(self, molecular_database=None, property_to_learn=None, xyz_derivative_property_to_learn=None,
+              save_model=True, invert_matrix=False, matrix_decomposition=None, prior=None,
+              hyperparameters: Union[Dict[str, Any], "hyperparameters"] = {}):
+        self.hyperparameters.update(hyperparameters)
+        if save_model:
+            if self.model_file is None:
+                self.model_file = f"kreg_{uuid.uuid4()}.npz"
+            elif self.model_file[-4:] != ".npz":
+                self.model_file += ".npz"
+        self.kreg_api = KREG_API(self.device)
+        self.kreg_api.nthreads = self.nthreads
+        if self.equilibrium_molecule is None:
+            self.equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=molecular_database)
+        lam, lam_g, prior = self._lambdas_and_prior(prior)
+        self.kreg_api.train(self.hyperparameters["sigma"].value, lam, lam_g, molecular_database,
+                            self.equilibrium_molecule, property_to_learn=property_to_learn,
+                            xyz_derivative_property_to_learn=xyz_derivative_property_to_learn, prior=prior)
+        if save_model:
+            self.kreg_api.save_model(self.model_file)
+
+    def predict(self, molecular_database=None, molecule=None, calculate_energy=False, calculate_energy_gradients=False,
+                calculate_hessian=False, property_to_predict=None, xyz_derivative_property_to_predict=None,
+                hessian_to_predict=None):
+        mol_db = _as_database(molecular_database, molecule)
+        # ml_model.predict's naming rule (mlatom/model_cls.py:366-390)
+        if calculate_energy:
+            property_to_predict = "energy"
+        if calculate_energy_gradients:
+            xyz_derivative_property_to_predict = "energy_gradients"
+        if calculate_hessian:
+            hessian_to_predict = "hessian"
+        if "kreg_api" not in self.__dict__:
+            raise RuntimeError("KREG_API model not found")
+        self.kreg_api.nthreads = self.nthreads
+        self.kreg_api.predict(molecular_database=mol_db, property_to_predict=property_to_predict,
+                              xyz_derivative_property_to_predict=xyz_derivative_property_to_predict,
+                              hessian_to_predict=hessian_to_predict)
+
+    def predict_xyz(self, xyz, calculate_energy=True, calculate_energy_gradients=True):
+        """Tensor entry point for large batches: xyz (N,Nat,3) cuda fp64 tensor or numpy -> (E, dE/dxyz).
+        (Python molecule objects cannot carry 10^6-10^7 geometries)"""
+        return self.kreg_api.predict_arrays(xyz, calculate_energy, calculate_energy_gradients)
+
+    # -- validation / hyper-parameter search (mlatom/model_cls.py:450-739) -------------------------------------
+    def holdout_validation(self, subtraining_molecular_database=None, validation_molecular_database=None,
+                           training_kwargs=None, prediction_kwargs=None):
+        self.train(molecular_database=subtraining_molecular_database, **(training_kwargs or {}))
+        self.predict(molecular_database=validation_molecular_database, **(prediction_kwargs or {}))
+
+    @staticmethod
+    def _names(training_kwargs, prediction_kwargs):
+        tk, pk = dict(training_kwargs or {}), dict(prediction_kwargs or {})
+        p_learn, g_learn = tk.get("property_to_learn"), tk.get("xyz_derivative_property_to_learn")
+        if p_learn is None and g_learn is None:
+            p_learn = tk["property_to_learn"] = "y"
+        p_pred, g_pred = pk.get("property_to_predict"), pk.get("xyz_derivative_property_to_predict")
+        if p_pred is None and g_pred is None:
+            if p_learn is not None:
+                p_pred = pk["property_to_predict"] = f"estimated_{p_learn}"
+            if g_learn is not None:
+                g_pred = pk["xyz_derivative_property_to_predict"] = f"estimated_{g_learn}"
+        return tk, pk, p_learn, g_learn, p_pred, g_pred
+
+    def calculate_validation_loss(self, training_kwargs=None, prediction_kwargs=None,
+                                  subtraining_molecular_database=None, validation_molecular_database=None,
+                                  validation_loss_function=None, validation_loss_function_kwargs={}, debug=False,
+                                  **unsupported):
+        """Hold-out validation loss: RMSE, geometric mean over scalar and XYZ-vectorial properties
+        (mlatom/model_cls.py:577-585)."""
+        for k, v in unsupported.items():
+            if v is not None and v is not False:
+                raise NotImplementedError(f"{k} is not supported by mlatom_b200.kreg")
+        tk, pk, p_learn, g_learn, p_pred, g_pred = self._names(training_kwargs, prediction_kwargs)
+        self.holdout_validation(subtraining_molecular_database, validation_molecular_database, tk, pk)
+        vdb = validation_molecular_database
+        total = 1.0
+        if p_learn is not None:
+            total *= rmse(vdb.get_properties(p_pred), vdb.get_properties(p_learn))
+        if g_learn is not None:
+            total *= rmse(vdb.get_xyz_vectorial_properties(g_pred), vdb.get_xyz_vectorial_properties(g_learn))
+        if p_learn is not None and g_learn is not None:
+            total = float(np.sqrt(total))
+        error = total if validation_loss_function is None else validation_loss_function(**validation_loss_function_kwargs)
+        self.reset()
+        if debug:
+            for name in self.hyperparameters.keys():
+                print(f"  Hyperparameter {name} = {self.hyperparameters[name].value}")
+            print(f"    Validation loss: {error}")
+        return error
+
+    def _grid(self, names, grid_size):
+        slices = []
+        for key in names:
+            hp = self.hyperparameters[key]
+            if hp.optimization_space == "linear":
+                slices.append(list(np.linspace(hp.minval, hp.maxval, num=grid_size)))
+            elif hp.optimization_space == "log":
+                slices.append(list(np.logspace(np.log(hp.minval), np.log(hp.maxval), num=grid_size, base=np.exp(1))))
+            else:
+                raise NotImplementedError(hp.optimization_space)
+        return slices
+
+    def optimize_hyperparameters(self, hyperparameters=None, training_kwargs=None, prediction_kwargs=None,
+                                 subtraining_molecular_database=None, validation_molecular_database=None,
+                                 optimization_algorithm=None, optimization_algorithm_kwargs={}, maximum_evaluations=10000,
+                                 validation_loss_function=None, validation_loss_function_kwargs={}, debug=False,
+                                 fused=True, **unsupported):
+        """Minimise the hold-out validation loss over the named hyper-parameters, then retrain with the
+        winners (mlatom/model_cls.py:609-727).  'grid' over 'lambda'/'sigma' takes the fused device path
+        (K assembled once per sigma, re-factorised per lambda, validation kernels stay in HBM); every other
+        case evaluates train+predict per point exactly like the reference."""
+        names = list(hyperparameters)
+        algo = optimization_algorithm.casefold()
+        vkw = dict(training_kwargs=training_kwargs, prediction_kwargs=prediction_kwargs,
+                   subtraining_molecular_database=subtraining_molecular_database,
+                   validation_molecular_database=validation_molecular_database,
+                   validation_loss_function=validation_loss_function,
+                   validation_loss_function_kwargs=validation_loss_function_kwargs, debug=debug, **unsupported)
+
+        def loss_at(values):
+            for name, v in zip(names, values):
+                self.hyperparameters[name].value = v
+            return self.calculate_validation_loss(**vkw)
+
+        saved_name = self.model_file
+        import tempfile
+
+        with tempfile.TemporaryDirectory() as tmp:
+            self.model_file = os.path.join(tmp, os.path.basename(saved_name or "kreg_tmp.npz"))
+            if algo in ("grid", "brute"):
+                slices = self._grid(names, optimization_algorithm_kwargs.get("grid_size", 9))
+                can_fuse = (fused and set(names) <= {"lambda", "sigma"} and validation_loss_function is None
+                            and not any(v for v in unsupported.values()))
+                if can_fuse:
+                    table = self._fused_grid_losses(names, slices, training_kwargs, prediction_kwargs,
+                                                    subtraining_molecular_database, validation_molecular_database)
+                    self.grid_losses = table
+                    params, _ = optimize_grid(lambda p: table[tuple(p)], slices)
+                else:
+                    params, _ = optimize_grid(loss_at, slices)
+            else:
+                import scipy.optimize
+
+                x0 = np.array([self.hyperparameters[k].value for k in names])
+                bounds = np.array([[self.hyperparameters[k].minval, self.hyperparameters[k].maxval] for k in names])
+                res = scipy.optimize.minimize(loss_at, x0, method=optimization_algorithm, bounds=bounds,
+                                              options={"maxiter": maximum_evaluations})
+                params = list(res.x)
+            for name, v in zip(names, params):
+                self.hyperparameters[name].value = v
+            self.model_file = saved_name
+        self.validation_loss = loss_at([self.hyperparameters[k].value for k in names])
+
+    def _fused_grid_losses(self, names, slices, training_kwargs, prediction_kwargs, sub_db, val_db):
+        """All (lambda, sigma) grid losses with K(sigma) built once per sigma."""
+        tk, _, p_learn, g_learn, _, _ = self._names(training_kwargs, prediction_kwargs)
+        api = KREG_API(self.device)
+        dev = api._dev()
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        if self.equilibrium_molecule is None:
+            self.equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=sub_db)
+        xeq = engine.xeq(t(self.equilibrium_molecule.xyz_coordinates))
+        xyz, xyz_val = t(sub_db.xyz_coordinates), t(val_db.xyz_coordinates)
+        ntr, nat = int(xyz.shape[0]), int(xyz.shape[1])
+        _, _, prior = self._lambdas_and_prior(tk.get("prior"))
+        parts, prior_value = [], 0.0
+        if p_learn is not None:
+            y = np.asarray(sub_db.get_properties(p_learn), dtype=np.float64)
+            prior_value = float(np.mean(y)) if isinstance(prior, str) and prior.casefold() == "mean" else float(prior or 0.0)
+            parts.append(y - prior_value)
+        if g_learn is not None:
+            parts.append(np.asarray(sub_db.get_xyz_vectorial_properties(g_learn), dtype=np.float64).reshape(-1))
+        ytrain = t(np.concatenate(parts))
+        nv, ng = (ntr if p_learn is not None else 0), (3 * nat * ntr if g_learn is not None else 0)
+        y_val = np.asarray(val_db.get_properties(p_learn)) if p_learn is not None else None
+        g_val = np.asarray(val_db.get_xyz_vectorial_properties(g_learn)) if g_learn is not None else None
+
+        current = {k: self.hyperparameters[k].value for k in ("lambda", "sigma")}
+        sig_list = slices[names.index("sigma")] if "sigma" in names else [current["sigma"]]
+        lam_list = slices[names.index("lambda")] if "lambda" in names else [current["lambda"]]
+        fixed_lam_g = self.hyperparameters["lambdaGradXYZ"].value if "lambdaGradXYZ" in self.hyperparameters.keys() else None
+        m = nv + ng
+        k0 = torch.empty((m, m), dtype=torch.float64, device=dev)
+        work = torch.empty_like(k0)
+        diag = torch.arange(m, device=dev)
+        table = {}
+        for sigma in sig_list:
+            engine.build_kernel_matrix(xyz, xeq, sigma, 0.0, 0.0, use_values=nv > 0, use_gradients=ng > 0,
+                                       fill=FILL_LOWER, out=k0)
+            for lam in lam_list:
+                lam_g = lam if fixed_lam_g is None else fixed_lam_g
+                work.copy_(k0)
+                work[diag[:nv], diag[:nv]] += lam
+                work[diag[nv:], diag[nv:]] += lam_g
+                try:
+                    alpha = engine.solve(work, ytrain)
+                    model = engine.PackedModel.from_training_set(xyz, xeq, alpha, sigma, prior_value, nv, ng)
+                    e, g = model.predict(xyz_val, p_learn is not None, g_learn is not None)
+                    total = 1.0
+                    if p_learn is not None:
+                        total *= rmse(e.cpu().numpy(), y_val)
+                    if g_learn is not None:
+                        total *= rmse(g.cpu().numpy(), g_val)
+                    if p_learn is not None and g_learn is not None:
+                        total = float(np.sqrt(total))
+                except KregError as err:
+                    if err.code <= 0:
+                        raise
+                    total = float("inf")  # not positive definite at this (lambda, sigma)
+                key = tuple(lam if n == "lambda" else sigma for n in names)
+                table[key] = total
+        return table

@@ -1,0 +1,208 @@
+"""CPU: host-side logic of the drop-in API (Ytrain ordering, prior handling, .npz layout, property
+write-back, grid visiting order) with the device engine replaced by oracle-backed fakes -- and, when the
+reference checkout is present, driven by REAL mlatom.data objects to prove duck-type compatibility."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from mlatom_b200 import data as D, synthetic as S  # noqa: E402
+from mlatom_b200 import kreg_api as KA, models as M  # noqa: E402
+
+
+class FakePacked:
+    def __init__(self, oracle, xyz_tr, xeq, alpha, sigma, prior, nv, ng):
+        self.o, self.sigma, self.prior, self.device = oracle, sigma, prior, torch.device("cpu")
+        self.xeq = xeq.numpy()
+        self.xyz_tr = xyz_tr.numpy()
+        self.X = oracle.descriptors(self.xyz_tr, self.xeq)
+        a = alpha.numpy().reshape(-1)
+        self.av = a[:nv] if nv else None
+        self.v = oracle.precompute_v(self.xyz_tr, self.X, a[nv:]) if ng else None
+
+    def predict(self, xyz, energy=True, gradient=True, **_):
+        x = xyz.numpy()
+        e, g = self.o.predict_factored(self.X, self.av, self.v, self.sigma, self.prior, x, self.o.descriptors(x, self.xeq))
+        return (torch.from_numpy(e) if energy else None), (torch.from_numpy(g) if gradient else None)
+
+    def predict_host(self, xyz, energy=True, gradient=True, **_):
+        return self.predict(torch.from_numpy(np.ascontiguousarray(xyz)), energy, gradient)
+
+
+@pytest.fixture
+def fake_engine(monkeypatch, oracle):
+    eng = KA.engine
+    monkeypatch.setattr(KA.KREG_API, "_dev", lambda self: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(eng, "xeq", lambda req: torch.from_numpy(oracle.xeq(req.numpy())))
+    monkeypatch.setattr(eng, "descriptors", lambda xyz, xeq: torch.from_numpy(oracle.descriptors(xyz.numpy(), xeq.numpy())))
+
+    def build(xyz, xeq, sigma, lv, lg, use_values=True, use_gradients=False, fill=0, rows=None, out=None):
+        x = xyz.numpy()
+        n, nat, _ = x.shape
+        nv, ng = (n if use_values else 0), (3 * nat * n if use_gradients else 0)
+        k = oracle.kernel_matrix(x, oracle.descriptors(x, xeq.numpy()), sigma, nv, ng, factored=True)
+        k[np.diag_indices_from(k)] += np.r_[np.full(nv, lv), np.full(ng, lg)]
+        k = torch.from_numpy(k)
+        if out is not None:
+            out.copy_(k)
+            return out
+        return k
+
+    def solve(k, y):
+        from scipy.linalg import cho_factor, cho_solve
+
+        a = np.tril(k.numpy())
+        a = a + np.tril(a, -1).T
+        return torch.from_numpy(cho_solve(cho_factor(a), y.numpy()))
+
+    monkeypatch.setattr(eng, "build_kernel_matrix", build)
+    monkeypatch.setattr(eng, "solve", solve)
+    monkeypatch.setattr(eng.PackedModel, "from_training_set",
+                        classmethod(lambda cls, xyz, xeq, alpha, sigma, prior, nv, ng, device=None:
+                                    FakePacked(oracle, xyz, xeq, alpha, sigma, prior, nv, ng)))
+    return eng
+
+
+def make_db(mod, nat, n, seed, with_labels=True):
+    eq = S.equilibrium(nat)
+    z = S.atomic_numbers(nat)
+    xyz = S.geometries(eq, n, seed)
+    e, g = S.pair_potential(xyz, eq)
+    db = mod.molecular_database()
+    for i in range(n):
+        mol = mod.molecule()
+        for a in range(nat):
+            mol.atoms.append(mod.atom(atomic_number=int(z[a]), xyz_coordinates=xyz[i, a]))
+        if with_labels:
+            mol.energy = float(e[i])
+            mol.add_xyz_vectorial_property(g[i], "energy_gradients")
+        db.molecules.append(mol)
+    return db, xyz, e, g
+
+
+def reference_mlatom():
+    if not os.path.isdir("/root/reference/mlatom"):
+        return None
+    os.environ["MLATOM_NO_VERSION_CHECK"] = "1"
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    try:
+        import mlatom.data as ref_data
+    except Exception:  # pragma: no cover - reference not importable here
+        return None
+    return ref_data
+
+
+@pytest.mark.parametrize("use_grads", [False, True])
+def test_train_predict_host_logic(fake_engine, oracle, tmp_path, use_grads):
+    nat, ntr, nte = 5, 14, 6
+    db, xyz, e, g = make_db(D, nat, ntr, 1)
+    test_db, xte, _, _ = make_db(D, nat, nte, 2, with_labels=False)
+    model = M.kreg(model_file=str(tmp_path / "m"), hyperparameters={"sigma": 0.9, "lambda": 1e-6})
+    model.train(molecular_database=db, property_to_learn="energy",
+                xyz_derivative_property_to_learn="energy_gradients" if use_grads else None, prior="mean")
+    assert model.model_file.endswith(".npz") and os.path.exists(model.model_file)
+    api = model.kreg_api
+    # equilibrium molecule = lowest energy (models.py:447-457); Ytrain order (kreg_api.py:51-72)
+    ieq = int(np.argmin(e))
+    assert np.array_equal(api.Req, xyz[ieq])
+    expect_y = np.concatenate([e - e.mean()] + ([g.reshape(-1)] if use_grads else []))
+    assert np.allclose(api.Ytrain, expect_y, rtol=0, atol=0)
+    assert api.NtrVal == ntr and api.NtrGrXYZ == (3 * nat * ntr if use_grads else 0)
+    # model-file layout
+    z = np.load(model.model_file)
+    assert set(z.files) == {"sigma", "Natoms", "Xsize", "Ntrain", "NtrVal", "NtrGrXYZ", "lambdav", "lambdagradxyz", "X",
+                            "XYZ", "ac2dArray", "Req", "Xeq", "alpha", "prior"}
+    assert z["alpha"].shape == (1, api.Ksize) and z["X"].shape == (ntr, nat * (nat - 1) // 2)
+    assert z["XYZ"].shape == (ntr, nat, 3) and z["ac2dArray"].dtype == np.int32
+    assert np.array_equal(z["ac2dArray"], oracle.ac2d(nat))
+    # prediction is written into the molecules; gradients (not forces) per atom
+    model.predict(molecular_database=test_db, calculate_energy=True, calculate_energy_gradients=True)
+    xeq = oracle.xeq(xyz[ieq])
+    X, Xte = oracle.descriptors(xyz, xeq), oracle.descriptors(xte, xeq)
+    a = z["alpha"].reshape(-1)
+    v = oracle.precompute_v(xyz, X, a[ntr:]) if use_grads else None
+    e_ref, g_ref = oracle.predict_factored(X, a[:ntr], v, 0.9, float(z["prior"]), xte, Xte)
+    assert np.allclose(test_db.get_properties("energy"), e_ref, rtol=1e-13)
+    assert np.allclose(test_db.get_xyz_vectorial_properties("energy_gradients"), g_ref, atol=1e-12)
+    # a fresh object auto-loads the file (models.py:370-375) and predicts a single molecule
+    again = M.kreg(model_file=model.model_file)
+    mol = test_db.molecules[0].copy()
+    again.predict(molecule=mol, calculate_energy=True, calculate_energy_gradients=True)
+    assert abs(mol.energy - e_ref[0]) <= 1e-12 * abs(e_ref[0])
+    assert np.allclose(mol.get_energy_gradients(), g_ref[0], atol=1e-12)
+    # custom property names
+    again.predict(molecular_database=test_db, property_to_predict="e_ml", xyz_derivative_property_to_predict="g_ml")
+    assert np.allclose(test_db.get_properties("e_ml"), e_ref, rtol=1e-13)
+
+
+def test_real_mlatom_objects_are_accepted(fake_engine, tmp_path):
+    ref_data = reference_mlatom()
+    if ref_data is None:
+        pytest.skip("reference checkout not available")
+    nat, ntr, nte = 5, 10, 4
+    db_ref, xyz, e, g = make_db(ref_data, nat, ntr, 1)
+    db_own, _, _, _ = make_db(D, nat, ntr, 1)
+    t_ref, xte, _, _ = make_db(ref_data, nat, nte, 2, with_labels=False)
+    t_own, _, _, _ = make_db(D, nat, nte, 2, with_labels=False)
+    out = []
+    for db, tdb, name in ((db_ref, t_ref, "ref"), (db_own, t_own, "own")):
+        model = M.kreg(model_file=str(tmp_path / name), hyperparameters={"sigma": 1.1, "lambda": 1e-5})
+        model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients")
+        model.predict(molecular_database=tdb, calculate_energy=True, calculate_energy_gradients=True)
+        out.append((tdb.get_properties("energy"), tdb.get_xyz_vectorial_properties("energy_gradients")))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    # per-atom write-back as the reference does it (kreg_api.py:126-131)
+    assert t_ref.molecules[0].atoms[0].energy_gradients.shape == (3,)
+
+
+def test_hyperparameter_objects():
+    m = M.kreg()
+    assert m.hyperparameters["lambda"].value == 2 ** -35 and m.hyperparameters["sigma"].value == 1.0
+    assert m.hyperparameters["sigma"].minval == 2 ** -5 and m.hyperparameters["sigma"].maxval == 2 ** 9
+    assert m.hyperparameters["lambda"].optimization_space == "log"
+    m.hyperparameters["sigma"] = 3
+    assert m.hyperparameters["sigma"].value == 3.0 and isinstance(m.hyperparameters["sigma"].value, float)
+    assert m.hyperparameters.sigma == 3.0
+    assert M.kreg().hyperparameters["sigma"].value == 1.0  # class default untouched
+    m2 = M.kreg(hyperparameters={"sigma": 2.0, "lambdaGradXYZ": 1e-3})
+    assert m2.hyperparameters["lambdaGradXYZ"].value == 1e-3
+    with pytest.raises(ValueError):
+        M.kreg(ml_program="MLatomF")
+
+
+def test_optimize_grid_visiting_order_and_ties():
+    seen = []
+
+    def f(p):
+        seen.append(tuple(p))
+        return 1.0 if p[1] != 2 else 0.5  # tie between (1,2) and (3,2)
+
+    params, val = M.optimize_grid(f, [[1, 3], [5, 2, 7]])
+    assert seen == [(1, 5), (1, 2), (1, 7), (3, 5), (3, 2), (3, 7)]
+    assert params == [1, 2] and val == 0.5
+
+
+def test_grid_search_fused_equals_pointwise(fake_engine, tmp_path):
+    nat = 5
+    sub, _, _, _ = make_db(D, nat, 12, 1)
+    val, _, _, _ = make_db(D, nat, 7, 3)
+    res = []
+    for fused in (True, False):
+        model = M.kreg(model_file=str(tmp_path / f"g{fused}"))
+        model.hyperparameters["lambda"].minval, model.hyperparameters["lambda"].maxval = 1e-8, 1e-2
+        model.hyperparameters["sigma"].minval, model.hyperparameters["sigma"].maxval = 0.3, 8.0
+        model.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="grid",
+                                       optimization_algorithm_kwargs={"grid_size": 3},
+                                       training_kwargs={"property_to_learn": "energy", "prior": "mean"},
+                                       prediction_kwargs={"property_to_predict": "estimated_energy"},
+                                       subtraining_molecular_database=sub, validation_molecular_database=val, fused=fused)
+        res.append((model.hyperparameters["lambda"].value, model.hyperparameters["sigma"].value, model.validation_loss))
+    assert res[0][:2] == res[1][:2]
+    assert abs(res[0][2] - res[1][2]) <= 1e-9 * res[1][2]

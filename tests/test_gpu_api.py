@@ -1,0 +1,121 @@
+"""GPU: the drop-in Python API (models.kreg / KREG_API) end to end on the device, against the oracle."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from mlatom_b200 import data as D, synthetic as S  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def M():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mlatom_b200 import models
+
+    return models
+
+
+def make_db(nat, n, seed, labels=True):
+    eq = S.equilibrium(nat)
+    xyz = S.geometries(eq, n, seed)
+    e, g = S.pair_potential(xyz, eq)
+    if labels:
+        return D.molecular_database.from_arrays(S.atomic_numbers(nat), xyz, energy=e, energy_gradients=g), xyz, e, g
+    return D.molecular_database.from_arrays(S.atomic_numbers(nat), xyz), xyz, e, g
+
+
+@pytest.mark.parametrize("nat,ntr,use_grads,sigma,lam", [(9, 200, False, 1.0, 1e-6), (9, 30, True, 1.0, 1e-6),
+                                                           (5, 50, True, 0.8, 1e-5), (21, 60, False, 2.0, 1e-6)])
+def test_kreg_train_predict_vs_oracle(M, oracle, tmp_path, nat, ntr, use_grads, sigma, lam):
+    db, xyz, e, g = make_db(nat, ntr, 1)
+    tdb, xte, e_true, g_true = make_db(nat, 64, 2, labels=False)
+    model = M.kreg(model_file=str(tmp_path / "model"), hyperparameters={"sigma": sigma, "lambda": lam})
+    model.train(molecular_database=db, property_to_learn="energy",
+                xyz_derivative_property_to_learn="energy_gradients" if use_grads else None, prior="mean")
+    model.predict(molecular_database=tdb, calculate_energy=True, calculate_energy_gradients=True)
+    e_gpu = tdb.get_properties("energy")
+    g_gpu = tdb.get_xyz_vectorial_properties("energy_gradients")
+    # oracle: same training through the CPU restatement (LAPACK Cholesky), same predictions
+    xeq = oracle.xeq(xyz[int(np.argmin(e))])
+    X, Xte = oracle.descriptors(xyz, xeq), oracle.descriptors(xte, xeq)
+    nv, ng = ntr, (3 * nat * ntr if use_grads else 0)
+    prior = float(e.mean())
+    k = oracle.kernel_matrix(xyz, X, sigma, nv, ng, factored=True)
+    alpha = oracle.solve(k, oracle.ytrain(e, g if use_grads else None, prior), nv, ng, lam, lam)
+    v = oracle.precompute_v(xyz, X, alpha[nv:]) if use_grads else None
+    e_ref, g_ref = oracle.predict_factored(X, alpha[:nv], v, sigma, prior, xte, Xte)
+    # trained-alpha path: two Cholesky libraries differ by cond*eps; state the bound
+    a = k.copy()
+    a[np.diag_indices_from(a)] += lam
+    tol = max(1e-10, 100 * np.linalg.cond(a) * 2.2e-16)
+    assert np.abs(e_gpu - e_ref).max() <= tol * np.abs(e_ref).max()
+    assert np.abs(g_gpu - g_ref).max() <= max(1e-8, tol) * max(1.0, np.abs(g_ref).max())
+    # the model actually learned the potential
+    if nat <= 9:
+        assert np.sqrt(np.mean((e_gpu - e_true) ** 2)) < np.std(e_true)
+    # fixed-alpha protocol through the API: load the file and predict with the oracle's alpha
+    api = model.kreg_api
+    api.alpha = alpha.reshape(1, -1)
+    api._model = None
+    e2, g2 = api.predict_arrays(xte)
+    assert np.abs(e2 - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
+    assert np.abs(g2 - g_ref).max() <= 1e-8
+
+
+def test_model_file_roundtrip_and_tensor_path(M, tmp_path):
+    db, xyz, e, g = make_db(9, 80, 1)
+    model = M.kreg(model_file=str(tmp_path / "rt.npz"), hyperparameters={"sigma": 1.0, "lambda": 1e-6})
+    model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients")
+    xte = S.geometries(S.equilibrium(9), 1000, 5)
+    e1, g1 = model.predict_xyz(torch.from_numpy(xte).cuda())
+    again = M.kreg(model_file=str(tmp_path / "rt.npz"))
+    e2, g2 = again.predict_xyz(torch.from_numpy(xte).cuda())
+    assert torch.equal(e1, e2) and torch.equal(g1, g2)
+    e3, g3 = again.predict_xyz(xte)  # numpy in -> streamed host pipeline -> numpy out
+    assert np.array_equal(e3, e1.cpu().numpy()) and np.array_equal(g3, g1.cpu().numpy())
+    mol = D.molecule.from_arrays(S.atomic_numbers(9), xte[3])
+    again.predict(molecule=mol, calculate_energy=True, calculate_energy_gradients=True)
+    assert mol.energy == e3[3] and np.array_equal(mol.get_energy_gradients(), g3[3])
+    assert mol.atoms[0].energy_gradients.shape == (3,)
+    with pytest.raises(NotImplementedError):
+        again.predict(molecule=mol, calculate_hessian=True)
+
+
+def test_grid_search_fused_equals_pointwise_on_device(M, tmp_path):
+    sub, _, _, _ = make_db(9, 60, 1)
+    val, _, _, _ = make_db(9, 40, 3)
+    res = []
+    for fused in (True, False):
+        model = M.kreg(model_file=str(tmp_path / f"grid{fused}"))
+        model.hyperparameters["lambda"].minval, model.hyperparameters["lambda"].maxval = 1e-9, 1e-2
+        model.hyperparameters["sigma"].minval, model.hyperparameters["sigma"].maxval = 0.25, 16.0
+        model.optimize_hyperparameters(
+            hyperparameters=["lambda", "sigma"], optimization_algorithm="grid",
+            optimization_algorithm_kwargs={"grid_size": 4},
+            training_kwargs={"property_to_learn": "energy", "xyz_derivative_property_to_learn": "energy_gradients"},
+            prediction_kwargs={"property_to_predict": "estimated_energy",
+                               "xyz_derivative_property_to_predict": "estimated_energy_gradients"},
+            subtraining_molecular_database=sub, validation_molecular_database=val, fused=fused)
+        res.append((model.hyperparameters["lambda"].value, model.hyperparameters["sigma"].value, model.validation_loss))
+        # as in the reference the last validation pass ends with reset() (model_cls.py:590): the file is gone,
+        # the trained in-memory backend remains (AL then calls model.kreg_api.save_model, al_utils.py:1105)
+        assert not os.path.exists(model.model_file) and model.kreg_api.alpha is not None
+    assert res[0][:2] == res[1][:2]
+    assert abs(res[0][2] - res[1][2]) <= 1e-8 * res[1][2]
+
+
+def test_indefinite_system_falls_back_instead_of_dying(M, tmp_path):
+    """The reference falls back to Bunch-Kaufman when dpotrf fails (mathUtils.f90:24-26) -- or kills the
+    interpreter on other errors; here: a warning and a pivoted solve."""
+    db, _, _, _ = make_db(5, 30, 1)
+    model = M.kreg(model_file=str(tmp_path / "neg"), hyperparameters={"sigma": 1.0, "lambda": -0.5})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.train(molecular_database=db, property_to_learn="energy")
+    assert any("not positive definite" in str(x.message) for x in w)
+    assert np.isfinite(model.kreg_api.alpha).all()
