@@ -40,7 +40,9 @@ __global__ void __launch_bounds__(256) descriptors_kernel(int nat, int64_t npoin
   }
 }
 
-// Deterministic mean of descriptor d over all points: one block per d, fixed-shape tree.
+// Deterministic centre for the descriptors: mean of descriptor d over the first min(N, 2048) points (one block
+// per d, fixed-shape tree).  Any centre is mathematically exact -- |X_i - X_j| does not depend on it -- it only
+// keeps |X'|^2 small so that n_i + n_j - 2 X'_i.X'_j loses no digits; a subsample mean does that at O(1) cost.
 __global__ void __launch_bounds__(256) descriptor_mean_kernel(int nat, int64_t npoints,
                                                               const double *__restrict__ xyz,
                                                               const double *__restrict__ xeq,
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(256) descriptor_mean_kernel(int nat, int64_t n
   for (int aa = 0; aa < nat; aa++)
     for (int bb = aa + 1; bb < nat; bb++)
       if (pair_index(nat, aa, bb) == d) { a = aa; b = bb; }
+  if (npoints > 2048) npoints = 2048;
   double s = 0.0;
   for (int64_t p = threadIdx.x; p < npoints; p += 256) {
     const double *m = xyz + p * nat * 3;

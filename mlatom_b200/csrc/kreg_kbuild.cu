@@ -19,7 +19,8 @@ namespace kreg {
 // Values block / rectangular value-value block:  S = XA . XB^T on DMMA.8x8x4, then exp.
 // CTA tile 128 x 128, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 64 = 4 x 8 DMMA tiles.
 // =================================================================================================
-constexpr int kTile = 128;
+constexpr int kTileI = 128;  // rows per CTA tile
+constexpr int kTileJ = 64;   // columns per CTA tile
 
 struct ValuesArgs {
   const double *XA;  // [na][XS] centred descriptors, zero padded
@@ -31,121 +32,173 @@ struct ValuesArgs {
   int nchunks;  // XS / (4*KC)
   double c1;
   double lambda;  // added where i == j when `symmetric`
-  int symmetric;  // 1: XA == XB (K build): exact 1+lambda on the diagonal, tiles with tj > ti skipped unless `all_cols`
+  int symmetric;  // 1: XA == XB (K build): exact 1+lambda on the diagonal, tiles above the diagonal skipped unless `all_cols`
   int all_cols;   // 1: compute every column tile directly (row-slab FULL mode / rectangular block)
-  int mirror;     // 1: also write K[j][i] for off-diagonal tiles (whole-matrix FULL mode)
+  int mirror;     // 1: also write K[j][i] for tiles strictly below the diagonal blocks (whole-matrix FULL mode)
   int64_t row_begin, row_end;  // rows of A to produce
   double *K;
   int64_t ldk;
+  int njt;  // column tiles walked by one CTA (set by the launcher)
 };
 
-template <int KC>
-__global__ void __launch_bounds__(256) values_tile_kernel(const ValuesArgs a) {
-  constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);  // stride = 4 mod 8 doubles: conflict-free LDS.64 fragments
-  extern __shared__ __align__(16) double sm[];
-  double *As = sm;                    // [128][XSP]
-  double *Bs = As + kTile * XSP;      // [128][XSP]
-  double *bA = Bs + kTile * XSP;      // [128]
-  double *bB = bA + kTile;            // [128]
-  double *tab = bB + kTile;           // [64]
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned sz = valid ? 16u : 0u;  // src-size 0: nothing is read, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-  const int64_t ti = (int64_t)blockIdx.y + a.row_begin / kTile;
-  const int64_t tj = blockIdx.x;
-  if (a.symmetric && !a.all_cols && tj > ti) return;
-  const int64_t i0 = ti * kTile, j0 = tj * kTile;
-  if (i0 >= a.na || j0 >= a.nb) return;
+// CTA tile 128 x 64, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 32 = 4 x 4 DMMA tiles, <= 128 registers so
+// two CTAs share an SM.  A CTA keeps its 128-row A tile and walks `njt` consecutive column tiles; the next
+// step's tile (B, and A too when the descriptor needs several K-chunks) is fetched with cp.async into the
+// other shared-memory buffer while the current one feeds the tensor pipe.
+template <int KC, bool MULTI>
+__global__ void __launch_bounds__(256, 2) values_tile_kernel(const ValuesArgs a) {
+  constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);  // stride = 4 mod 8 doubles: conflict-free LDS.64 fragments
+  constexpr int A_DBL = kTileI * XSP, B_DBL = kTileJ * XSP;
+  extern __shared__ __align__(16) double sm[];
+  double *Abuf = sm;                                  // [MULTI ? 2 : 1][A_DBL]
+  double *Bbuf = Abuf + (MULTI ? 2 : 1) * A_DBL;      // [2][B_DBL]
+  double *bA = Bbuf + 2 * B_DBL;                      // [128]   row bias
+  double *bBt = bA + kTileI;                          // [2][64] column bias, slot = column-tile parity
+  double *tab = bBt + 2 * kTileJ;                     // [64]
+
+  const int64_t ti = (int64_t)blockIdx.y + a.row_begin / kTileI;
+  const int64_t i0 = ti * kTileI;
+  if (i0 >= a.na) return;
+  int64_t tj_lo = (int64_t)blockIdx.x * a.njt;
+  int64_t tj_hi = tj_lo + a.njt;
+  const int64_t ntj = (a.nb + kTileJ - 1) / kTileJ;
+  if (tj_hi > ntj) tj_hi = ntj;
+  if (a.symmetric && !a.all_cols) {
+    const int64_t last = (i0 + kTileI - 1) / kTileJ + 1;  // tiles entirely above the diagonal are not needed
+    if (tj_hi > last) tj_hi = last;
+  }
+  if (tj_lo >= tj_hi) return;
+  const int nsteps = (int)(tj_hi - tj_lo) * a.nchunks;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int wi = warp >> 1, wj = warp & 1;
 
-  fill_exp_table(tab, tid, 256);
-  if (tid < kTile) {
-    bA[tid] = (i0 + tid < a.na) ? a.biasA[i0 + tid] : 0.0;
-    bB[tid] = (j0 + tid < a.nb) ? a.biasB[j0 + tid] : 0.0;
-  }
+  auto issue = [&](int step) {
+    const int64_t j0 = (tj_lo + step / a.nchunks) * kTileJ;
+    const int ch = step % a.nchunks, buf = step & 1;
+    if (MULTI || step == 0) {
+      double *dst = Abuf + (MULTI ? buf : 0) * A_DBL;
+      for (int e = tid; e < kTileI * KC * 2; e += 256) {
+        const int r = e / (KC * 2), c2 = e % (KC * 2);
+        const bool ok = i0 + r < a.na;
+        cp_async16(dst + r * XSP + c2 * 2, a.XA + (ok ? i0 + r : 0) * a.XS + ch * KC * 4 + c2 * 2, ok);
+      }
+    }
+    double *dst = Bbuf + buf * B_DBL;
+    for (int e = tid; e < kTileJ * KC * 2; e += 256) {
+      const int r = e / (KC * 2), c2 = e % (KC * 2);
+      const bool ok = j0 + r < a.nb;
+      cp_async16(dst + r * XSP + c2 * 2, a.XB + (ok ? j0 + r : 0) * a.XS + ch * KC * 4 + c2 * 2, ok);
+    }
+    if (ch == 0 && tid < kTileJ)
+      bBt[((step / a.nchunks) & 1) * kTileJ + tid] = (j0 + tid < a.nb) ? a.biasB[j0 + tid] : 0.0;
+    cp_async_commit();
+  };
 
-  double S[4][8][2];
+  issue(0);
+  fill_exp_table(tab, tid, 256);
+  if (tid < kTileI) bA[tid] = (i0 + tid < a.na) ? a.biasA[i0 + tid] : 0.0;
+
+  double S[4][4][2];
 #pragma unroll
   for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
+    for (int nt = 0; nt < 4; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
+  const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
 
-  for (int ch = 0; ch < a.nchunks; ch++) {
-    if (ch) __syncthreads();
-    // stage the K-chunk of both tiles (16-byte vector loads; rows past the end read as zero)
-    for (int e = tid; e < kTile * KC * 2; e += 256) {
-      const int r = e / (KC * 2), c2 = e % (KC * 2);
-      double2 va = make_double2(0.0, 0.0), vb = va;
-      if (i0 + r < a.na) va = *reinterpret_cast<const double2 *>(a.XA + (i0 + r) * a.XS + ch * KC * 4 + c2 * 2);
-      if (j0 + r < a.nb) vb = *reinterpret_cast<const double2 *>(a.XB + (j0 + r) * a.XS + ch * KC * 4 + c2 * 2);
-      *reinterpret_cast<double2 *>(As + r * XSP + c2 * 2) = va;
-      *reinterpret_cast<double2 *>(Bs + r * XSP + c2 * 2) = vb;
-    }
-    __syncthreads();
+  for (int step = 0; step < nsteps; step++) {
+    cp_async_wait_all();
+    __syncthreads();  // this step's tiles are visible; every warp is done with the other buffer
+    if (step + 1 < nsteps) issue(step + 1);
+    const int ch = step % a.nchunks, buf = step & 1;
+    const double *As = Abuf + (MULTI ? buf : 0) * A_DBL;
+    const double *Bs = Bbuf + buf * B_DBL;
 #pragma unroll
     for (int ks = 0; ks < KC; ks++) {
-      double af[4], bf[8];
+      double af[4], bf[4];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++) af[mt] = As[(wi * 32 + mt * 8 + g) * XSP + ks * 4 + q];
 #pragma unroll
-      for (int nt = 0; nt < 8; nt++) bf[nt] = Bs[(wj * 64 + nt * 8 + g) * XSP + ks * 4 + q];
+      for (int nt = 0; nt < 4; nt++) bf[nt] = Bs[(wj * 32 + nt * 8 + g) * XSP + ks * 4 + q];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) dmma884(S[mt][nt], af[mt], bf[nt]);
+        for (int nt = 0; nt < 4; nt++) dmma884(S[mt][nt], af[mt], bf[nt]);
     }
-  }
+    if (ch != a.nchunks - 1) continue;
 
-  // epilogue: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly 1 + lambda, coalesced 16-byte stores
-  const bool diag_tile = a.symmetric && ti == tj;
-  const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
+    // epilogue: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly 1 + lambda, 16-byte stores (64 B runs per row)
+    const int64_t j0 = (tj_lo + step / a.nchunks) * kTileJ;
+    const double *bB = bBt + ((step / a.nchunks) & 1) * kTileJ;
+    const bool diag_tile = a.symmetric && j0 + kTileJ - 1 >= i0;  // touches the diagonal block: computed directly
 #pragma unroll
-  for (int mt = 0; mt < 4; mt++) {
-    const int ri = wi * 32 + mt * 8 + g;
-    const int64_t i = i0 + ri;
-    const bool row_ok = i < a.na && i >= a.row_begin && i < a.row_end;
-    const double bi = bA[ri];
+    for (int mt = 0; mt < 4; mt++) {
+      const int ri = wi * 32 + mt * 8 + g;
+      const int64_t i = i0 + ri;
+      const bool row_ok = i < a.na && i >= a.row_begin && i < a.row_end;
+      const double bi = bA[ri];
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-      const int cj = wj * 64 + nt * 8 + 2 * q;
-      const int64_t j = j0 + cj;
-      double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bB[cj]), 0.0), tab);
-      double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bB[cj + 1]), 0.0), tab);
-      if (a.symmetric) {
-        if (i == j) k0 = 1.0 + a.lambda;
-        if (i == j + 1) k1 = 1.0 + a.lambda;
-      }
-      if (row_ok) {
-        double *dst = a.K + i * a.ldk + j;
-        const bool w0 = j < a.nb && (!lower_only || j <= i);
-        const bool w1 = j + 1 < a.nb && (!lower_only || j + 1 <= i);
-        if (w0 && w1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-          *reinterpret_cast<double2 *>(dst) = make_double2(k0, k1);
-        } else {
-          if (w0) dst[0] = k0;
-          if (w1) dst[1] = k1;
+      for (int nt = 0; nt < 4; nt++) {
+        const int cj = wj * 32 + nt * 8 + 2 * q;
+        const int64_t j = j0 + cj;
+        double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bB[cj]), 0.0), tab);
+        double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bB[cj + 1]), 0.0), tab);
+        S[mt][nt][0] = S[mt][nt][1] = 0.0;
+        if (a.symmetric) {
+          if (i == j) k0 = 1.0 + a.lambda;
+          if (i == j + 1) k1 = 1.0 + a.lambda;
         }
-      }
-      if (a.mirror && !diag_tile && i < a.na) {
-        if (j < a.nb) a.K[j * a.ldk + i] = k0;
-        if (j + 1 < a.nb) a.K[(j + 1) * a.ldk + i] = k1;
+        if (row_ok) {
+          double *dst = a.K + i * a.ldk + j;
+          const bool w0 = j < a.nb && (!lower_only || j <= i);
+          const bool w1 = j + 1 < a.nb && (!lower_only || j + 1 <= i);
+          if (w0 && w1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            *reinterpret_cast<double2 *>(dst) = make_double2(k0, k1);
+          } else {
+            if (w0) dst[0] = k0;
+            if (w1) dst[1] = k1;
+          }
+        }
+        if (a.mirror && !diag_tile && i < a.na) {
+          if (j < a.nb) a.K[j * a.ldk + i] = k0;
+          if (j + 1 < a.nb) a.K[(j + 1) * a.ldk + i] = k1;
+        }
       }
     }
   }
 }
 
 template <int KC>
-static int launch_values_kc(const ValuesArgs &a, cudaStream_t st) {
+static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
-  const size_t smem = (size_t)(2 * kTile * XSP + 2 * kTile + 64) * sizeof(double);
-  auto kern = values_tile_kernel<KC>;
-  KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool multi = a.nchunks > 1;
+  const size_t smem =
+      (size_t)((multi ? 2 : 1) * kTileI * XSP + 2 * kTileJ * XSP + kTileI + 2 * kTileJ + 64) * sizeof(double);
   const int64_t r1 = a.row_end < a.na ? a.row_end : a.na;
   if (r1 <= a.row_begin) return KREG_OK;
-  const int64_t ti0 = a.row_begin / kTile, ti1 = (r1 - 1) / kTile;
-  dim3 grid((unsigned)((a.nb + kTile - 1) / kTile), (unsigned)(ti1 - ti0 + 1));
-  kern<<<grid, 256, smem, st>>>(a);
+  const int64_t ti0 = a.row_begin / kTileI, ti1 = (r1 - 1) / kTileI;
+  const int64_t ntj = (a.nb + kTileJ - 1) / kTileJ;
+  const int64_t tiles = ntj * (ti1 - ti0 + 1) / ((a.symmetric && !a.all_cols) ? 2 : 1);
+  a.njt = tiles > 40000 ? 16 : tiles > 5000 ? 8 : tiles > 1000 ? 4 : 2;
+  dim3 grid((unsigned)((ntj + a.njt - 1) / a.njt), (unsigned)(ti1 - ti0 + 1));
+  if (multi) {
+    auto kern = values_tile_kernel<KC, true>;
+    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(a);
+  } else {
+    auto kern = values_tile_kernel<KC, false>;
+    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(a);
+  }
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
@@ -237,111 +290,136 @@ template <int NAT>
 struct GradCfg {
   static constexpr int G3 = 3 * NAT;
   static constexpr int D = NAT * (NAT - 1) / 2;
-  static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);
-  static constexpr int THREADS = ((TJ * G3 + 31) / 32) * 32;
+  static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);  // geometries j per CTA
+  static constexpr int TI = NAT <= 12 ? 8 : 4;                                      // geometries i per CTA
+  static constexpr int COLS = TJ * G3;
+  static constexpr int THREADS = ((COLS + 31) / 32) * 32;
+  // shared memory carve-up (doubles)
+  static constexpr int SM_EI = 0;                         // [TI][NAT*NAT*3]
+  static constexpr int SM_XI = SM_EI + TI * NAT * NAT * 3;  // [TI][D]
+  static constexpr int SM_DLT = SM_XI + TI * D;           // [TI][TJ][D]   X_j - X_i
+  static constexpr int SM_UI = SM_DLT + TI * TJ * D;      // [TI][TJ][G3]  J_i^T (X_j - X_i)
+  static constexpr int SM_KS = SM_UI + TI * TJ * G3;      // [TI][TJ]      k_ij / sigma^2
+  static constexpr int SM_TAB = SM_KS + TI * TJ;          // [64]
+  static constexpr int SM_DOUBLES = SM_TAB + 64;
 };
 
+// One CTA = TI geometries i (3 Nat rows each) x TJ geometries j (3 Nat columns each).  Thread = one matrix
+// column (j, b, u): it keeps E_j(b, .)[u] in registers, and for every i walks the 3 Nat rows, so each store
+// instruction of a warp covers 32 consecutive doubles of one matrix row.
 template <int NAT>
 __global__ void __launch_bounds__(GradCfg<NAT>::THREADS) grad_blocks_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
-  constexpr int G3 = C::G3, D = C::D, TJ = C::TJ;
-  __shared__ double Xi[D];
-  __shared__ double Ei[NAT * NAT * 3];
-  __shared__ double dlt[TJ][D];   // X_j - X_i
-  __shared__ double ui[TJ][G3];   // J_i^T (X_j - X_i)
-  __shared__ double ks[TJ];       // k_ij / sigma^2
-  __shared__ double tab[64];
+  constexpr int G3 = C::G3, D = C::D, TJ = C::TJ, TI = C::TI, NN3 = NAT * NAT * 3;
+  extern __shared__ __align__(16) double gsm[];
+  double *Ei = gsm + C::SM_EI, *Xi = gsm + C::SM_XI, *dlt = gsm + C::SM_DLT, *ui = gsm + C::SM_UI;
+  double *ks = gsm + C::SM_KS, *tab = gsm + C::SM_TAB;
 
-  const int64_t i = blockIdx.y;
-  const int64_t jb = (int64_t)blockIdx.x * TJ;
-  const int64_t row_i = a.nv + i * G3;
-  // this CTA's rows: [row_i, row_i + G3)
-  if (row_i + G3 <= a.row_begin || row_i >= a.row_end) return;
-  const bool need_gg = jb <= i || a.fill == KREG_FILL_FULL;  // grad-grad columns wanted for this j block
+  const int64_t ib = (int64_t)blockIdx.y * TI;   // first geometry i
+  const int64_t jb = (int64_t)blockIdx.x * TJ;   // first geometry j
+  const int ni = (int)((a.ntr - ib) < TI ? (a.ntr - ib) : TI);
+  const int nj = (int)((a.ntr - jb) < TJ ? (a.ntr - jb) : TJ);
+  const int64_t row0 = a.nv + ib * G3;
+  if (row0 + (int64_t)ni * G3 <= a.row_begin || row0 >= a.row_end) return;
+  const bool full = a.fill == KREG_FILL_FULL;
+  const bool need_gg = full || jb <= ib + ni - 1;  // some (i, j) of the block has j <= i
   if (!need_gg && a.nv == 0) return;
 
   const int tid = threadIdx.x;
-  const int jl = tid / G3, col = tid % G3;  // column (j, b, u)
+  const int jl = tid / G3, col = tid % G3;  // this thread's column (j, b, u)
   const int b = col / 3, u = col % 3;
   const int64_t j = jb + jl;
-  const bool active = jl < TJ && j < a.ntr;
+  const bool active = tid < C::COLS && jl < nj;
 
   fill_exp_table(tab, tid, C::THREADS);
-  for (int e = tid; e < D; e += C::THREADS) Xi[e] = a.Xc[i * a.XS + e];
-  for (int e = tid; e < NAT * NAT * 3; e += C::THREADS) Ei[e] = a.E[i * (NAT * NAT * 3) + e];
+  for (int e = tid; e < ni * NN3; e += C::THREADS) Ei[e] = a.E[ib * NN3 + e];
+  for (int e = tid; e < ni * D; e += C::THREADS) Xi[e] = a.Xc[(ib + e / D) * a.XS + e % D];
   __syncthreads();
-  for (int e = tid; e < TJ * D; e += C::THREADS) {
-    const int jj = e / D, d = e % D;
-    dlt[jj][d] = (jb + jj < a.ntr) ? a.Xc[(jb + jj) * a.XS + d] - Xi[d] : 0.0;
+  for (int e = tid; e < ni * TJ * D; e += C::THREADS) {
+    const int il = e / (TJ * D), r = e % (TJ * D), jj = r / D, d = r % D;
+    dlt[e] = (jj < nj) ? a.Xc[(jb + jj) * a.XS + d] - Xi[il * D + d] : 0.0;
   }
   __syncthreads();
-  if (tid < TJ) {
+  for (int p = tid; p < ni * TJ; p += C::THREADS) {
+    const int il = p / TJ, jj = p % TJ;
     double k = 0.0;
-    if (jb + tid < a.ntr) {
+    if (jj < nj) {
+      const double *dd = dlt + p * D;
       double d2 = 0.0;
-      for (int d = 0; d < D; d++) d2 = fma(dlt[tid][d], dlt[tid][d], d2);
-      k = (jb + tid == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
+      for (int d = 0; d < D; d++) d2 = fma(dd[d], dd[d], d2);
+      k = (jb + jj == ib + il) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
     }
-    ks[tid] = k * a.inv_s2;
+    ks[p] = k * a.inv_s2;
   }
-  // u_i^{(j)}[(a,t)] = sum_c E_i(a,c)[t] * D_j[d_ac]   -- thread (jl, col) computes entry col of its j
   double ej[NAT];  // E_j(b,c)[u] for all c (0 at c == b)
-  double ujs = 0.0;
   if (active) {
-    double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < NAT; c++) {
-      if (c != b) {
-        const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
-        s = fma(Ei[(b * NAT + c) * 3 + u], dlt[jl][d], s);
+    for (int c = 0; c < NAT; c++) ej[c] = a.E[(j * NAT * NAT + b * NAT + c) * 3 + u];
+    // u_i^{(j)}[(b,u)] = sum_c E_i(b,c)[u] * D_ij[d_bc] for every i of the block
+    for (int il = 0; il < ni; il++) {
+      const double *dd = dlt + (il * TJ + jl) * D;
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < NAT; c++)
+        if (c != b) s = fma(Ei[il * NN3 + (b * NAT + c) * 3 + u], dd[pair_index(NAT, b < c ? b : c, b < c ? c : b)], s);
+      ui[(il * TJ + jl) * G3 + col] = s;
+    }
+  }
+  __syncthreads();
+
+  // value-gradient block: K[row_i + q][j] = (k/s^2) (J_i^T (X_j - X_i))_q.  Re-map threads so consecutive threads
+  // write consecutive j of one row.
+  if (a.nv) {
+    for (int e = tid; e < ni * G3 * TJ; e += C::THREADS) {
+      const int il = e / (G3 * TJ), r = e % (G3 * TJ), q = r / TJ, jj = r % TJ;
+      if (jj < nj) {
+        const int64_t row = row0 + (int64_t)il * G3 + q;
+        if (row >= a.row_begin && row < a.row_end) {
+          const double v = ks[il * TJ + jj] * ui[(il * TJ + jj) * G3 + q];
+          a.K[row * a.ldk + jb + jj] = v;
+          if (full) a.K[(jb + jj) * a.ldk + row] = v;
+        }
       }
     }
-    ui[jl][col] = s;
+  }
+  if (!need_gg || !active) return;
+
+  // gradient-gradient blocks
+  for (int il = 0; il < ni; il++) {
+    const int64_t i = ib + il;
+    if (!full && j > i) continue;
+    const double *dd = dlt + (il * TJ + jl) * D;
     double sj = 0.0;
 #pragma unroll
-    for (int c = 0; c < NAT; c++) {
-      ej[c] = a.E[(j * NAT * NAT + b * NAT + c) * 3 + u];
-      if (c != b) {
-        const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
-        sj = fma(ej[c], dlt[jl][d], sj);
-      }
-    }
-    ujs = sj * a.inv_s2;  // u_j[col] / sigma^2
-  }
-  __syncthreads();
-  if (!active) return;
-  const double kj = ks[jl];
-
-  // value-gradient block: K[row_i + q][j] = (k/s^2) (J_i^T (X_j - X_i))_q ; thread (jl, col) writes q = col
-  if (a.nv) {
-    const int64_t r = row_i + col;
-    if (r >= a.row_begin && r < a.row_end) {
-      const double v = kj * ui[jl][col];
-      a.K[r * a.ldk + j] = v;
-      if (a.fill == KREG_FILL_FULL) a.K[j * a.ldk + r] = v;  // mirrored value-gradient entry (value row j)
-    }
-  }
-  if (!need_gg) return;
-  if (a.fill != KREG_FILL_FULL && j > i) return;
-  // gradient-gradient block, rows (a,t) of geometry i, this thread's column (j,b,u)
-  double *dst = a.K + row_i * a.ldk + a.nv + j * G3 + col;
-#pragma unroll
-  for (int aa = 0; aa < NAT; aa++) {
+    for (int c = 0; c < NAT; c++)
+      if (c != b) sj = fma(ej[c], dd[pair_index(NAT, b < c ? b : c, b < c ? c : b)], sj);
+    const double ujs = sj * a.inv_s2;  // u_j[col] / sigma^2
+    const double kj = ks[il * TJ + jl];
+    const double *E = Ei + il * NN3;
+    const double *uu = ui + (il * TJ + jl) * G3;
+    // diagonal 3x3 block (a == b): sum_c E_i(b,c)[t] E_j(b,c)[u], hoisted out of the row loop so that the loop
+    // below is branch-free (E(b,b) = 0 makes the generic product vanish there)
+    double jd[3];
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-      const int q = aa * 3 + t;
-      double jj;
-      if (aa == b) {
-        jj = 0.0;
+      double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < NAT; c++) jj = fma(Ei[(b * NAT + c) * 3 + t], ej[c], jj);  // E(b,b) = 0
-      } else {
-        jj = Ei[(aa * NAT + b) * 3 + t] * ej[aa];  // E_i(a,b)[t] * E_j(b,a)[u]
+      for (int c = 0; c < NAT; c++) acc = fma(E[(b * NAT + c) * 3 + t], ej[c], acc);
+      jd[t] = acc;
+    }
+    const int64_t rbase = row0 + (int64_t)il * G3;
+    double *dst = a.K + rbase * a.ldk + a.nv + j * G3 + col;
+#pragma unroll
+    for (int aa = 0; aa < NAT; aa++) {
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int q = aa * 3 + t;
+        const double jj = fma(E[(aa * NAT + b) * 3 + t], ej[aa], aa == b ? jd[t] : 0.0);  // E_i(a,b)[t] E_j(b,a)[u]
+        double v = kj * fma(-uu[q], ujs, jj);
+        if (j == i && q == col) v += a.lambdag;
+        const int64_t r = rbase + q;
+        if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * a.ldk] = v;
       }
-      double v = kj * fma(-ui[jl][q], ujs, jj);
-      if (j == i && q == col) v += a.lambdag;
-      const int64_t r = row_i + q;
-      if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * a.ldk] = v;
     }
   }
 }
@@ -349,8 +427,11 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS) grad_blocks_kernel(cons
 template <int NAT>
 static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
   using C = GradCfg<NAT>;
-  dim3 grid((unsigned)((a.ntr + C::TJ - 1) / C::TJ), (unsigned)a.ntr);
-  grad_blocks_kernel<NAT><<<grid, C::THREADS, 0, st>>>(a);
+  auto kern = grad_blocks_kernel<NAT>;
+  const size_t smem = (size_t)C::SM_DOUBLES * sizeof(double);
+  KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((a.ntr + C::TJ - 1) / C::TJ), (unsigned)((a.ntr + C::TI - 1) / C::TI));
+  kern<<<grid, C::THREADS, smem, st>>>(a);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }

@@ -80,11 +80,13 @@ def build_kernel_matrix(
     fill: int = FILL_LOWER,
     rows: Optional[Tuple[int, int]] = None,
     out: Optional[torch.Tensor] = None,
+    row_offset: int = 0,
 ) -> torch.Tensor:
     """K + diag(lambda) assembled on the device (KREG.f90:293-346 + :616-622).
 
     Returns the (M, M) row-major matrix; with ``fill=FILL_LOWER`` only j <= i is defined.
-    ``rows=(r0, r1)`` restricts the assembly to a row slab of ``out`` (multi-GPU sharding).
+    ``rows=(r0, r1)`` restricts the assembly to a row slab (multi-GPU sharding); ``out`` is then either the
+    whole matrix or, with ``row_offset=r0``, a slab buffer whose first row is matrix row r0.
     """
     xyz = _dev(xyz, xeq_.device)
     ntr, nat, _ = xyz.shape
@@ -93,13 +95,15 @@ def build_kernel_matrix(
     m = ntrval + ntrgr
     if out is None:
         out = torch.empty((m, m), dtype=F64, device=xyz.device)
-    assert out.is_cuda and out.dtype == F64 and out.shape[0] == m and out.stride(1) == 1
     r0, r1 = (0, m) if rows is None else rows
+    assert out.is_cuda and out.dtype == F64 and out.stride(1) == 1 and out.shape[1] >= m
+    assert out.shape[0] >= r1 - row_offset and row_offset <= r0
     ws_bytes = _lib.load().kreg_build_workspace_bytes(nat, ntr, ntrgr)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
     call(
         "kreg_build_kernel_matrix", nat, ntr, ntrval, ntrgr, _ptr(xyz), _ptr(xeq_), float(sigma), float(lambdav),
-        float(lambdagradxyz), r0, r1, fill, _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream(),
+        float(lambdagradxyz), r0, r1, fill, _ptr(out) - row_offset * out.stride(0) * 8, out.stride(0), _ptr(ws), ws_bytes,
+        _stream(),
     )
     return out
 
