@@ -178,7 +178,7 @@ struct PredictCfg {
   static constexpr size_t SMEM_BYTES = (size_t)SM_DOUBLES * 8;
 };
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
 __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs args) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
   constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
   // ---- per-warp register state ----
   double afrag[A_IN_SMEM ? 1 : MT][A_IN_SMEM ? 1 : KS];
   double bi[MT];
-  double acc[MT][NT][2];
+  double acc[WANT_G ? MT : 1][WANT_G ? NT : 1][2];  // GEMM2 accumulators (energy + gradient passes)
+  double esum[WANT_G ? 1 : MT];                      // energy-only passes: per-thread partial row sums of W
   const double *arow[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) {
@@ -253,8 +254,12 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
 #pragma unroll
       for (int ks = 0; ks < KS; ks++) afrag[mt][ks] = arow[mt][4 * ks];
     }
+    if (WANT_G) {
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < NT; nt++) acc[WANT_G ? mt : 0][WANT_G ? nt : 0][0] = acc[WANT_G ? mt : 0][WANT_G ? nt : 0][1] = 0.0;
+    } else {
+      esum[WANT_G ? 0 : mt] = 0.0;
+    }
   }
   const double c1 = args.c1;
 
@@ -317,20 +322,26 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
           W[mt][1] = k1 * sc.z;
         }
       }
+      if (!WANT_G) {
+        // energy only: E_i = sum_j w_ij needs no second GEMM, just the row sums of W
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) esum[WANT_G ? 0 : mt] += W[mt][0] + W[mt][1];
+        continue;
+      }
       // GEMM2: acc += W . [Xtrain | 1]  (+ K . V)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
         const double2 bx = *reinterpret_cast<const double2 *>(cb + C::OFF_B2X + (nt * 32 + lane) * 2);
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt], W[mt][0], bx.x);
+        for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], W[mt][0], bx.x);
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt], W[mt][1], bx.y);
+        for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], W[mt][1], bx.y);
         if (HAS_V) {
           const double2 bv = *reinterpret_cast<const double2 *>(cb + C::OFF_B2V + (nt * 32 + lane) * 2);
 #pragma unroll
-          for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt], Kf[mt][0], bv.x);
+          for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], Kf[mt][0], bv.x);
 #pragma unroll
-          for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt], Kf[mt][1], bv.y);
+          for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], Kf[mt][1], bv.y);
         }
       }
     }
@@ -340,12 +351,24 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
 
   // ---- epilogue: accumulators -> shared tile, then one thread per test geometry ----
   __syncthreads();
+  if (WANT_G) {
 #pragma unroll
-  for (int mt = 0; mt < MT; mt++) {
-    const int r = (warp * MT + mt) * 8 + g;
+    for (int mt = 0; mt < MT; mt++) {
+      const int r = (warp * MT + mt) * 8 + g;
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++)
-      *reinterpret_cast<double2 *>(tile + r * TS + 8 * nt + 2 * q) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      for (int nt = 0; nt < NT; nt++)
+        *reinterpret_cast<double2 *>(tile + r * TS + 8 * nt + 2 * q) =
+            make_double2(acc[WANT_G ? mt : 0][WANT_G ? nt : 0][0], acc[WANT_G ? mt : 0][WANT_G ? nt : 0][1]);
+    }
+  } else {
+    // the four lanes q = 0..3 of a row hold disjoint column subsets: fixed-order butterfly, lane q == 0 stores
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      double s = esum[WANT_G ? 0 : mt];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) tile[((warp * MT + mt) * 8 + g) * TS + D] = s;
+    }
   }
   __syncthreads();
   for (int r = tid; r < C::ROWS; r += kThreads) {
@@ -354,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
     const double *y = tile + r * TS;
     const double esum = y[D];
     if (args.E) args.E[p] = args.prior + esum;
-    if (args.G) {
+    if (WANT_G && args.G) {
       const double *m = args.xyz + p * (NAT * 3);
       double mm[NAT * 3], gr[NAT * 3];
 #pragma unroll
@@ -387,16 +410,23 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
 }
 
 // ---- host-side dispatch -----------------------------------------------------------------------
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
-static int launch_predict_cfg(const PredictArgs &a, cudaStream_t st) {
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
+static int launch_predict_g(const PredictArgs &a, cudaStream_t st) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
-  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
   const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
   kern<<<(unsigned)blocks, kThreads, C::SMEM_BYTES, st>>>(a);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
+}
+
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+static int launch_predict_cfg(const PredictArgs &a, cudaStream_t st) {
+  // energy-only requests skip the second GEMM entirely
+  return a.G ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true>(a, st)
+             : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false>(a, st);
 }
 
 template <int NAT>

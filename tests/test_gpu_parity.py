@@ -83,9 +83,10 @@ def test_golden_predict_from_reference_alpha(golden, eng):
     ref_e = g["prior"] + g["E_test"]
     assert np.abs(e - ref_e).max() <= E_RTOL * np.abs(ref_e).max()
     assert np.abs(gr - g["G_test"]).max() <= G_TOL * max(1.0, np.abs(g["G_test"]).max())
-    # energy only / gradient only paths give the same numbers
+    # energy-only passes skip the second GEMM (row sums of W instead of the ones column): same numbers to rounding
     e2, none = model.predict(dev(g["xyz_test"]), energy=True, gradient=False)
-    assert none is None and np.array_equal(e2.cpu().numpy(), e)
+    assert none is None and np.abs(e2.cpu().numpy() - ref_e).max() <= E_RTOL * np.abs(ref_e).max()
+    assert np.abs(e2.cpu().numpy() - e).max() <= 1e-12 * np.abs(ref_e).max()
     none, g2 = model.predict(dev(g["xyz_test"]), energy=False, gradient=True)
     assert none is None and np.array_equal(g2.cpu().numpy(), gr)
 

@@ -87,6 +87,13 @@ def main():
     t_build = torch.tensor([float(np.mean(build_ms))], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(t_build, op=dist.ReduceOp.MAX)
+    if ws > 1:  # warm the NCCL point-to-point channels up (lazy connection setup is not part of the gather)
+        tiny = torch.zeros(8, dtype=torch.float64, device=dev)
+        if rank == 0:
+            for r in range(1, ws):
+                dist.recv(tiny, r)
+        else:
+            dist.send(tiny, 0)
     sync()
     t0 = time.perf_counter()
     kd.gather_row_slabs(k, target if rank else k[r0:r1], slabs, 0)
