@@ -149,6 +149,11 @@ int kreg_predict(int natoms, int64_t ntrain, const void *packed, const double *c
                  int64_t npoints, const double *xyz, int flags, double *E, double *G,
                  void *stream);
 
+/* Test geometries one CTA of kreg_predict handles for this molecule size / model kind (<0: unsupported size).
+ * Callers that split a batch into chunks (host streaming, multi-stream pipelines) should use multiples of
+ * SM count x this value so that every chunk fills whole waves. */
+int kreg_predict_tile_rows(int natoms, int has_gradient_terms);
+
 #ifdef __cplusplus
 }
 #endif

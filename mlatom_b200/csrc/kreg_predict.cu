@@ -446,6 +446,14 @@ static int launch_predict_nat(const PredictArgs &a, bool has_v, cudaStream_t st)
   }
 }
 
+// test geometries handled by one CTA of the kernel launch_predict_nat<NAT> would pick
+template <int NAT>
+static int tile_rows_nat(bool has_v) {
+  constexpr TcShape sh(NAT);
+  const int mt = sh.D <= 36 ? (has_v ? 2 : 4) : sh.D <= 66 ? (has_v ? 1 : 2) : 1;
+  return kWarps * mt * 8;
+}
+
 static int launch_predict(int nat, const PredictArgs &a, bool has_v, cudaStream_t st) {
   switch (nat) {
 #define KREG_CASE(N) \
@@ -473,6 +481,20 @@ extern "C" int kreg_precompute_v(int natoms, int64_t ntrain, const double *xyz_t
   precompute_v_kernel<<<blocks, 256, 0, as_stream(stream)>>>(natoms, ntrain, xyz_train, xeq, alpha_grad, V);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
+}
+
+extern "C" int kreg_predict_tile_rows(int natoms, int has_gradient_terms) {
+  const bool v = has_gradient_terms != 0;
+  switch (natoms) {
+#define KREG_CASE(N) \
+  case N:            \
+    return tile_rows_nat<N>(v);
+    KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9)
+    KREG_CASE(10) KREG_CASE(11) KREG_CASE(12) KREG_CASE(21)
+#undef KREG_CASE
+    default:
+      return KREG_E_UNSUPPORTED;
+  }
 }
 
 extern "C" size_t kreg_packed_model_bytes(int natoms, int64_t ntrain, int has_gradient_terms) {

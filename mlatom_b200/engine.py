@@ -195,7 +195,13 @@ class PackedModel:
              _stream())
         return e, g
 
-    def predict_host(self, xyz_host: np.ndarray, energy: bool = True, gradient: bool = True, chunk: int = 65536):
+    def wave_rows(self) -> int:
+        """Test geometries in one full wave of the prediction kernel on this device (SM count x rows per CTA)."""
+        rows = _lib.load().kreg_predict_tile_rows(self.natoms, 1 if self.has_gradient_terms else 0)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        return int(rows) * int(sms)
+
+    def predict_host(self, xyz_host: np.ndarray, energy: bool = True, gradient: bool = True, chunk: Optional[int] = None):
         """Host-buffer entry point: numpy (N, Nat, 3) in, numpy out.  Streams chunks through pinned
         staging buffers with H2D copy / kernel / D2H copy overlapped on three streams."""
         return HostPredictor(self, chunk).run(xyz_host, energy, gradient)
@@ -204,7 +210,9 @@ class PackedModel:
 class HostPredictor:
     """Double-buffered host <-> device pipeline around PackedModel.predict."""
 
-    def __init__(self, model: PackedModel, chunk: int = 65536, nbuf: int = 3):
+    def __init__(self, model: PackedModel, chunk: Optional[int] = None, nbuf: int = 3):
+        if chunk is None:
+            chunk = 2 * model.wave_rows()  # whole waves per chunk: no partially filled last wave in every launch
         self.model, self.chunk, self.nbuf = model, int(chunk), nbuf
         dev, nat = model.device, model.natoms
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
