@@ -140,6 +140,32 @@ __global__ void __launch_bounds__(256, 2) values_tile_kernel(const ValuesArgs a)
     const int64_t j0 = (tj_lo + step / a.nchunks) * kTileJ;
     const double *bB = bBt + ((step / a.nchunks) & 1) * kTileJ;
     const bool diag_tile = a.symmetric && j0 + kTileJ - 1 >= i0;  // touches the diagonal block: computed directly
+    // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
+    const bool interior = !diag_tile && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
+                          j0 + kTileJ <= a.nb && (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
+    if (interior) {
+      double *row = a.K + (i0 + wi * 32 + g) * a.ldk + j0 + wj * 32 + 2 * q;
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) {
+        const double bi = bA[wi * 32 + mt * 8 + g];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          const int cj = wj * 32 + nt * 8 + 2 * q;
+          const double2 bj = *reinterpret_cast<const double2 *>(bB + cj);
+          const double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bj.x), 0.0), tab);
+          const double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bj.y), 0.0), tab);
+          S[mt][nt][0] = S[mt][nt][1] = 0.0;
+          *reinterpret_cast<double2 *>(row + nt * 8) = make_double2(k0, k1);
+          if (a.mirror) {
+            double *t = a.K + (j0 + cj) * a.ldk + i0 + wi * 32 + mt * 8 + g;
+            t[0] = k0;
+            t[a.ldk] = k1;
+          }
+        }
+        row += 8 * a.ldk;
+      }
+      continue;
+    }
 #pragma unroll
     for (int mt = 0; mt < 4; mt++) {
       const int ri = wi * 32 + mt * 8 + g;
