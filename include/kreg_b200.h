@@ -138,16 +138,22 @@ int kreg_pack_model(int natoms, int64_t ntrain, const double *xyz_train, const d
                     const double *alpha_val, const double *V, double sigma, double *center,
                     void *packed, size_t packed_bytes, void *stream);
 
+/* Scratch bytes kreg_predict can use for a batch of `npoints` geometries: small batches (fewer CTAs than half the
+ * SMs -- the single-geometry MD / geometry-optimisation step) split the training set across the chip and reduce
+ * the partial sums in a fixed order.  0 for batches large enough to fill the device. */
+size_t kreg_predict_workspace_bytes(int natoms, int64_t ntrain, int has_gradient_terms, int64_t npoints);
+
 /* Replaces KREG.kreg.predict (KREG.f90:534-596: Yest_KRR :348-366, YgradXYZest_KRR :368-391)
  * and MLatomF calcEst_KRR (A_KRR.f90:985-1029; A_KRR_kernel.f90:225-245, :327-412):
  *   E[i]       = prior + sum_j alpha_j k_ij + sum_j sum_bu alpha_j,bu dk_ij/dM_j,bu
  *   G[i][a][t] = dE_i / d xyz[i][a][t]            (gradient, not force: kreg_api.py:126-131)
  * for npoints geometries, energies and gradients in ONE pass over the training set.
- * flags: KREG_PREDICT_ENERGY | KREG_PREDICT_GRADIENT; E or G may be NULL when not requested. */
+ * flags: KREG_PREDICT_ENERGY | KREG_PREDICT_GRADIENT; E or G may be NULL when not requested.
+ * workspace may be NULL (or smaller than kreg_predict_workspace_bytes): the batch then runs unsplit. */
 int kreg_predict(int natoms, int64_t ntrain, const void *packed, const double *center,
                  const double *xeq, double sigma, double prior, int has_gradient_terms,
                  int64_t npoints, const double *xyz, int flags, double *E, double *G,
-                 void *stream);
+                 void *workspace, size_t workspace_bytes, void *stream);
 
 /* Test geometries one CTA of kreg_predict handles for this molecule size / model kind (<0: unsupported size).
  * Callers that split a batch into chunks (host streaming, multi-stream pipelines) should use multiples of

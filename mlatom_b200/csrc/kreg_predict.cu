@@ -154,6 +154,11 @@ struct PredictArgs {
   double prior;
   double *E;
   double *G;
+  // small-batch mode: the training set is split over gridDim.y slices of `stages_per_slice` ring stages; CTAs write
+  // raw accumulators to `partial` and predict_finish_kernel reduces them in slice order (deterministic)
+  int nslices;
+  int stages_per_slice;
+  double *partial;
 };
 
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
@@ -178,6 +183,66 @@ struct PredictCfg {
   static constexpr size_t SMEM_BYTES = (size_t)SM_DOUBLES * 8;
 };
 
+// Per-geometry epilogue: E = prior + A[D];  g = (A[:D] - X'_i A[D]) / s^2;  dE/dM = J_i^T g  (KREG.f90:121 Jacobian)
+template <int NAT, bool WANT_G>
+__device__ __forceinline__ void predict_row_epilogue(const PredictArgs &args, const double *y, int64_t p) {
+  constexpr int D = NAT * (NAT - 1) / 2;
+  const double esum = y[D];
+  if (args.E) args.E[p] = args.prior + esum;
+  if (WANT_G && args.G) {
+    const double *m = args.xyz + p * (NAT * 3);
+    double mm[NAT * 3], gr[NAT * 3];
+#pragma unroll
+    for (int i = 0; i < NAT * 3; i++) {
+      mm[i] = m[i];
+      gr[i] = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < NAT; a++)
+#pragma unroll
+      for (int b = a + 1; b < NAT; b++) {
+        const int d = pair_index(NAT, a, b);
+        const double r2 = rij2_exact(mm + 3 * a, mm + 3 * b);
+        const double x = __ldg(args.xeq + d) / sqrt(r2);
+        const double xc = x - __ldg(args.center + d);
+        const double gd = (y[d] - xc * esum) * args.inv_s2;
+        const double f = gd * x / r2;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const double dx = mm[3 * b + t] - mm[3 * a + t];
+          gr[3 * a + t] = fma(f, dx, gr[3 * a + t]);
+          gr[3 * b + t] = fma(-f, dx, gr[3 * b + t]);
+        }
+      }
+    double *out = args.G + p * (NAT * 3);
+#pragma unroll
+    for (int i = 0; i < NAT * 3; i++) out[i] = gr[i];
+  }
+}
+
+// Small-batch mode, second kernel: sum the slices' accumulators in slice order, then the usual epilogue.
+template <int NAT, int ROWS, int TS>
+__global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictArgs args) {
+  extern __shared__ __align__(16) double ftile[];  // [ROWS][TS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+  const size_t slice_stride = (size_t)gridDim.x * ROWS * TS;
+  for (int r = warp; r < ROWS; r += kWarps) {
+    if (row0 + r >= args.npoints) break;
+    const double *src = args.partial + ((size_t)blockIdx.x * ROWS + r) * TS;
+    for (int c = lane; c < TS; c += 32) {
+      double s = 0.0;
+      for (int sl = 0; sl < args.nslices; sl++) s += src[(size_t)sl * slice_stride + c];
+      ftile[r * TS + c] = s;
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < ROWS; r += kThreads) {
+    const int64_t p = row0 + r;
+    if (p < args.npoints) predict_row_epilogue<NAT, true>(args, ftile + r * TS, p);
+  }
+}
+
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
 __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs args) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
@@ -193,7 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int64_t row0 = (int64_t)blockIdx.x * C::ROWS;
-  const int total_stages = (args.ngroups + GPS - 1) / GPS;
+  const int all_stages = (args.ngroups + GPS - 1) / GPS;
+  const int stage0 = args.nslices > 1 ? (int)blockIdx.y * args.stages_per_slice : 0;  // first ring stage of this slice
+  const int total_stages = args.nslices > 1 ? min(args.stages_per_slice, all_stages - stage0) : all_stages;
 
   // ---- barrier init + first TMA bulk copies (overlap with the descriptor prologue) ----
   if (tid == 0) {
@@ -207,10 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < NSTAGE && s < total_stages; s++) {
-      int ng = min(GPS, args.ngroups - s * GPS);
+      int ng = min(GPS, args.ngroups - (stage0 + s) * GPS);
       unsigned bytes = (unsigned)(ng * C::CHUNK * 8);
       mbar_arrive_expect_tx(&full_bar[s], bytes);
-      bulk_g2s(ring + s * C::STAGE, args.packed + (size_t)s * C::STAGE, bytes, &full_bar[s]);
+      bulk_g2s(ring + s * C::STAGE, args.packed + (size_t)(stage0 + s) * C::STAGE, bytes, &full_bar[s]);
     }
   }
 
@@ -270,14 +337,14 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
       const int sp = (it - 1) % NSTAGE;
       const int nxt = it - 1 + NSTAGE;
       mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
-      int ng = min(GPS, args.ngroups - nxt * GPS);
+      int ng = min(GPS, args.ngroups - (stage0 + nxt) * GPS);
       unsigned bytes = (unsigned)(ng * C::CHUNK * 8);
       mbar_arrive_expect_tx(&full_bar[sp], bytes);
-      bulk_g2s(ring + sp * C::STAGE, args.packed + (size_t)nxt * C::STAGE, bytes, &full_bar[sp]);
+      bulk_g2s(ring + sp * C::STAGE, args.packed + (size_t)(stage0 + nxt) * C::STAGE, bytes, &full_bar[sp]);
     }
     const int s = it % NSTAGE;
     mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
-    const int ng = min(GPS, args.ngroups - it * GPS);
+    const int ng = min(GPS, args.ngroups - (stage0 + it) * GPS);
     for (int gi = 0; gi < ng; gi++) {
       const double *cb = ring + s * C::STAGE + gi * C::CHUNK;
       // GEMM1: S = Xtest . Xtrain^T  (and S2 = Xtest . (V/s^2)^T)
@@ -371,78 +438,102 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
     }
   }
   __syncthreads();
+  if (WANT_G && args.nslices > 1) {
+    // small-batch mode: hand the raw accumulators of the valid rows to predict_finish_kernel
+    double *dst = args.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::ROWS * TS;
+    const int64_t left = args.npoints - row0;
+    const int nvalid = (int)(left < C::ROWS ? left : C::ROWS);
+    for (int e = tid; e < nvalid * TS; e += kThreads) dst[e] = tile[e];
+    return;
+  }
   for (int r = tid; r < C::ROWS; r += kThreads) {
     const int64_t p = row0 + r;
-    if (p >= args.npoints) continue;
-    const double *y = tile + r * TS;
-    const double esum = y[D];
-    if (args.E) args.E[p] = args.prior + esum;
-    if (WANT_G && args.G) {
-      const double *m = args.xyz + p * (NAT * 3);
-      double mm[NAT * 3], gr[NAT * 3];
-#pragma unroll
-      for (int i = 0; i < NAT * 3; i++) {
-        mm[i] = m[i];
-        gr[i] = 0.0;
-      }
-#pragma unroll
-      for (int a = 0; a < NAT; a++)
-#pragma unroll
-        for (int b = a + 1; b < NAT; b++) {
-          const int d = pair_index(NAT, a, b);
-          const double r2 = rij2_exact(mm + 3 * a, mm + 3 * b);
-          const double x = __ldg(args.xeq + d) / sqrt(r2);
-          const double xc = x - __ldg(args.center + d);
-          const double gd = (y[d] - xc * esum) * args.inv_s2;
-          const double f = gd * x / r2;
-#pragma unroll
-          for (int t = 0; t < 3; t++) {
-            const double dx = mm[3 * b + t] - mm[3 * a + t];
-            gr[3 * a + t] = fma(f, dx, gr[3 * a + t]);
-            gr[3 * b + t] = fma(-f, dx, gr[3 * b + t]);
-          }
-        }
-      double *out = args.G + p * (NAT * 3);
-#pragma unroll
-      for (int i = 0; i < NAT * 3; i++) out[i] = gr[i];
-    }
+    if (p < args.npoints) predict_row_epilogue<NAT, WANT_G>(args, tile + r * TS, p);
   }
 }
 
 // ---- host-side dispatch -----------------------------------------------------------------------
+// Small batches (fewer CTAs than half the SMs) split the training set over gridDim.y slices so the whole chip works
+// on them: the single-geometry MD / geometry-optimisation step is latency-, not throughput-bound.
+template <int GPS>
+static void plan_slices(int ngroups, int64_t blocks, int sms, int *nslices, int *stages_per_slice) {
+  const int all_stages = (ngroups + GPS - 1) / GPS;
+  *nslices = 1;
+  *stages_per_slice = all_stages;
+  if (blocks * 2 > sms || all_stages < 8) return;
+  int want = (int)((2 * sms + blocks - 1) / blocks);  // ~2 CTAs per SM in total
+  int per = (all_stages + want - 1) / want;
+  if (per < 4) per = 4;                               // keep the TMA ring busy
+  *stages_per_slice = per;
+  *nslices = (all_stages + per - 1) / per;
+}
+
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
-static int launch_predict_g(const PredictArgs &a, cudaStream_t st) {
+static int launch_predict_g(PredictArgs a, cudaStream_t st) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
   auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
   const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
-  kern<<<(unsigned)blocks, kThreads, C::SMEM_BYTES, st>>>(a);
+  dim3 grid((unsigned)blocks, (unsigned)(a.nslices > 1 ? a.nslices : 1));
+  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(a);
   KREG_LAUNCH_CHECK();
+  if (a.nslices > 1) {
+    auto fin = predict_finish_kernel<NAT, C::ROWS, C::TS>;
+    const size_t smem = (size_t)C::ROWS * C::TS * sizeof(double);
+    KREG_CUDA_TRY(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fin<<<(unsigned)blocks, kThreads, smem, st>>>(a);
+    KREG_LAUNCH_CHECK();
+  }
   return KREG_OK;
 }
 
+// Workspace (bytes) the small-batch mode needs for this launch; 0 when the batch is large enough to run unsplit.
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
-static int launch_predict_cfg(const PredictArgs &a, cudaStream_t st) {
-  // energy-only requests skip the second GEMM entirely
-  return a.G ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true>(a, st)
-             : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false>(a, st);
+static size_t predict_ws_cfg(int ngroups, int64_t npoints, int sms, int *nslices, int *stages_per_slice) {
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+  const int64_t blocks = (npoints + C::ROWS - 1) / C::ROWS;
+  plan_slices<GPS>(ngroups, blocks, sms, nslices, stages_per_slice);
+  return *nslices > 1 ? (size_t)*nslices * blocks * C::ROWS * C::TS * sizeof(double) : 0;
+}
+
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+static int launch_predict_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes, bool query, size_t *need,
+                              cudaStream_t st) {
+  int nslices, per;
+  const size_t bytes = predict_ws_cfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>(a.ngroups, a.npoints, sms, &nslices, &per);
+  if (query) {
+    *need = bytes;
+    return KREG_OK;
+  }
+  a.nslices = 1;
+  a.stages_per_slice = 0;
+  a.partial = nullptr;
+  if (nslices > 1 && ws && ws_bytes >= bytes) {  // without a workspace the batch simply runs unsplit
+    a.nslices = nslices;
+    a.stages_per_slice = per;
+    a.partial = static_cast<double *>(ws);
+  }
+  // energy-only requests skip the second GEMM entirely (the split mode always carries the full accumulators)
+  return (a.G || a.nslices > 1) ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true>(a, st)
+                                : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false>(a, st);
 }
 
 template <int NAT>
-static int launch_predict_nat(const PredictArgs &a, bool has_v, cudaStream_t st) {
+static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *ws, size_t ws_bytes, bool query,
+                              size_t *need, cudaStream_t st) {
   constexpr TcShape sh(NAT);
   if constexpr (sh.D <= 36) {
     // small molecules: test-row fragments live in registers, 4 (values) / 2 (gradient models) m-tiles per warp
-    return has_v ? launch_predict_cfg<NAT, 2, true, false, 2, 4>(a, st)
-                 : launch_predict_cfg<NAT, 4, false, false, 4, 4>(a, st);
+    return has_v ? launch_predict_cfg<NAT, 2, true, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 4, false, false, 4, 4>(a, sms, ws, ws_bytes, query, need, st);
   } else if constexpr (sh.D <= 66) {
-    return has_v ? launch_predict_cfg<NAT, 1, true, false, 1, 4>(a, st)
-                 : launch_predict_cfg<NAT, 2, false, false, 2, 4>(a, st);
+    return has_v ? launch_predict_cfg<NAT, 1, true, false, 1, 4>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 2, false, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st);
   } else {
     // large molecules: accumulators fill the register file; test-row fragments stay in shared memory
-    return has_v ? launch_predict_cfg<NAT, 1, true, true, 1, 2>(a, st)
-                 : launch_predict_cfg<NAT, 1, false, true, 1, 3>(a, st);
+    return has_v ? launch_predict_cfg<NAT, 1, true, true, 1, 2>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 1, false, true, 1, 3>(a, sms, ws, ws_bytes, query, need, st);
   }
 }
 
@@ -454,11 +545,12 @@ static int tile_rows_nat(bool has_v) {
   return kWarps * mt * 8;
 }
 
-static int launch_predict(int nat, const PredictArgs &a, bool has_v, cudaStream_t st) {
+static int launch_predict(int nat, const PredictArgs &a, bool has_v, int sms, void *ws, size_t ws_bytes, bool query,
+                          size_t *need, cudaStream_t st) {
   switch (nat) {
 #define KREG_CASE(N) \
   case N:            \
-    return launch_predict_nat<N>(a, has_v, st);
+    return launch_predict_nat<N>(a, has_v, sms, ws, ws_bytes, query, need, st);
     KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9)
     KREG_CASE(10) KREG_CASE(11) KREG_CASE(12) KREG_CASE(21)
 #undef KREG_CASE
@@ -531,9 +623,33 @@ extern "C" int kreg_pack_model(int natoms, int64_t ntrain, const double *xyz_tra
   return KREG_OK;
 }
 
+static int device_sm_count(int *sms) {
+  static thread_local int cached_dev = -1, cached_sms = 0;
+  int dev = 0;
+  KREG_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    KREG_CUDA_TRY(cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  *sms = cached_sms;
+  return KREG_OK;
+}
+
+extern "C" size_t kreg_predict_workspace_bytes(int natoms, int64_t ntrain, int has_gradient_terms, int64_t npoints) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0 || npoints <= 0) return 0;
+  int sms = 0;
+  if (device_sm_count(&sms) != KREG_OK) return 0;
+  PredictArgs a = {};
+  a.npoints = npoints;
+  a.ngroups = (int)((ntrain + 7) / 8);
+  size_t need = 0;
+  if (launch_predict(natoms, a, has_gradient_terms != 0, sms, nullptr, 0, true, &need, nullptr) != KREG_OK) return 0;
+  return need;
+}
+
 extern "C" int kreg_predict(int natoms, int64_t ntrain, const void *packed, const double *center, const double *xeq,
                             double sigma, double prior, int has_gradient_terms, int64_t npoints, const double *xyz,
-                            int flags, double *E, double *G, void *stream) {
+                            int flags, double *E, double *G, void *workspace, size_t workspace_bytes, void *stream) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
   if (ntrain <= 0 || npoints < 0 || !packed || !center || !xeq || !(sigma > 0.0)) return KREG_E_BADARG;
   if (!(flags & (KREG_PREDICT_ENERGY | KREG_PREDICT_GRADIENT))) return KREG_E_BADARG;
@@ -541,7 +657,10 @@ extern "C" int kreg_predict(int natoms, int64_t ntrain, const void *packed, cons
   if (!xyz) return KREG_E_BADARG;
   if ((flags & KREG_PREDICT_ENERGY) && !E) return KREG_E_BADARG;
   if ((flags & KREG_PREDICT_GRADIENT) && !G) return KREG_E_BADARG;
-  PredictArgs a;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  PredictArgs a = {};
   a.xyz = xyz;
   a.npoints = npoints;
   a.xeq = xeq;
@@ -553,5 +672,7 @@ extern "C" int kreg_predict(int natoms, int64_t ntrain, const void *packed, cons
   a.prior = prior;
   a.E = (flags & KREG_PREDICT_ENERGY) ? E : nullptr;
   a.G = (flags & KREG_PREDICT_GRADIENT) ? G : nullptr;
-  return launch_predict(natoms, a, has_gradient_terms != 0, as_stream(stream));
+  size_t need = 0;
+  return launch_predict(natoms, a, has_gradient_terms != 0, sms, workspace, workspace_bytes, false, &need,
+                        as_stream(stream));
 }

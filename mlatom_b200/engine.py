@@ -190,16 +190,31 @@ class PackedModel:
         e = (out_e if out_e is not None else torch.empty(n, dtype=F64, device=xyz.device)) if energy else None
         g = (out_g if out_g is not None else torch.empty((n, self.natoms, 3), dtype=F64, device=xyz.device)) if gradient else None
         flags = (PREDICT_ENERGY if energy else 0) | (PREDICT_GRADIENT if gradient else 0)
+        hv = 1 if self.has_gradient_terms else 0
+        ws, ws_bytes = None, 0
+        if 0 < n <= self._small_batch_limit():  # latency mode: split the training set over the chip
+            ws_bytes = _lib.load().kreg_predict_workspace_bytes(self.natoms, self.ntrain, hv, n)
+            if ws_bytes:
+                if self._ws is None or self._ws.numel() < ws_bytes:
+                    self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+                ws = self._ws
         call("kreg_predict", self.natoms, self.ntrain, _ptr(self.packed), _ptr(self.center), _ptr(self.xeq),
-             self.sigma, self.prior, 1 if self.has_gradient_terms else 0, n, _ptr(xyz), flags, _ptr(e), _ptr(g),
-             _stream())
+             self.sigma, self.prior, hv, n, _ptr(xyz), flags, _ptr(e), _ptr(g), _ptr(ws), ws_bytes, _stream())
         return e, g
+
+    _ws: Optional[torch.Tensor] = None       # small-batch scratch, grown on demand
+    _wave_rows: Optional[int] = None
+
+    def _small_batch_limit(self) -> int:
+        return self.wave_rows() // 2
 
     def wave_rows(self) -> int:
         """Test geometries in one full wave of the prediction kernel on this device (SM count x rows per CTA)."""
-        rows = _lib.load().kreg_predict_tile_rows(self.natoms, 1 if self.has_gradient_terms else 0)
-        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        return int(rows) * int(sms)
+        if self._wave_rows is None:
+            rows = _lib.load().kreg_predict_tile_rows(self.natoms, 1 if self.has_gradient_terms else 0)
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self._wave_rows = int(rows) * int(sms)
+        return self._wave_rows
 
     def predict_host(self, xyz_host: np.ndarray, energy: bool = True, gradient: bool = True, chunk: Optional[int] = None):
         """Host-buffer entry point: numpy (N, Nat, 3) in, numpy out.  Streams chunks through pinned

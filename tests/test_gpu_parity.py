@@ -241,10 +241,40 @@ def test_full_size_properties(eng):
     fd = ((ep - em) / (2 * h)).cpu().numpy()
     an = (g[:64].cpu().numpy() * dirn).sum((1, 2))
     assert np.abs(fd - an).max() <= 1e-6 * max(1.0, np.abs(an).max())
-    # host pipeline
-    eh, gh = model.predict_host(xte, chunk=8192)
+    # host pipeline: whole-wave chunks reproduce the device path bit for bit; small chunks take the split
+    # (latency) mode, whose fixed-order slice reduction differs from the unsplit sum only by rounding
+    eh, gh = model.predict_host(xte)
     torch.cuda.synchronize()
     assert torch.equal(eh, e.cpu()) and torch.equal(gh, g.cpu())
+    eh, gh = model.predict_host(xte, chunk=8192)
+    torch.cuda.synchronize()
+    assert (eh - e.cpu()).abs().max() <= 1e-12 * e.abs().max().item() and (gh - g.cpu()).abs().max() <= 1e-11
+
+
+@pytest.mark.parametrize("nat,ntr,use_grads", [(9, 2000, False), (9, 300, True), (21, 600, False), (5, 100, False)])
+def test_small_batch_latency_mode_vs_oracle(eng, oracle, nat, ntr, use_grads):
+    """Single-geometry / small-batch predictions (MD, geometry optimisation) split the training set over the chip;
+    they must agree with the oracle and with the same geometries predicted inside a large batch."""
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, 40000, 2)
+    xeq = oracle.xeq(eq)
+    X = oracle.descriptors(xtr, xeq)
+    nv, ng = ntr, (3 * nat * ntr if use_grads else 0)
+    alpha = np.random.default_rng(8).standard_normal(nv + ng) * 0.1
+    model = eng.PackedModel.from_training_set(dev(xtr), dev(xeq), dev(alpha), 1.3, 2.0, nv, ng)
+    d_xte = dev(xte)
+    e_big, g_big = model.predict(d_xte)  # 40000 geometries: unsplit
+    v = oracle.precompute_v(xtr, X, alpha[nv:]) if use_grads else None
+    for n in (1, 7, 300, 5000):
+        e, g = model.predict(d_xte[:n].contiguous())
+        e_ref, g_ref, sc = oracle.predict_factored(X, alpha[:nv], v, 1.3, 2.0, xte[:n], oracle.descriptors(xte[:n], xeq),
+                                                   want_scale=True)
+        assert np.all(np.abs(e.cpu().numpy() - e_ref) <= 1e-13 * np.maximum(sc, 1.0) + E_RTOL * np.abs(e_ref))
+        assert np.abs(g.cpu().numpy() - g_ref).max() <= G_TOL * max(1.0, np.abs(g_ref).max())
+        assert (e - e_big[:n]).abs().max().item() <= 1e-12 * max(1.0, np.abs(sc).max())
+        assert (g - g_big[:n]).abs().max().item() <= 1e-11 * max(1.0, np.abs(g_ref).max())
+        e_only, _ = model.predict(d_xte[:n].contiguous(), gradient=False)
+        assert (e_only - e).abs().max().item() <= 1e-12 * max(1.0, np.abs(sc).max())
 
 
 def test_edge_cases(eng):
