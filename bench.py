@@ -120,6 +120,89 @@ def cpu_baseline(eq, xyz_tr, alpha, prior, seconds=12.0, threads=None):
             "sample": f"{n} of {NTEST} test geometries, full Ntrain={NTRAIN}, {t:.1f} s wall"}, n, t
 
 
+def kbuild_configs(engine, dev, hbm_peak, fp64_peak):
+    """K assembly at BASELINE configs[2] (values, 50k) and configs[4] (gradient-augmented, 2000 x 9 atoms -> 56k)."""
+    import torch
+
+    from mlatom_b200 import synthetic as S
+
+    out = {}
+    eq = S.equilibrium(NAT)
+    xeq = engine.xeq(torch.from_numpy(eq).to(dev))
+    for name, ntr, grads in (("cfg3_values_50k", 50000, False), ("cfg5_gradients_56k", 2000, True)):
+        xyz = torch.from_numpy(S.geometries(eq, ntr, seed=1)).to(dev)
+        m = ntr + (3 * NAT * ntr if grads else 0)
+        k = torch.empty((m, m), dtype=torch.float64, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ms = []
+        for it in range(4):
+            torch.cuda.synchronize()
+            ev[0].record()
+            engine.build_kernel_matrix(xyz, xeq, SIGMA, LAMBDA, LAMBDA, use_gradients=grads, out=k)
+            ev[1].record()
+            torch.cuda.synchronize()
+            if it:
+                ms.append(ev[0].elapsed_time(ev[1]))
+        t = float(np.mean(ms))
+        nbytes = 4.0 * m * (m + 1)
+        rec = {"M": m, "ms": t, "bytes_lower_triangle": nbytes, "gb_per_s": nbytes / t * 1e-6,
+               "frac_of_hbm_copy_peak": nbytes / t * 1e-6 / hbm_peak}
+        if not grads:
+            fp64_ms = ntr * (ntr + 1) / 2 * (3 * D + 3) / (fp64_peak * 1e12) * 1e3
+            rec.update({"bound": "fp64 issue (SURVEY.md App. D)", "fp64_bound_ms": fp64_ms, "frac_of_fp64_bound": fp64_ms / t})
+        else:
+            rec.update({"bound": "hbm write"})
+        out[name] = rec
+        del k
+        torch.cuda.empty_cache()
+    return out
+
+
+def cfg1_side_by_side(engine, dev):
+    """BASELINE configs[0]: energies only, Ntrain=1000, Ntest=10k -- train + predict, CPU port in full beside the GPU."""
+    import torch
+
+    from mlatom_b200 import synthetic as S
+    from oracle import kreg_oracle as O
+
+    ntr, nte = 1000, 10000
+    eq = S.equilibrium(NAT)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
+    e_tr, _ = S.pair_potential(xtr, eq)
+    prior = float(e_tr.mean())
+    # CPU: the oracle's literal restatement (K assembly, LAPACK Cholesky, MLatomF prediction loop), all threads
+    O.set_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    xeq = O.xeq(eq)
+    X, Xte = O.descriptors(xtr, xeq), O.descriptors(xte, xeq)
+    k = O.kernel_matrix(xtr, X, SIGMA, ntr, 0)
+    alpha_cpu = O.solve(k, e_tr - prior, ntr, 0, LAMBDA, LAMBDA)
+    t1 = time.perf_counter()
+    e_cpu, _ = O.predict_mlatomf(xtr, X, alpha_cpu, SIGMA, prior, ntr, 0, xte, Xte, True, False)
+    t2 = time.perf_counter()
+    # GPU: host numpy in, host numpy out (copies included)
+    to_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    res = {}
+    for it in range(3):
+        torch.cuda.synchronize()
+        g0 = time.perf_counter()
+        d_xeq = engine.xeq(to_dev(eq))
+        d_xtr = to_dev(xtr)
+        kk = engine.build_kernel_matrix(d_xtr, d_xeq, SIGMA, LAMBDA, LAMBDA)
+        a = engine.solve(kk, to_dev(e_tr - prior))
+        model = engine.PackedModel.from_training_set(d_xtr, d_xeq, a, SIGMA, prior, ntr, 0)
+        torch.cuda.synchronize()
+        g1 = time.perf_counter()
+        e_gpu, _ = model.predict(to_dev(xte), True, False)
+        e_host = e_gpu.cpu().numpy()
+        g2 = time.perf_counter()
+        res = {"train_ms": 1e3 * (g1 - g0), "predict_ms": 1e3 * (g2 - g1)}
+    return {"workload": "cfg1: KREG energies only, 9 atoms, Ntrain=1000, Ntest=10000, train + predict, host arrays in/out",
+            "gpu": res, "cpu_port": {"train_ms": 1e3 * (t1 - t0), "predict_ms": 1e3 * (t2 - t1), "cores": os.cpu_count()},
+            "max_abs_energy_difference": float(np.abs(e_host - e_cpu).max()),
+            "max_rel_energy_difference": float(np.abs(e_host - e_cpu).max() / np.abs(e_cpu).max())}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm on the host CPU (MLatomF itself cannot be built here:
     no Fortran compiler, binary absent from the checkout)."""
@@ -297,7 +380,9 @@ def run_ours(args):
         "gpu_launches": args.steps,
         "roofline": {"bound": "tensor", "pipe": "FP64 tensor core (DMMA.8x8x4); shares the FP64 pipe with DFMA",
                      "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
-                     "traffic": None,
+                     "traffic": 429.13e6,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
+                                       "profiles/r01_predict_ncu.txt (algorithmic I/O: 440 MB per launch)",
                      "peak_source": "measured live by kreg_measure_fp64_peak(DMMA) (MEASURED_PEAKS.json has no FP64 figure)",
                      "peak_dfma": peak_dfma, "algorithmic_flop_per_launch": FLOP_PER_STEP,
                      "kernel": "kreg::predict_kernel<9,4,false,false,4,4>", "kernel_ms": kernel_ms},
@@ -322,9 +407,12 @@ def run_ours(args):
                           "fp64_bound_ms": fp64_ms, "frac_of_fp64_bound": fp64_ms / kb["ms"],
                           "note": "values-only K at D=36 is FP64-issue-bound, not HBM-bound (SURVEY.md App. D)",
                           "potrf_potrs_ms_timed_separately": extra.get("solve_ms")}
+    if world == 1:
+        line["kbuild_configs"] = kbuild_configs(engine, dev, line["kbuild"]["hbm_peak_gbs"], peak_dmma)
     if world == 1 and not args.no_cpu:
         base, _, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
         line["cpu_baseline"] = base
+        line["cfg1"] = cfg1_side_by_side(engine, dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
