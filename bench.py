@@ -385,10 +385,10 @@ def run_ours(args):
                                        "profiles/r01_predict_ncu.txt (algorithmic I/O: 440 MB per launch)",
                      "peak_source": "measured live by kreg_measure_fp64_peak(DMMA) (MEASURED_PEAKS.json has no FP64 figure)",
                      "peak_dfma": peak_dfma, "algorithmic_flop_per_launch": FLOP_PER_STEP,
-                     "kernel": "kreg::predict_kernel<9,4,false,false,4,4>", "kernel_ms": kernel_ms},
+                     "kernel": "kreg::predict_kernel<9,2,false,false,3,3,true>", "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NTEST * NAT * 3 * 8,
                 "d2h_bytes_per_step": NTEST * 8 + NTEST * NAT * 3 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "PackedModel.predict_host (pinned host xyz -> pinned host E, dE/dxyz; 2-wave chunks (75776 geometries), 3 streams)",
+                "api": "PackedModel.predict_host (pinned host xyz -> pinned host E, dE/dxyz; 2-wave chunks, 3 streams)",
                 "checksum": checksum},
     }
     if "kbuild" in extra:

@@ -14,6 +14,8 @@
 // whole pass over the training set, and the training set arrives pre-swizzled in fragment order
 // through a TMA bulk-copy ring in shared memory.  Energies and gradients come out of ONE pass (the
 // reference makes two and recomputes k_ij 3*Nat+1 times).
+#include <stdlib.h>
+
 #include "kreg_common.cuh"
 #include "kreg_internal.h"
 
@@ -130,12 +132,22 @@ __global__ void __launch_bounds__(32) pack_model_kernel(int nat, int64_t ntrain,
     }
   double *osc = o2x + 64 * sh.NT * (HAS_V ? 2 : 1);
   if (lane < 8) {
+    // scal[q][4] = { x(2q), s(2q), x(2q+1), s(2q+1) }:  s_j initialises the GEMM1 accumulator so that
+    // c1 * (s_j + X'_i.X'_j) + bias_i is the scaled exponent (no per-element add in the kernel).
+    //   gradient models: x_j = a'_j = alpha_j - X'_j.v_j/s^2,  s_j = -n_j/2
+    //   value models   : x_j = +0.0 / -0.0 (sign of alpha_j),  s_j = -n_j/2 + s^2 ln|alpha_j|  -> w_ij comes out of
+    //                    the exponential already multiplied by |alpha_j|; alpha_j = 0 (and padding) -> s_j = -1e300
     int64_t j = grp * 8 + lane;
     double a = (alpha && j < ntrain) ? alpha[j] : 0.0;
-    if (HAS_V) a -= xv[lane] * inv_s2;
-    if (j >= ntrain) a = 0.0;
-    osc[(lane >> 1) * 4 + (lane & 1) * 2 + 0] = a;
-    osc[(lane >> 1) * 4 + (lane & 1) * 2 + 1] = -0.5 * c1 * nj[lane];
+    double x, sj = -0.5 * nj[lane];
+    if (HAS_V) {
+      x = (j < ntrain) ? a - xv[lane] * inv_s2 : 0.0;
+    } else {
+      x = (a < 0.0) ? -0.0 : 0.0;
+      sj = (a != 0.0) ? sj + log(fabs(a)) / inv_s2 : -1e300;
+    }
+    osc[(lane >> 1) * 4 + (lane & 1) * 2 + 0] = x;
+    osc[(lane >> 1) * 4 + (lane & 1) * 2 + 1] = sj;
   }
 }
 
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
 }
 
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
-__global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs args) {
+__global__ void __launch_bounds__(kThreads, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
   constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
   extern __shared__ __align__(128) double smem[];
@@ -347,11 +359,13 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
     const int ng = min(GPS, args.ngroups - (stage0 + it) * GPS);
     for (int gi = 0; gi < ng; gi++) {
       const double *cb = ring + s * C::STAGE + gi * C::CHUNK;
-      // GEMM1: S = Xtest . Xtrain^T  (and S2 = Xtest . (V/s^2)^T)
+      // GEMM1: S = s_j + Xtest . Xtrain^T  (and S2 = Xtest . (V/s^2)^T); the accumulator starts from the column term
+      const double4 sc = *reinterpret_cast<const double4 *>(cb + C::OFF_SCAL + q * 4);
       double S[MT][2], S2[HAS_V ? MT : 1][2];
 #pragma unroll
       for (int mt = 0; mt < MT; mt++) {
-        S[mt][0] = S[mt][1] = 0.0;
+        S[mt][0] = sc.y;
+        S[mt][1] = sc.w;
         if (HAS_V) S2[mt][0] = S2[mt][1] = 0.0;
       }
 #pragma unroll
@@ -372,21 +386,21 @@ __global__ void __launch_bounds__(kThreads, 1) predict_kernel(const PredictArgs 
           }
         }
       }
-      // elementwise: k = exp(c1 (s - n_i/2 - n_j/2)), w = k (a'_j + S2)
-      const double4 sc = *reinterpret_cast<const double4 *>(cb + C::OFF_SCAL + q * 4);
+      // elementwise: k = exp(c1 S + bias_i); gradient models w = k (a'_j + S2); value models w = sign(alpha_j) k
+      // (|alpha_j| is inside the exponent), so no multiply at all
       double W[MT][2], Kf[HAS_V ? MT : 1][2];
 #pragma unroll
       for (int mt = 0; mt < MT; mt++) {
-        const double k0 = exp_from_scaled(fma(S[mt][0], c1, bi[mt] + sc.y), tab);
-        const double k1 = exp_from_scaled(fma(S[mt][1], c1, bi[mt] + sc.w), tab);
+        const double k0 = exp_from_scaled_cvt(fma(S[mt][0], c1, bi[mt]), tab);
+        const double k1 = exp_from_scaled_cvt(fma(S[mt][1], c1, bi[mt]), tab);
         if (HAS_V) {
           W[mt][0] = k0 * (sc.x + S2[mt][0]);
           W[mt][1] = k1 * (sc.z + S2[mt][1]);
           Kf[mt][0] = k0;
           Kf[mt][1] = k1;
         } else {
-          W[mt][0] = k0 * sc.x;
-          W[mt][1] = k1 * sc.z;
+          W[mt][0] = __hiloint2double(__double2hiint(k0) ^ __double2hiint(sc.x), __double2loint(k0));
+          W[mt][1] = __hiloint2double(__double2hiint(k1) ^ __double2hiint(sc.z), __double2loint(k1));
         }
       }
       if (!WANT_G) {
@@ -524,9 +538,10 @@ static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *w
                               size_t *need, cudaStream_t st) {
   constexpr TcShape sh(NAT);
   if constexpr (sh.D <= 36) {
-    // small molecules: test-row fragments live in registers, 4 (values) / 2 (gradient models) m-tiles per warp
-    return has_v ? launch_predict_cfg<NAT, 2, true, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st)
-                 : launch_predict_cfg<NAT, 4, false, false, 4, 4>(a, sms, ws, ws_bytes, query, need, st);
+    // small molecules: test-row fragments live in registers, 2 m-tiles per warp, two CTAs per SM (16 warps hide the
+    // fixed DMMA issue latency better than one CTA with 4 m-tiles per warp: 51.5 vs 53.7 ms on cfg2)
+    return has_v ? launch_predict_cfg<NAT, 2, true, false, 1, 3>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 2, false, false, 3, 3>(a, sms, ws, ws_bytes, query, need, st);
   } else if constexpr (sh.D <= 66) {
     return has_v ? launch_predict_cfg<NAT, 1, true, false, 1, 4>(a, sms, ws, ws_bytes, query, need, st)
                  : launch_predict_cfg<NAT, 2, false, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st);
@@ -541,7 +556,7 @@ static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *w
 template <int NAT>
 static int tile_rows_nat(bool has_v) {
   constexpr TcShape sh(NAT);
-  const int mt = sh.D <= 36 ? (has_v ? 2 : 4) : sh.D <= 66 ? (has_v ? 1 : 2) : 1;
+  const int mt = sh.D <= 36 ? 2 : sh.D <= 66 ? (has_v ? 1 : 2) : 1;
   return kWarps * mt * 8;
 }
 

@@ -227,7 +227,7 @@ class HostPredictor:
 
     def __init__(self, model: PackedModel, chunk: Optional[int] = None, nbuf: int = 3):
         if chunk is None:
-            chunk = 2 * model.wave_rows()  # whole waves per chunk: no partially filled last wave in every launch
+            chunk = 4 * model.wave_rows()  # whole waves per chunk (up to 2 CTAs per SM): no partially filled last wave
         self.model, self.chunk, self.nbuf = model, int(chunk), nbuf
         dev, nat = model.device, model.natoms
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
