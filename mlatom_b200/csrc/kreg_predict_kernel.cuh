@@ -1,0 +1,403 @@
+// kreg_predict_kernel.cuh -- the prediction kernel templates (see kreg_predict.cu for the algebra and the packed
+// model layout).  Included by kreg_predict_inst.cu, which is compiled once per range of molecule sizes so that the
+// per-Natoms instantiations build in parallel.
+#pragma once
+#include <stdlib.h>
+
+#include "kreg_common.cuh"
+#include "kreg_internal.h"
+#include "kreg_predict_args.h"
+
+namespace kreg {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+struct PredictCfg {
+  static constexpr TcShape sh = TcShape(NAT);
+  static constexpr int D = sh.D, KS = sh.KS, KS2 = sh.KS2, NT = sh.NT;
+  static constexpr int ROWS = kWarps * MT * 8;
+  static constexpr int TS = (NT * 8 > KS * 4 ? NT * 8 : KS * 4) + (A_IN_SMEM ? 4 : 0);  // +4: conflict-free A loads
+  static constexpr int CHUNK = sh.chunk_doubles(HAS_V);
+  static constexpr int STAGE = CHUNK * GPS;
+  static constexpr int OFF_B1V = 64 * KS2;
+  static constexpr int OFF_B2X = 64 * KS2 * (HAS_V ? 2 : 1);
+  static constexpr int OFF_B2V = OFF_B2X + 64 * NT;
+  static constexpr int OFF_SCAL = OFF_B2X + 64 * NT * (HAS_V ? 2 : 1);
+  // shared memory carve-up (in doubles)
+  static constexpr int SM_RING = 0;
+  static constexpr int SM_TILE = SM_RING + NSTAGE * STAGE;
+  static constexpr int SM_BIAS = SM_TILE + ROWS * TS;
+  static constexpr int SM_TAB = SM_BIAS + ROWS;
+  static constexpr int SM_BAR = SM_TAB + 64;
+  static constexpr int SM_DOUBLES = SM_BAR + 2 * NSTAGE;
+  static constexpr size_t SMEM_BYTES = (size_t)SM_DOUBLES * 8;
+};
+
+// Per-geometry epilogue: E = prior + A[D];  g = (A[:D] - X'_i A[D]) / s^2;  dE/dM = J_i^T g  (KREG.f90:121 Jacobian)
+template <int NAT, bool WANT_G>
+__device__ __forceinline__ void predict_row_epilogue(const PredictArgs &args, const double *y, int64_t p) {
+  constexpr int D = NAT * (NAT - 1) / 2;
+  const double esum = y[D];
+  if (args.E) args.E[p] = args.prior + esum;
+  if (WANT_G && args.G) {
+    const double *m = args.xyz + p * (NAT * 3);
+    double mm[NAT * 3], gr[NAT * 3];
+#pragma unroll
+    for (int i = 0; i < NAT * 3; i++) {
+      mm[i] = m[i];
+      gr[i] = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < NAT; a++)
+#pragma unroll
+      for (int b = a + 1; b < NAT; b++) {
+        const int d = pair_index(NAT, a, b);
+        const double r2 = rij2_exact(mm + 3 * a, mm + 3 * b);
+        const double x = __ldg(args.xeq + d) / sqrt(r2);
+        const double xc = x - __ldg(args.center + d);
+        const double gd = (y[d] - xc * esum) * args.inv_s2;
+        const double f = gd * x / r2;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const double dx = mm[3 * b + t] - mm[3 * a + t];
+          gr[3 * a + t] = fma(f, dx, gr[3 * a + t]);
+          gr[3 * b + t] = fma(-f, dx, gr[3 * b + t]);
+        }
+      }
+    double *out = args.G + p * (NAT * 3);
+#pragma unroll
+    for (int i = 0; i < NAT * 3; i++) out[i] = gr[i];
+  }
+}
+
+// Small-batch mode, second kernel: sum the slices' accumulators in slice order, then the usual epilogue.
+template <int NAT, int ROWS, int TS>
+__global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictArgs args) {
+  extern __shared__ __align__(16) double ftile[];  // [ROWS][TS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+  const size_t slice_stride = (size_t)gridDim.x * ROWS * TS;
+  for (int r = warp; r < ROWS; r += kWarps) {
+    if (row0 + r >= args.npoints) break;
+    const double *src = args.partial + ((size_t)blockIdx.x * ROWS + r) * TS;
+    for (int c = lane; c < TS; c += 32) {
+      double s = 0.0;
+      for (int sl = 0; sl < args.nslices; sl++) s += src[(size_t)sl * slice_stride + c];
+      ftile[r * TS + c] = s;
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < ROWS; r += kThreads) {
+    const int64_t p = row0 + r;
+    if (p < args.npoints) predict_row_epilogue<NAT, true>(args, ftile + r * TS, p);
+  }
+}
+
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
+__global__ void __launch_bounds__(kThreads, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+  constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
+  extern __shared__ __align__(128) double smem[];
+  double *ring = smem + C::SM_RING;
+  double *tile = smem + C::SM_TILE;
+  double *bias = smem + C::SM_BIAS;
+  double *tab = smem + C::SM_TAB;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + C::SM_BAR);
+  uint64_t *empty_bar = full_bar + NSTAGE;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int64_t row0 = (int64_t)blockIdx.x * C::ROWS;
+  const int all_stages = (args.ngroups + GPS - 1) / GPS;
+  const int stage0 = args.nslices > 1 ? (int)blockIdx.y * args.stages_per_slice : 0;  // first ring stage of this slice
+  const int total_stages = args.nslices > 1 ? min(args.stages_per_slice, all_stages - stage0) : all_stages;
+
+  // ---- barrier init + first TMA bulk copies (overlap with the descriptor prologue) ----
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kWarps);
+    }
+    mbar_fence_init();
+  }
+  fill_exp_table(tab, tid, kThreads);
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE && s < total_stages; s++) {
+      int ng = min(GPS, args.ngroups - (stage0 + s) * GPS);
+      unsigned bytes = (unsigned)(ng * C::CHUNK * 8);
+      mbar_arrive_expect_tx(&full_bar[s], bytes);
+      bulk_g2s(ring + s * C::STAGE, args.packed + (size_t)(stage0 + s) * C::STAGE, bytes, &full_bar[s]);
+    }
+  }
+
+  // ---- prologue: centred descriptors of this CTA's test rows -> shared tile ----
+  for (int r = tid; r < C::ROWS; r += kThreads) {
+    int64_t p = row0 + r;
+    if (p >= args.npoints) p = args.npoints - 1;  // duplicate a valid row; its results are not stored
+    const double *m = args.xyz + p * (NAT * 3);
+    double mm[NAT * 3];
+#pragma unroll
+    for (int i = 0; i < NAT * 3; i++) mm[i] = m[i];
+    double n = 0.0;
+#pragma unroll
+    for (int a = 0; a < NAT; a++)
+#pragma unroll
+      for (int b = a + 1; b < NAT; b++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int d = pair_index(NAT, a, b);
+        double x = __ldg(args.xeq + d) / sqrt(rij2_exact(mm + 3 * a, mm + 3 * b)) - __ldg(args.center + d);
+        tile[r * TS + d] = x;
+        n = fma(x, x, n);
+      }
+    for (int d = D; d < TS; d++) tile[r * TS + d] = 0.0;
+    bias[r] = -0.5 * args.c1 * n;
+  }
+  __syncthreads();
+
+  // ---- per-warp register state ----
+  double afrag[A_IN_SMEM ? 1 : MT][A_IN_SMEM ? 1 : KS];
+  double bi[MT];
+  double acc[WANT_G ? MT : 1][WANT_G ? NT : 1][2];  // GEMM2 accumulators (energy + gradient passes)
+  double esum[WANT_G ? 1 : MT];                      // energy-only passes: per-thread partial row sums of W
+  const double *arow[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) {
+    const int r = (warp * MT + mt) * 8 + g;
+    arow[mt] = tile + r * TS + q;
+    bi[mt] = bias[r];
+    if (!A_IN_SMEM) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) afrag[mt][ks] = arow[mt][4 * ks];
+    }
+    if (WANT_G) {
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) acc[WANT_G ? mt : 0][WANT_G ? nt : 0][0] = acc[WANT_G ? mt : 0][WANT_G ? nt : 0][1] = 0.0;
+    } else {
+      esum[WANT_G ? 0 : mt] = 0.0;
+    }
+  }
+  const double c1 = args.c1;
+
+  // ---- main loop over the training set ----
+  for (int it = 0; it < total_stages; it++) {
+    // producer duty: refill the stage every warp finished in the previous iteration
+    if (tid == 0 && it >= 1 && it - 1 + NSTAGE < total_stages) {
+      const int sp = (it - 1) % NSTAGE;
+      const int nxt = it - 1 + NSTAGE;
+      mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
+      int ng = min(GPS, args.ngroups - (stage0 + nxt) * GPS);
+      unsigned bytes = (unsigned)(ng * C::CHUNK * 8);
+      mbar_arrive_expect_tx(&full_bar[sp], bytes);
+      bulk_g2s(ring + sp * C::STAGE, args.packed + (size_t)(stage0 + nxt) * C::STAGE, bytes, &full_bar[sp]);
+    }
+    const int s = it % NSTAGE;
+    mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
+    const int ng = min(GPS, args.ngroups - (stage0 + it) * GPS);
+    for (int gi = 0; gi < ng; gi++) {
+      const double *cb = ring + s * C::STAGE + gi * C::CHUNK;
+      // GEMM1: S = s_j + Xtest . Xtrain^T  (and S2 = Xtest . (V/s^2)^T); the accumulator starts from the column term
+      const double4 sc = *reinterpret_cast<const double4 *>(cb + C::OFF_SCAL + q * 4);
+      double S[MT][2], S2[HAS_V ? MT : 1][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        S[mt][0] = sc.y;
+        S[mt][1] = sc.w;
+        if (HAS_V) S2[mt][0] = S2[mt][1] = 0.0;
+      }
+#pragma unroll
+      for (int p = 0; p < KS2; p++) {
+        const double2 bx = *reinterpret_cast<const double2 *>(cb + (p * 32 + lane) * 2);
+        double2 bv = make_double2(0.0, 0.0);
+        if (HAS_V) bv = *reinterpret_cast<const double2 *>(cb + C::OFF_B1V + (p * 32 + lane) * 2);
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int ks = 2 * p + e;
+          if (ks < KS) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+              const double a = A_IN_SMEM ? arow[mt][4 * ks] : afrag[A_IN_SMEM ? 0 : mt][A_IN_SMEM ? 0 : ks];
+              dmma884(S[mt], a, e ? bx.y : bx.x);
+              if (HAS_V) dmma884(S2[mt], a, e ? bv.y : bv.x);
+            }
+          }
+        }
+      }
+      // elementwise: k = exp(c1 S + bias_i); gradient models w = k (a'_j + S2); value models w = sign(alpha_j) k
+      // (|alpha_j| is inside the exponent), so no multiply at all
+      double W[MT][2], Kf[HAS_V ? MT : 1][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        const double k0 = exp_from_scaled_cvt(fma(S[mt][0], c1, bi[mt]), tab);
+        const double k1 = exp_from_scaled_cvt(fma(S[mt][1], c1, bi[mt]), tab);
+        if (HAS_V) {
+          W[mt][0] = k0 * (sc.x + S2[mt][0]);
+          W[mt][1] = k1 * (sc.z + S2[mt][1]);
+          Kf[mt][0] = k0;
+          Kf[mt][1] = k1;
+        } else {
+          W[mt][0] = __hiloint2double(__double2hiint(k0) ^ __double2hiint(sc.x), __double2loint(k0));
+          W[mt][1] = __hiloint2double(__double2hiint(k1) ^ __double2hiint(sc.z), __double2loint(k1));
+        }
+      }
+      if (!WANT_G) {
+        // energy only: E_i = sum_j w_ij needs no second GEMM, just the row sums of W
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) esum[WANT_G ? 0 : mt] += W[mt][0] + W[mt][1];
+        continue;
+      }
+      // GEMM2: acc += W . [Xtrain | 1]  (+ K . V)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        const double2 bx = *reinterpret_cast<const double2 *>(cb + C::OFF_B2X + (nt * 32 + lane) * 2);
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], W[mt][0], bx.x);
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], W[mt][1], bx.y);
+        if (HAS_V) {
+          const double2 bv = *reinterpret_cast<const double2 *>(cb + C::OFF_B2V + (nt * 32 + lane) * 2);
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], Kf[mt][0], bv.x);
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) dmma884(acc[WANT_G ? mt : 0][WANT_G ? nt : 0], Kf[mt][1], bv.y);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // ---- epilogue: accumulators -> shared tile, then one thread per test geometry ----
+  __syncthreads();
+  if (WANT_G) {
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      const int r = (warp * MT + mt) * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+        *reinterpret_cast<double2 *>(tile + r * TS + 8 * nt + 2 * q) =
+            make_double2(acc[WANT_G ? mt : 0][WANT_G ? nt : 0][0], acc[WANT_G ? mt : 0][WANT_G ? nt : 0][1]);
+    }
+  } else {
+    // the four lanes q = 0..3 of a row hold disjoint column subsets: fixed-order butterfly, lane q == 0 stores
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      double s = esum[WANT_G ? 0 : mt];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) tile[((warp * MT + mt) * 8 + g) * TS + D] = s;
+    }
+  }
+  __syncthreads();
+  if (WANT_G && args.nslices > 1) {
+    // small-batch mode: hand the raw accumulators of the valid rows to predict_finish_kernel
+    double *dst = args.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::ROWS * TS;
+    const int64_t left = args.npoints - row0;
+    const int nvalid = (int)(left < C::ROWS ? left : C::ROWS);
+    for (int e = tid; e < nvalid * TS; e += kThreads) dst[e] = tile[e];
+    return;
+  }
+  for (int r = tid; r < C::ROWS; r += kThreads) {
+    const int64_t p = row0 + r;
+    if (p < args.npoints) predict_row_epilogue<NAT, WANT_G>(args, tile + r * TS, p);
+  }
+}
+
+// ---- host-side dispatch -----------------------------------------------------------------------
+// Small batches (fewer CTAs than half the SMs) split the training set over gridDim.y slices so the whole chip works
+// on them: the single-geometry MD / geometry-optimisation step is latency-, not throughput-bound.
+template <int GPS>
+static void plan_slices(int ngroups, int64_t blocks, int sms, int *nslices, int *stages_per_slice) {
+  const int all_stages = (ngroups + GPS - 1) / GPS;
+  *nslices = 1;
+  *stages_per_slice = all_stages;
+  if (blocks * 2 > sms || all_stages < 8) return;
+  int want = (int)((2 * sms + blocks - 1) / blocks);  // ~2 CTAs per SM in total
+  int per = (all_stages + want - 1) / want;
+  if (per < 4) per = 4;                               // keep the TMA ring busy
+  *stages_per_slice = per;
+  *nslices = (all_stages + per - 1) / per;
+}
+
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
+static int launch_predict_g(PredictArgs a, cudaStream_t st) {
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G>;
+  static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+  KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+  const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
+  dim3 grid((unsigned)blocks, (unsigned)(a.nslices > 1 ? a.nslices : 1));
+  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(a);
+  KREG_LAUNCH_CHECK();
+  if (a.nslices > 1) {
+    auto fin = predict_finish_kernel<NAT, C::ROWS, C::TS>;
+    const size_t smem = (size_t)C::ROWS * C::TS * sizeof(double);
+    KREG_CUDA_TRY(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fin<<<(unsigned)blocks, kThreads, smem, st>>>(a);
+    KREG_LAUNCH_CHECK();
+  }
+  return KREG_OK;
+}
+
+// Workspace (bytes) the small-batch mode needs for this launch; 0 when the batch is large enough to run unsplit.
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+static size_t predict_ws_cfg(int ngroups, int64_t npoints, int sms, int *nslices, int *stages_per_slice) {
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+  const int64_t blocks = (npoints + C::ROWS - 1) / C::ROWS;
+  plan_slices<GPS>(ngroups, blocks, sms, nslices, stages_per_slice);
+  return *nslices > 1 ? (size_t)*nslices * blocks * C::ROWS * C::TS * sizeof(double) : 0;
+}
+
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+static int launch_predict_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes, bool query, size_t *need,
+                              cudaStream_t st) {
+  int nslices, per;
+  const size_t bytes = predict_ws_cfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>(a.ngroups, a.npoints, sms, &nslices, &per);
+  if (query) {
+    *need = bytes;
+    return KREG_OK;
+  }
+  a.nslices = 1;
+  a.stages_per_slice = 0;
+  a.partial = nullptr;
+  if (nslices > 1 && ws && ws_bytes >= bytes) {  // without a workspace the batch simply runs unsplit
+    a.nslices = nslices;
+    a.stages_per_slice = per;
+    a.partial = static_cast<double *>(ws);
+  }
+  // energy-only requests skip the second GEMM entirely (the split mode always carries the full accumulators)
+  return (a.G || a.nslices > 1) ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true>(a, st)
+                                : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false>(a, st);
+}
+
+template <int NAT>
+static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *ws, size_t ws_bytes, bool query,
+                              size_t *need, cudaStream_t st) {
+  constexpr TcShape sh(NAT);
+  if constexpr (sh.D <= 36) {
+    // small molecules: test-row fragments live in registers, 2 m-tiles per warp, two CTAs per SM (16 warps hide the
+    // fixed DMMA issue latency better than one CTA with 4 m-tiles per warp: 51.5 vs 53.7 ms on cfg2)
+    return has_v ? launch_predict_cfg<NAT, 2, true, false, 1, 3>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 2, false, false, 3, 3>(a, sms, ws, ws_bytes, query, need, st);
+  } else if constexpr (sh.D <= 66) {
+    return has_v ? launch_predict_cfg<NAT, 1, true, false, 1, 4>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 2, false, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st);
+  } else {
+    // large molecules: accumulators fill the register file; test-row fragments stay in shared memory
+    return has_v ? launch_predict_cfg<NAT, 1, true, true, 1, 2>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 1, false, true, 1, 3>(a, sms, ws, ws_bytes, query, need, st);
+  }
+}
+
+// test geometries handled by one CTA of the kernel launch_predict_nat<NAT> would pick
+template <int NAT>
+static int tile_rows_nat(bool has_v) {
+  constexpr TcShape sh(NAT);
+  const int mt = sh.D <= 36 ? 2 : sh.D <= 66 ? (has_v ? 1 : 2) : 1;
+  return kWarps * mt * 8;
+}
+
+}  // namespace kreg

@@ -277,6 +277,30 @@ def test_small_batch_latency_mode_vs_oracle(eng, oracle, nat, ntr, use_grads):
         assert (e_only - e).abs().max().item() <= 1e-12 * max(1.0, np.abs(sc).max())
 
 
+@pytest.mark.parametrize("nat", list(range(2, 22)))
+def test_every_supported_molecule_size(eng, oracle, nat):
+    """Natoms = 2..21 (KREG_MIN/MAX_NATOMS): K blocks and E/dE for a gradient-trained model against the oracle."""
+    ntr, nte = 11, 23
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
+    xeq = oracle.xeq(eq)
+    X, Xte = oracle.descriptors(xtr, xeq), oracle.descriptors(xte, xeq)
+    nv, ng = ntr, 3 * nat * ntr
+    sigma = 0.8 + 0.06 * nat
+    ref = oracle.kernel_matrix(xtr, X, sigma, nv, ng, factored=True)
+    k = eng.build_kernel_matrix(dev(xtr), dev(xeq), sigma, 0.0, 0.0, use_gradients=True).cpu().numpy()
+    assert np.abs(np.tril(k) - np.tril(ref)).max() <= K_RTOL * np.abs(ref).max()
+    alpha = np.random.default_rng(nat).standard_normal(nv + ng) * 0.3
+    v = oracle.precompute_v(xtr, X, alpha[nv:])
+    for use_g in (False, True):
+        a = alpha if use_g else alpha[:nv]
+        e_ref, g_ref, sc = oracle.predict_factored(X, alpha[:nv], v if use_g else None, sigma, 1.0, xte, Xte, want_scale=True)
+        model = eng.PackedModel.from_training_set(dev(xtr), dev(xeq), dev(a), sigma, 1.0, nv, ng if use_g else 0)
+        e, g = model.predict(dev(xte))
+        assert np.all(np.abs(e.cpu().numpy() - e_ref) <= 1e-13 * np.maximum(sc, 1.0) + E_RTOL * np.abs(e_ref))
+        assert np.abs(g.cpu().numpy() - g_ref).max() <= G_TOL * max(1.0, np.abs(g_ref).max())
+
+
 def test_edge_cases(eng):
     nat = 9
     eq = S.equilibrium(nat)
