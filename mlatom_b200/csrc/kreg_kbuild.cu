@@ -288,6 +288,7 @@ struct GradArgs {
   int64_t row_begin, row_end;  // absolute row range of K to produce
   double *K;
   int64_t ldk;
+  double *P;             // [ntr][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
 };
 
 // E(a,c)[t] = X_d (x_c - x_a)_t / R^2   (KREG.f90:121)
@@ -312,139 +313,243 @@ __global__ void __launch_bounds__(128) jacobian_rows_kernel(int nat, int64_t n, 
   }
 }
 
+// The gradient-augmented blocks are produced by two kernels so that the store kernel has NO per-pair prologue:
+//   pair_terms_kernel : per geometry pair (i, j): k_ij/s^2 and u_i^(j) = J_i^T (X_j - X_i)  -> workspace P[i][j][PW]
+//                       (PW = 3 Nat + 1 doubles, 4 % of the bytes of the block it describes); also emits the
+//                       value-gradient rows.
+//   grad_emit_kernel  : CTA = ONE geometry i x TJ geometries j, thread = matrix column (j, b, u); one round of global
+//                       loads, one barrier, then 3 Nat stores per thread.  Small, short-lived CTAs (4 per SM) write
+//                       flat 3 Nat-row strips -- the schedule that measured fastest for this layout
+//                       (profiles/r01_store_pattern.txt).
 template <int NAT>
 struct GradCfg {
   static constexpr int G3 = 3 * NAT;
+  static constexpr int G3P = (G3 + 1) & ~1;   // E_i rows padded to an even length
+  static constexpr int PW = (G3 + 3) & ~1;    // doubles per pair in the workspace: [k/s^2, pad, u_i[0..G3)] (+pad)
   static constexpr int D = NAT * (NAT - 1) / 2;
-  static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);  // geometries j per CTA
-  static constexpr int TI = NAT <= 12 ? 8 : 4;                                      // geometries i per CTA
+  static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);  // geometries j per emit CTA
   static constexpr int COLS = TJ * G3;
   static constexpr int THREADS = ((COLS + 31) / 32) * 32;
-  // shared memory carve-up (doubles)
-  static constexpr int SM_EI = 0;                         // [TI][NAT*NAT*3]
-  static constexpr int SM_XI = SM_EI + TI * NAT * NAT * 3;  // [TI][D]
-  static constexpr int SM_DLT = SM_XI + TI * D;           // [TI][TJ][D]   X_j - X_i
-  static constexpr int SM_UI = SM_DLT + TI * TJ * D;      // [TI][TJ][G3]  J_i^T (X_j - X_i)
-  static constexpr int SM_KS = SM_UI + TI * TJ * G3;      // [TI][TJ]      k_ij / sigma^2
-  static constexpr int SM_TAB = SM_KS + TI * TJ;          // [64]
-  static constexpr int SM_DOUBLES = SM_TAB + 64;
+  static constexpr int JT = 64;               // geometries j per pair-terms CTA
+  static constexpr int NJB = 8;               // steps (of TJ geometries) walked by one emit CTA
 };
 
-// One CTA = TI geometries i (3 Nat rows each) x TJ geometries j (3 Nat columns each).  Thread = one matrix
-// column (j, b, u): it keeps E_j(b, .)[u] in registers, and for every i walks the 3 Nat rows, so each store
-// instruction of a warp covers 32 consecutive doubles of one matrix row.
 template <int NAT>
-__global__ void __launch_bounds__(GradCfg<NAT>::THREADS) grad_blocks_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
-  constexpr int G3 = C::G3, D = C::D, TJ = C::TJ, TI = C::TI, NN3 = NAT * NAT * 3;
-  extern __shared__ __align__(16) double gsm[];
-  double *Ei = gsm + C::SM_EI, *Xi = gsm + C::SM_XI, *dlt = gsm + C::SM_DLT, *ui = gsm + C::SM_UI;
-  double *ks = gsm + C::SM_KS, *tab = gsm + C::SM_TAB;
+  constexpr int G3 = C::G3, PW = C::PW, D = C::D, JT = C::JT, DP = D | 1;  // odd row stride: conflict-free columns
+  extern __shared__ __align__(16) double psm[];
+  double *Ei = psm;                    // [NAT*NAT*3]  E_i(a,c)[t]
+  double *Xi = Ei + NAT * NAT * 3;     // [D]
+  double *Dl = Xi + ((D + 1) & ~1);    // [JT][DP]     X_j - X_i
+  double *Us = Dl + JT * DP;           // [JT][PW]     k/s^2, u_i^(j)
+  double *tab = Us + JT * PW;          // [64]
 
-  const int64_t ib = (int64_t)blockIdx.y * TI;   // first geometry i
-  const int64_t jb = (int64_t)blockIdx.x * TJ;   // first geometry j
-  const int ni = (int)((a.ntr - ib) < TI ? (a.ntr - ib) : TI);
-  const int nj = (int)((a.ntr - jb) < TJ ? (a.ntr - jb) : TJ);
-  const int64_t row0 = a.nv + ib * G3;
-  if (row0 + (int64_t)ni * G3 <= a.row_begin || row0 >= a.row_end) return;
+  const int64_t i = blockIdx.y;
+  const int64_t rbase = a.nv + i * G3;
+  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
   const bool full = a.fill == KREG_FILL_FULL;
-  const bool need_gg = full || jb <= ib + ni - 1;  // some (i, j) of the block has j <= i
-  if (!need_gg && a.nv == 0) return;
-
+  const int64_t jend = (a.nv || full) ? a.ntr : i + 1;  // value-gradient rows need every j
+  const int64_t j0 = (int64_t)blockIdx.x * JT;
+  if (j0 >= jend) return;
+  const int nj = (int)(jend - j0 < JT ? jend - j0 : JT);
   const int tid = threadIdx.x;
-  const int jl = tid / G3, col = tid % G3;  // this thread's column (j, b, u)
-  const int b = col / 3, u = col % 3;
-  const int64_t j = jb + jl;
-  const bool active = tid < C::COLS && jl < nj;
 
-  fill_exp_table(tab, tid, C::THREADS);
-  for (int e = tid; e < ni * NN3; e += C::THREADS) Ei[e] = a.E[ib * NN3 + e];
-  for (int e = tid; e < ni * D; e += C::THREADS) Xi[e] = a.Xc[(ib + e / D) * a.XS + e % D];
+  fill_exp_table(tab, tid, 256);
+  for (int e = tid; e < NAT * NAT * 3; e += 256) Ei[e] = a.E[i * (NAT * NAT * 3) + e];
+  for (int e = tid; e < D; e += 256) Xi[e] = a.Xc[i * a.XS + e];
   __syncthreads();
-  for (int e = tid; e < ni * TJ * D; e += C::THREADS) {
-    const int il = e / (TJ * D), r = e % (TJ * D), jj = r / D, d = r % D;
-    dlt[e] = (jj < nj) ? a.Xc[(jb + jj) * a.XS + d] - Xi[il * D + d] : 0.0;
+  for (int e = tid; e < nj * D; e += 256) {
+    const int jj = e / D, d = e % D;
+    Dl[jj * DP + d] = a.Xc[(j0 + jj) * a.XS + d] - Xi[d];
   }
   __syncthreads();
-  for (int p = tid; p < ni * TJ; p += C::THREADS) {
-    const int il = p / TJ, jj = p % TJ;
-    double k = 0.0;
-    if (jj < nj) {
-      const double *dd = dlt + p * D;
-      double d2 = 0.0;
-      for (int d = 0; d < D; d++) d2 = fma(dd[d], dd[d], d2);
-      k = (jb + jj == ib + il) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
-    }
-    ks[p] = k * a.inv_s2;
-  }
-  double ej[NAT];  // E_j(b,c)[u] for all c (0 at c == b)
-  if (active) {
-#pragma unroll
-    for (int c = 0; c < NAT; c++) ej[c] = a.E[(j * NAT * NAT + b * NAT + c) * 3 + u];
-    // u_i^{(j)}[(b,u)] = sum_c E_i(b,c)[u] * D_ij[d_bc] for every i of the block
-    for (int il = 0; il < ni; il++) {
-      const double *dd = dlt + (il * TJ + jl) * D;
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < NAT; c++)
-        if (c != b) s = fma(Ei[il * NN3 + (b * NAT + c) * 3 + u], dd[pair_index(NAT, b < c ? b : c, b < c ? c : b)], s);
-      ui[(il * TJ + jl) * G3 + col] = s;
+  {  // k_ij / s^2: four lanes per pair (JT * 4 == blockDim: every lane takes part in the shuffles)
+    const int jj = tid >> 2, sub = tid & 3;
+    const double *dd = Dl + (jj < nj ? jj : 0) * DP;
+    double d2 = 0.0;
+    for (int d = sub; d < D; d += 4) d2 = fma(dd[d], dd[d], d2);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
+    if (sub == 0 && jj < nj) {
+      const double k = (j0 + jj == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
+      Us[jj * PW] = k * a.inv_s2;
+      Us[jj * PW + 1] = 0.0;
     }
   }
+  // u_i^(j)[(a,t)] = sum_c E_i(a,c)[t] D_j[d_ac]: thread = (j, atom a) produces the three components t, reading each
+  // D_j[d_ac] once (conflict-free columns, odd stride) and E_i(a, .)[.] as warp-wide broadcasts
+  for (int e = tid; e < JT * NAT; e += 256) {
+    const int aa = e / JT, jj = e % JT;
+    if (jj >= nj) continue;
+    const double *dd = Dl + jj * DP;
+    const double *ea = Ei + aa * NAT * 3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < NAT; c++)
+      if (c != aa) {
+        const double dl = dd[pair_index(NAT, aa < c ? aa : c, aa < c ? c : aa)];
+        s0 = fma(ea[c * 3 + 0], dl, s0);
+        s1 = fma(ea[c * 3 + 1], dl, s1);
+        s2 = fma(ea[c * 3 + 2], dl, s2);
+      }
+    double *out = Us + jj * PW + 2 + aa * 3;
+    out[0] = s0;
+    out[1] = s1;
+    out[2] = s2;
+  }
   __syncthreads();
-
-  // value-gradient block: K[row_i + q][j] = (k/s^2) (J_i^T (X_j - X_i))_q.  Re-map threads so consecutive threads
-  // write consecutive j of one row.
+  // pair terms -> workspace (coalesced)
+  double *P = a.P + (i * a.ntr + j0) * PW;
+  for (int e = tid; e < nj * PW; e += 256) P[e] = Us[e];
+  // value-gradient rows: K[rbase + q][j] = (k/s^2) u_i^(j)[q], consecutive threads -> consecutive j
   if (a.nv) {
-    for (int e = tid; e < ni * G3 * TJ; e += C::THREADS) {
-      const int il = e / (G3 * TJ), r = e % (G3 * TJ), q = r / TJ, jj = r % TJ;
-      if (jj < nj) {
-        const int64_t row = row0 + (int64_t)il * G3 + q;
-        if (row >= a.row_begin && row < a.row_end) {
-          const double v = ks[il * TJ + jj] * ui[(il * TJ + jj) * G3 + q];
-          a.K[row * a.ldk + jb + jj] = v;
-          if (full) a.K[(jb + jj) * a.ldk + row] = v;
-        }
+    for (int e = tid; e < G3 * JT; e += 256) {
+      const int q = e / JT, jj = e % JT;
+      const int64_t row = rbase + q;
+      if (jj < nj && row >= a.row_begin && row < a.row_end) {
+        const double v = Us[jj * PW] * Us[jj * PW + 2 + q];
+        a.K[row * a.ldk + j0 + jj] = v;
+        if (full) a.K[(j0 + jj) * a.ldk + row] = v;
       }
     }
   }
-  if (!need_gg || !active) return;
+}
 
-  // gradient-gradient blocks
-  for (int il = 0; il < ni; il++) {
-    const int64_t i = ib + il;
-    if (!full && j > i) continue;
-    const double *dd = dlt + (il * TJ + jl) * D;
-    double sj = 0.0;
+// CTA = ONE geometry i x up to NJB*TJ geometries j, walked TJ at a time; thread = matrix column (j, b, u) of the current
+// step.  This thread's 3 Nat values E_i(b, .)[.] live in registers for the whole strip; per step the pair terms, the X_j
+// rows and the E_j blocks arrive by cp.async into the other shared buffer while the current step's 3 Nat stores are
+// issued.  One barrier per step; shared-memory reads are 16-byte wide where the layout allows.
+template <int NAT>
+struct EmitSmem {
+  using C = GradCfg<NAT>;
+  static constexpr int DS = (C::D + 1) & ~1;
+  static constexpr int EJ = NAT * NAT * 3 + ((NAT * NAT * 3) & 1);  // one E_j block, padded to an even length
+  static constexpr int OFF_P = 0;                                    // [2][TJ*PW]
+  static constexpr int OFF_X = OFF_P + 2 * C::TJ * C::PW;            // [2][TJ*DS]
+  static constexpr int OFF_E = OFF_X + 2 * C::TJ * DS;               // [2][TJ*EJ]
+  static constexpr int OFF_XI = OFF_E + 2 * C::TJ * EJ;              // [DS]
+  static constexpr int DOUBLES = OFF_XI + DS;
+};
+
+template <int NAT>
+__global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) grad_emit_kernel(const GradArgs a) {
+  using C = GradCfg<NAT>;
+  using SM = EmitSmem<NAT>;
+  constexpr int G3 = C::G3, G3P = C::G3P, PW = C::PW, TJ = C::TJ, NJB = C::NJB, D = C::D, DS = SM::DS, EJ = SM::EJ;
+  extern __shared__ __align__(16) double esm[];
+  double *Pb = esm + SM::OFF_P, *Xj = esm + SM::OFF_X, *Ejs = esm + SM::OFF_E, *Xi = esm + SM::OFF_XI;
+
+  const int64_t i = blockIdx.y;
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t jend = full ? a.ntr : i + 1;
+  const int64_t jb0 = (int64_t)blockIdx.x * (NJB * TJ);
+  if (jb0 >= jend) return;
+  const int64_t rbase = a.nv + i * G3;
+  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
+  const int nsteps = (int)(((jend - jb0 < NJB * TJ ? jend - jb0 : NJB * TJ) + TJ - 1) / TJ);
+
+  const int tid = threadIdx.x;
+  const int jl = tid / G3, col = tid % G3;
+  const int b = col / 3, u = col % 3;
+  const bool colthread = tid < C::COLS;
+  const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
+  const int64_t ld = a.ldk;
+
+  auto prefetch = [&](int n) {
+    const int64_t jb = jb0 + (int64_t)n * TJ;
+    const int npair = (int)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
+    const int buf = n & 1;
+    // pair terms: TJ * PW contiguous doubles (pairs past the end of the set read as zero -> k = 0)
+    const double *P = a.P + (i * a.ntr + jb) * PW;
+    for (int e = tid; e < TJ * PW / 2; e += C::THREADS)
+      cp_async16(Pb + buf * TJ * PW + 2 * e, P + (2 * e < npair * PW ? 2 * e : 0), 2 * e < npair * PW);
+    // X_j rows (XS is a multiple of 4 doubles: every 16-byte piece is aligned)
+    for (int e = tid; e < TJ * (DS / 2); e += C::THREADS) {
+      const int jj = e / (DS / 2), c2i = e % (DS / 2);
+      const bool ok = jj < npair && 2 * c2i < a.XS;
+      cp_async16(Xj + buf * TJ * DS + jj * DS + 2 * c2i, a.Xc + (ok ? (jb + jj) * a.XS + 2 * c2i : 0), ok);
+    }
+    // E_j blocks: the TJ blocks are contiguous in global memory (NAT*NAT*3 doubles each); 8-byte pieces because an
+    // odd block length breaks 16-byte alignment
+    for (int e = tid; e < TJ * NAT * NAT * 3; e += C::THREADS) {
+      const int jj = e / (NAT * NAT * 3), r = e % (NAT * NAT * 3);
+      const bool ok = jj < npair;
+      const unsigned sz = ok ? 8u : 0u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(Ejs + buf * TJ * EJ + jj * EJ + r)),
+                   "l"(a.E + (ok ? (jb + jj) * (NAT * NAT * 3) + r : 0)), "r"(sz)
+                   : "memory");
+    }
+    cp_async_commit();
+  };
+
+  for (int e = tid; e < D; e += C::THREADS) Xi[e] = a.Xc[i * a.XS + e];
+  prefetch(0);
+  double e27[G3P];  // E_i(b, c)[t] for all (c, t);  E_i(a, b)[t] = -E_i(b, a)[t]
+  if (colthread) {
+#pragma unroll
+    for (int z = 0; z < G3; z++) e27[z] = a.E[(i * NAT * NAT + (int64_t)b * NAT) * 3 + z];
+  }
+
+  for (int n = 0; n < nsteps; n++) {
+    cp_async_wait_all();
+    __syncthreads();  // step n's operands (and, for n = 0, X_i) are visible; everyone left buffer (n+1)&1
+    if (n + 1 < nsteps) prefetch(n + 1);
+    const int64_t j = jb0 + (int64_t)n * TJ + jl;
+    if (!colthread || j >= jend) continue;
+    const int buf = n & 1;
+    const double *pb = Pb + buf * TJ * PW + jl * PW;
+    const double *xj = Xj + buf * TJ * DS + jl * DS;
+    const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * NAT * 3 + u;  // E_j(b, c)[u] at ejb[3c]
+    double nej[NAT];
+#pragma unroll
+    for (int c = 0; c < NAT; c++) nej[c] = -ejb[3 * c];
+    const double kj = pb[0];
+    double sj = 0.0;  // -u_j[col] = -sum_c E_j(b,c)[u] (X_j - X_i)[d_bc]
 #pragma unroll
     for (int c = 0; c < NAT; c++)
-      if (c != b) sj = fma(ej[c], dd[pair_index(NAT, b < c ? b : c, b < c ? c : b)], sj);
-    const double ujs = sj * a.inv_s2;  // u_j[col] / sigma^2
-    const double kj = ks[il * TJ + jl];
-    const double *E = Ei + il * NN3;
-    const double *uu = ui + (il * TJ + jl) * G3;
-    // diagonal 3x3 block (a == b): sum_c E_i(b,c)[t] E_j(b,c)[u], hoisted out of the row loop so that the loop
-    // below is branch-free (E(b,b) = 0 makes the generic product vanish there)
-    double jd[3];
+      if (c != b) {
+        const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
+        sj = fma(nej[c], xj[d] - Xi[d], sj);
+      }
+    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+    double kjd[3];  // diagonal 3x3 block (a == b): (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u]
 #pragma unroll
     for (int t = 0; t < 3; t++) {
       double acc = 0.0;
 #pragma unroll
-      for (int c = 0; c < NAT; c++) acc = fma(E[(b * NAT + c) * 3 + t], ej[c], acc);
-      jd[t] = acc;
+      for (int c = 0; c < NAT; c++) acc = fma(e27[c * 3 + t], nej[c], acc);
+      kjd[t] = -acc * kj;
     }
-    const int64_t rbase = row0 + (int64_t)il * G3;
-    double *dst = a.K + rbase * a.ldk + a.nv + j * G3 + col;
+    const double2 *u2 = reinterpret_cast<const double2 *>(pb + 2);
+    double *dst = a.K + rbase * ld + a.nv + j * G3 + col;
+    if (interior && j != i) {
+      // the common case: (k/s^2) [ E_i(a,b)[t] E_j(b,a)[u] - u_i[q] u_j[col] / s^2 ]
 #pragma unroll
-    for (int aa = 0; aa < NAT; aa++) {
+      for (int q2 = 0; q2 < G3P / 2; q2++) {
+        const double2 uq = u2[q2];
 #pragma unroll
-      for (int t = 0; t < 3; t++) {
-        const int q = aa * 3 + t;
-        const double jj = fma(E[(aa * NAT + b) * 3 + t], ej[aa], aa == b ? jd[t] : 0.0);  // E_i(a,b)[t] E_j(b,a)[u]
-        double v = kj * fma(-uu[q], ujs, jj);
+        for (int h = 0; h < 2; h++) {
+          const int q = 2 * q2 + h;
+          if (q < G3) {
+            const int aa = q / 3, t = q % 3;
+            double v = fma(h ? uq.y : uq.x, c2, kj * (e27[q] * nej[aa]));
+            if (aa == b) v += kjd[t];
+            *dst = v;
+            dst += ld;
+          }
+        }
+      }
+    } else {
+      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal; operands re-read
+      const double *eig = a.E + (i * NAT * NAT + (int64_t)b * NAT) * 3;
+#pragma unroll 1
+      for (int q = 0; q < G3; q++) {
+        const int aa = q / 3, t = q % 3;
+        double v = fma(pb[2 + q], c2, kj * (eig[q] * -ejb[3 * aa]));
+        if (aa == b) v += (t == 0 ? kjd[0] : t == 1 ? kjd[1] : kjd[2]);
         if (j == i && q == col) v += a.lambdag;
         const int64_t r = rbase + q;
-        if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * a.ldk] = v;
+        if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * ld] = v;
       }
     }
   }
@@ -453,11 +558,20 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS) grad_blocks_kernel(cons
 template <int NAT>
 static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
   using C = GradCfg<NAT>;
-  auto kern = grad_blocks_kernel<NAT>;
-  const size_t smem = (size_t)C::SM_DOUBLES * sizeof(double);
-  KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((a.ntr + C::TJ - 1) / C::TJ), (unsigned)((a.ntr + C::TI - 1) / C::TI));
-  kern<<<grid, C::THREADS, smem, st>>>(a);
+  {
+    auto kern = pair_terms_kernel<NAT>;
+    constexpr int DP = C::D | 1;
+    const size_t smem = (size_t)(NAT * NAT * 3 + ((C::D + 1) & ~1) + C::JT * DP + C::JT * C::PW + 64) * sizeof(double);
+    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((a.ntr + C::JT - 1) / C::JT), (unsigned)a.ntr);
+    kern<<<grid, 256, smem, st>>>(a);
+    KREG_LAUNCH_CHECK();
+  }
+  dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)a.ntr);
+  auto emit = grad_emit_kernel<NAT>;
+  const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
+  KREG_CUDA_TRY(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+  emit<<<grid, C::THREADS, esmem, st>>>(a);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
@@ -478,7 +592,7 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
 
 // workspace carve-up helpers ---------------------------------------------------------------
 struct BuildWs {
-  size_t off_center, off_X, off_bias, off_E, total;
+  size_t off_center, off_X, off_bias, off_E, off_P, total;
   int XS, KC, nchunks;
 };
 
@@ -497,6 +611,7 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
   w.off_X = take((size_t)n * w.XS);
   w.off_bias = take((size_t)n);
   w.off_E = with_grad ? take((size_t)n * nat * nat * 3) : off;
+  w.off_P = with_grad ? take((size_t)n * n * ((3 * nat + 3) & ~1)) : off;
   w.total = off;
   return w;
 }
@@ -586,6 +701,7 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     g.row_end = row_end;
     g.K = K;
     g.ldk = ldk;
+    g.P = reinterpret_cast<double *>(ws + w.off_P);
     rc = launch_grad(natoms, g, st);
     if (rc) return rc;
   }
