@@ -277,3 +277,48 @@ class HostPredictor:
             start.wait_stream(self.s_k)
             start.wait_stream(self.s_in)
         return out_e, out_g
+
+
+class GraphPredictor:
+    """Fixed-shape prediction captured ONCE in a CUDA graph (pinned-host xyz -> device -> kernels -> pinned-host E, G).
+
+    For the loops that call ``predict`` on the same number of geometries every step -- molecular dynamics
+    (mlatom/md.py:169,198: one geometry per step; md_parallel.py:168,194: one batch per step) and geometry
+    optimisation -- replaying the graph removes the per-call launch and Python overhead of the four operations.
+    """
+
+    def __init__(self, model: PackedModel, n: int, energy: bool = True, gradient: bool = True):
+        self.model, self.n, self.energy, self.gradient = model, int(n), energy, gradient
+        dev, nat = model.device, model.natoms
+        self.x_host = torch.zeros((n, nat, 3), dtype=F64).pin_memory()
+        self.e_host = torch.zeros(n, dtype=F64).pin_memory()
+        self.g_host = torch.zeros((n, nat, 3), dtype=F64).pin_memory()
+        self.x = torch.zeros((n, nat, 3), dtype=F64, device=dev)
+        self.e = torch.zeros(n, dtype=F64, device=dev)
+        self.g = torch.zeros((n, nat, 3), dtype=F64, device=dev)
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside capture: allocates the small-batch workspace, sets attributes
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+
+    def _body(self):
+        self.x.copy_(self.x_host, non_blocking=True)
+        self.model.predict(self.x, self.energy, self.gradient, out_e=self.e, out_g=self.g)
+        if self.energy:
+            self.e_host.copy_(self.e, non_blocking=True)
+        if self.gradient:
+            self.g_host.copy_(self.g, non_blocking=True)
+
+    def __call__(self, xyz: np.ndarray):
+        """xyz (n, Nat, 3) numpy -> (E (n,), dE/dxyz (n, Nat, 3)) numpy views of the pinned result buffers."""
+        self.x_host.numpy()[...] = xyz
+        self.graph.replay()
+        torch.cuda.current_stream(self.model.device).synchronize()
+        return (self.e_host.numpy() if self.energy else None), (self.g_host.numpy() if self.gradient else None)

@@ -73,6 +73,8 @@ class KREG_API:
         self.Ytrain = None
         self.nthreads = None  # accepted and ignored: there are no host threads on the path
         self._model = None    # engine.PackedModel, device resident
+        self._graphs = {}     # (n, want_E, want_G) -> engine.GraphPredictor for small fixed-shape batches
+        self.graph_batch_limit = 64
 
     # -- helpers ----------------------------------------------------------------------------
     def _dev(self):
@@ -182,7 +184,17 @@ class KREG_API:
         model = self._ensure_model()
         if torch.is_tensor(xyz) and xyz.is_cuda:
             return model.predict(xyz.to(torch.float64).contiguous(), calculate_energy, calculate_energy_gradients)
-        e, g = model.predict_host(np.asarray(xyz, dtype=np.float64), calculate_energy, calculate_energy_gradients)
+        xyz = np.asarray(xyz, dtype=np.float64)
+        n = xyz.shape[0]
+        if 0 < n <= self.graph_batch_limit:
+            # MD / geometry optimisation: the same small batch shape every step -> replay a captured CUDA graph
+            key = (n, bool(calculate_energy), bool(calculate_energy_gradients))
+            gp = self._graphs.get(key)
+            if gp is None or gp.model is not model:
+                gp = self._graphs[key] = engine.GraphPredictor(model, n, calculate_energy, calculate_energy_gradients)
+            e, g = gp(xyz)
+            return (None if e is None else e.copy()), (None if g is None else g.copy())
+        e, g = model.predict_host(xyz, calculate_energy, calculate_energy_gradients)
         torch.cuda.synchronize(model.device)
         return (None if e is None else e.numpy()), (None if g is None else g.numpy())
 
@@ -219,6 +231,7 @@ class KREG_API:
             for key in model.files:
                 self.__dict__[key] = model[key]
         self._model = None
+        self._graphs = {}
 
     def clean_up(self):
         dev = self.device

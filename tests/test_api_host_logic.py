@@ -60,6 +60,15 @@ def fake_engine(monkeypatch, oracle):
         a = a + np.tril(a, -1).T
         return torch.from_numpy(cho_solve(cho_factor(a), y.numpy()))
 
+    class FakeGraph:
+        def __init__(self, model, n, energy=True, gradient=True):
+            self.model, self.energy, self.gradient = model, energy, gradient
+
+        def __call__(self, xyz):
+            e, g = self.model.predict_host(xyz, self.energy, self.gradient)
+            return (None if e is None else e.numpy()), (None if g is None else g.numpy())
+
+    monkeypatch.setattr(eng, "GraphPredictor", FakeGraph)
     monkeypatch.setattr(eng, "build_kernel_matrix", build)
     monkeypatch.setattr(eng, "solve", solve)
     monkeypatch.setattr(eng.PackedModel, "from_training_set",

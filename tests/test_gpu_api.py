@@ -119,3 +119,28 @@ def test_indefinite_system_falls_back_instead_of_dying(M, tmp_path):
         model.train(molecular_database=db, property_to_learn="energy")
     assert any("not positive definite" in str(x.message) for x in w)
     assert np.isfinite(model.kreg_api.alpha).all()
+
+
+def test_graph_predictor_matches_direct_path(M):
+    """CUDA-graph replay for fixed small batches (the MD step): same numbers as the direct call, also through the
+    molecule API where KREG_API caches one graph per batch shape."""
+    from mlatom_b200 import engine
+
+    db, xyz, e, g = make_db(9, 120, 1)
+    model = M.kreg(hyperparameters={"sigma": 1.0, "lambda": 1e-6})
+    model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients",
+                save_model=False)
+    pm = model.kreg_api._ensure_model()
+    xte = S.geometries(S.equilibrium(9), 5, 7)
+    e_ref, g_ref = pm.predict(torch.from_numpy(xte).cuda())
+    gp = engine.GraphPredictor(pm, 5)
+    for _ in range(3):
+        e1, g1 = gp(xte)
+        assert np.array_equal(e1, e_ref.cpu().numpy()) and np.array_equal(g1, g_ref.cpu().numpy())
+    # through the public API, one molecule at a time (md.py:198)
+    for k in range(3):
+        mol = D.molecule.from_arrays(S.atomic_numbers(9), xte[k])
+        model.predict(molecule=mol, calculate_energy=True, calculate_energy_gradients=True)
+        e_one, g_one = pm.predict(torch.from_numpy(xte[k:k + 1]).cuda())
+        assert mol.energy == e_one.item() and np.array_equal(mol.get_energy_gradients(), g_one[0].cpu().numpy())
+    assert len(model.kreg_api._graphs) == 1

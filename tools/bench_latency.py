@@ -27,5 +27,13 @@ for n in (1, 8, 64, 512, 4096, 18944):
     for _ in range(200):
         e, g = model.predict(x); e[0].item()
     sync_us = (time.perf_counter() - t0) / 200 * 1e6
-    out[n] = {"device_us": round(back_to_back_us, 1), "call_plus_readback_us": round(sync_us, 1)}
+    rec = {"device_us": round(back_to_back_us, 1), "call_plus_readback_us": round(sync_us, 1)}
+    if n <= 512:
+        gp = engine.GraphPredictor(model, n)
+        xh = x.cpu().numpy()
+        for _ in range(20): gp(xh)
+        t0 = time.perf_counter()
+        for _ in range(500): gp(xh)
+        rec["graph_host_to_host_us"] = round((time.perf_counter() - t0) / 500 * 1e6, 1)
+    out[n] = rec
 print(json.dumps({"natoms": nat, "ntrain": ntr, "latency_by_batch": out}))
