@@ -138,6 +138,12 @@ int kreg_pack_model(int natoms, int64_t ntrain, const double *xyz_train, const d
                     const double *alpha_val, const double *V, double sigma, double *center,
                     void *packed, size_t packed_bytes, void *stream);
 
+/* Same as kreg_pack_model for a model that carries its training DESCRIPTORS X_train[ntrain][D] but no Cartesian
+ * coordinates -- MLatomF's values-only .unf model files store exactly that (MLmodel.f90:880-886). */
+int kreg_pack_model_x(int natoms, int64_t ntrain, const double *X_train, const double *alpha_val,
+                      const double *V, double sigma, double *center, void *packed, size_t packed_bytes,
+                      void *stream);
+
 /* Scratch bytes kreg_predict can use for a batch of `npoints` geometries: small batches (fewer CTAs than half the
  * SMs -- the single-geometry MD / geometry-optimisation step) split the training set across the chip and reduce
  * the partial sums in a fixed order.  0 for batches large enough to fill the device. */

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(32) pack_model_kernel(int nat, int64_t ntrain,
                                                         const double *__restrict__ center,
                                                         const double *__restrict__ alpha,
                                                         const double *__restrict__ V, double c1, double inv_s2,
-                                                        double *__restrict__ packed) {
+                                                        double *__restrict__ packed,
+                                                        const double *__restrict__ Xin /* optional [ntrain][D] */) {
   extern __shared__ double sm[];
   const TcShape sh(nat);
   const int TS = sh.NT * 8 > sh.KS * 4 ? sh.NT * 8 : sh.KS * 4;
@@ -85,8 +86,12 @@ __global__ void __launch_bounds__(32) pack_model_kernel(int nat, int64_t ntrain,
       if (lane < 8) {
         int64_t j = grp * 8 + lane;
         if (j < ntrain) {
-          const double *m = xyz + j * nat * 3;
-          Xs[lane * TS + d] = xeq[d] / sqrt(rij2_exact(m + 3 * a, m + 3 * b)) - center[d];
+          if (Xin) {
+            Xs[lane * TS + d] = Xin[j * sh.D + d] - center[d];
+          } else {
+            const double *m = xyz + j * nat * 3;
+            Xs[lane * TS + d] = xeq[d] / sqrt(rij2_exact(m + 3 * a, m + 3 * b)) - center[d];
+          }
           if (HAS_V) Vs[lane * TS + d] = V[j * sh.D + d];
         }
       }
@@ -186,6 +191,50 @@ extern "C" int kreg_precompute_v(int natoms, int64_t ntrain, const double *xyz_t
   return KREG_OK;
 }
 
+// centre = mean of the first min(N, 2048) descriptor rows (same rule as descriptor_mean_kernel)
+__global__ void __launch_bounds__(256) descriptor_mean_x_kernel(int D, int64_t npoints, const double *__restrict__ X,
+                                                                double *__restrict__ center) {
+  __shared__ double red[256];
+  const int d = blockIdx.x;
+  if (npoints > 2048) npoints = 2048;
+  double s = 0.0;
+  for (int64_t p = threadIdx.x; p < npoints; p += 256) s += X[p * D + d];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) center[d] = npoints > 0 ? red[0] / (double)npoints : 0.0;
+}
+
+extern "C" int kreg_pack_model_x(int natoms, int64_t ntrain, const double *X_train, const double *alpha_val,
+                                 const double *V, double sigma, double *center, void *packed, size_t packed_bytes,
+                                 void *stream) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  if (ntrain <= 0 || !X_train || !center || !packed || !(sigma > 0.0)) return KREG_E_BADARG;
+  const bool has_v = V != nullptr;
+  if (packed_bytes < kreg_packed_model_bytes(natoms, ntrain, has_v)) return KREG_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return KREG_E_BADARG;
+  cudaStream_t st = as_stream(stream);
+  const TcShape sh(natoms);
+  descriptor_mean_x_kernel<<<sh.D, 256, 0, st>>>(sh.D, ntrain, X_train, center);
+  KREG_LAUNCH_CHECK();
+  const int TS = sh.NT * 8 > sh.KS * 4 ? sh.NT * 8 : sh.KS * 4;
+  const size_t smem = (size_t)(16 * TS + 16) * sizeof(double);
+  const double inv_s2 = 1.0 / (sigma * sigma);
+  const double c1 = kExpScale * inv_s2;
+  const unsigned groups = (unsigned)((ntrain + 7) / 8);
+  if (has_v)
+    pack_model_kernel<true><<<groups, 32, smem, st>>>(natoms, ntrain, nullptr, nullptr, center, alpha_val, V, c1, inv_s2,
+                                                      static_cast<double *>(packed), X_train);
+  else
+    pack_model_kernel<false><<<groups, 32, smem, st>>>(natoms, ntrain, nullptr, nullptr, center, alpha_val, nullptr, c1,
+                                                       inv_s2, static_cast<double *>(packed), X_train);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
 extern "C" int kreg_predict_tile_rows(int natoms, int has_gradient_terms) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
   return tile_rows(natoms, has_gradient_terms != 0);
@@ -217,10 +266,10 @@ extern "C" int kreg_pack_model(int natoms, int64_t ntrain, const double *xyz_tra
   const unsigned groups = (unsigned)((ntrain + 7) / 8);
   if (has_v)
     pack_model_kernel<true><<<groups, 32, smem, st>>>(natoms, ntrain, xyz_train, xeq, center, alpha_val, V, c1,
-                                                      inv_s2, static_cast<double *>(packed));
+                                                      inv_s2, static_cast<double *>(packed), nullptr);
   else
     pack_model_kernel<false><<<groups, 32, smem, st>>>(natoms, ntrain, xyz_train, xeq, center, alpha_val, nullptr,
-                                                       c1, inv_s2, static_cast<double *>(packed));
+                                                       c1, inv_s2, static_cast<double *>(packed), nullptr);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }

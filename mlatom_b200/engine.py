@@ -182,6 +182,22 @@ class PackedModel:
              _ptr(center), _ptr(packed), nbytes, _stream())
         return cls(nat, ntr, float(sigma), float(prior), v is not None, xeq_, center, packed)
 
+    @classmethod
+    def from_descriptors(cls, x_tr, xeq_, alpha_v, sigma: float, prior: float, natoms: int, device=None):
+        """Values-only model given by its training DESCRIPTORS (Ntrain, D) instead of geometries -- what MLatomF's
+        .unf files carry (MLmodel.f90:880-886)."""
+        xeq_ = _dev(xeq_, device)
+        x_tr = _dev(x_tr, xeq_.device)
+        alpha_v = _dev(alpha_v, xeq_.device).reshape(-1)
+        ntr = int(x_tr.shape[0])
+        assert x_tr.shape[1] == natoms * (natoms - 1) // 2 and alpha_v.numel() == ntr
+        nbytes = _lib.load().kreg_packed_model_bytes(natoms, ntr, 0)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=xeq_.device)
+        center = torch.empty_like(xeq_)
+        call("kreg_pack_model_x", natoms, ntr, _ptr(x_tr), _ptr(alpha_v), None, float(sigma), _ptr(center), _ptr(packed),
+             nbytes, _stream())
+        return cls(natoms, ntr, float(sigma), float(prior), False, xeq_, center, packed)
+
     def predict(self, xyz: torch.Tensor, energy: bool = True, gradient: bool = True, out_e=None, out_g=None):
         """xyz (N, Nat, 3) cuda fp64 -> (E (N,) or None, dE/dxyz (N, Nat, 3) or None)."""
         assert xyz.is_cuda and xyz.dtype == F64 and xyz.is_contiguous()

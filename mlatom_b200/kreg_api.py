@@ -170,9 +170,14 @@ class KREG_API:
     # -- prediction -------------------------------------------------------------------------
     def _ensure_model(self):
         if self._model is None:
-            if self.alpha is None or self.XYZ is None:
+            if self.alpha is None or (self.XYZ is None and self.X is None):
                 raise RuntimeError("KREG_API model not found: train or load a model first")
             req = np.asarray(self.Req, dtype=np.float64)
+            if self.XYZ is None:  # values-only model read from an MLatomF .unf file: descriptors, no geometries
+                self._model = engine.PackedModel.from_descriptors(
+                    self._t(self.X), engine.xeq(self._t(req)), self._t(np.asarray(self.alpha).reshape(-1)),
+                    float(self.sigma), float(self.prior), int(self.Natoms))
+                return self._model
             self._model = engine.PackedModel.from_training_set(
                 self._t(self.XYZ), engine.xeq(self._t(req)), self._t(np.asarray(self.alpha).reshape(-1)),
                 float(self.sigma), float(self.prior), int(self.NtrVal), int(self.NtrGrXYZ))
@@ -232,6 +237,33 @@ class KREG_API:
                 self.__dict__[key] = model[key]
         self._model = None
         self._graphs = {}
+
+    def save_unf(self, filename, atomic_numbers=None):
+        """Write the model as an MLatomF ``.unf`` file (MLmodel.f90:819-967), readable by ``MLatomF useMLmodel``."""
+        from . import unf
+
+        prior = float(self.prior)
+        unf.write_unf(filename, X=self.X, alpha=np.asarray(self.alpha).reshape(-1), sigma=float(self.sigma),
+                      lambdav=float(self.lambdav), prior=prior, xyz=self.XYZ, atomic_numbers=atomic_numbers,
+                      ntrval=int(self.NtrVal), ntrgr=int(self.NtrGrXYZ), lambdagradxyz=float(self.lambdagradxyz),
+                      xyz_eq=self.Req, z_eq=atomic_numbers)
+
+    def load_unf(self, filename):
+        """Read an MLatomF ``.unf`` KREG model (RE 'unsorted' descriptor, Gaussian kernel)."""
+        from . import unf
+
+        m = unf.read_unf(filename)
+        if "Req" not in m:
+            raise ValueError("the .unf file carries no equilibrium geometry: the RE descriptor cannot be rebuilt")
+        self.clean_up()
+        self.sigma, self.lambdav, self.lambdagradxyz = m["sigma"], m["lambdav"], m["lambdagradxyz"]
+        self.Natoms, self.Xsize, self.Ntrain = int(m["Natoms"]), int(m["Xsize"]), int(m["Ntrain"])
+        self.NtrVal, self.NtrGrXYZ = int(m["NtrVal"]), int(m["NtrGrXYZ"])
+        self.Ksize = self.NtrVal + self.NtrGrXYZ
+        self.ac2dArray = ac2d_array(self.Natoms)
+        self.Req, self.X, self.XYZ = m["Req"], m["X"], m.get("XYZ")
+        self.alpha, self.prior = m["alpha"].reshape(1, -1), m["prior"]
+        return self
 
     def clean_up(self):
         dev = self.device

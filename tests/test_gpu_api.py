@@ -144,3 +144,24 @@ def test_graph_predictor_matches_direct_path(M):
         e_one, g_one = pm.predict(torch.from_numpy(xte[k:k + 1]).cuda())
         assert mol.energy == e_one.item() and np.array_equal(mol.get_energy_gradients(), g_one[0].cpu().numpy())
     assert len(model.kreg_api._graphs) == 1
+
+
+@pytest.mark.parametrize("use_grads", [False, True])
+def test_unf_model_file_roundtrip_on_device(M, tmp_path, use_grads):
+    """.unf written from a trained model, read into a fresh backend: identical predictions (values-only files carry
+    descriptors, not geometries -> the pack-from-descriptors entry point)."""
+    from mlatom_b200.kreg_api import KREG_API
+
+    db, xyz, e, g = make_db(9, 60, 1)
+    model = M.kreg(hyperparameters={"sigma": 1.0, "lambda": 1e-6})
+    model.train(molecular_database=db, property_to_learn="energy",
+                xyz_derivative_property_to_learn="energy_gradients" if use_grads else None, prior="mean", save_model=False)
+    xte = S.geometries(S.equilibrium(9), 500, 9)
+    e1, g1 = model.predict_xyz(torch.from_numpy(xte).cuda())
+    path = str(tmp_path / "model.unf")
+    model.kreg_api.save_unf(path, atomic_numbers=S.atomic_numbers(9))
+    api = KREG_API().load_unf(path)
+    assert (api.XYZ is None) == (not use_grads)
+    e2, g2 = api.predict_arrays(torch.from_numpy(xte).cuda())
+    assert (e1 - e2).abs().max().item() <= 1e-12 * e1.abs().max().item()
+    assert (g1 - g2).abs().max().item() <= 1e-11
