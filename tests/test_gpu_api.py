@@ -165,3 +165,33 @@ def test_unf_model_file_roundtrip_on_device(M, tmp_path, use_grads):
     e2, g2 = api.predict_arrays(torch.from_numpy(xte).cuda())
     assert (e1 - e2).abs().max().item() <= 1e-12 * e1.abs().max().item()
     assert (g1 - g2).abs().max().item() <= 1e-11
+
+
+def test_batched_md_on_device_conserves_energy(M):
+    """Velocity Verlet for 64 trajectories entirely on the GPU (CUDA-graphed step): total energy is conserved, i.e.
+    the predicted gradients are the derivative of the predicted energies; graph replay == eager stepping."""
+    from mlatom_b200 import engine, md
+
+    nat, ntr = 9, 400
+    eq = S.equilibrium(nat)
+    xtr = S.geometries(eq, ntr, 1, spread=0.08)
+    e, g = S.pair_potential(xtr, eq)
+    api_model = M.kreg(hyperparameters={"sigma": 1.0, "lambda": 1e-8})
+    db = D.molecular_database.from_arrays(S.atomic_numbers(nat), xtr, energy=e, energy_gradients=g)
+    api_model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients",
+                    save_model=False)
+    pm = api_model.kreg_api._ensure_model()
+    b = 64
+    x0 = torch.from_numpy(S.geometries(eq, b, 5, spread=0.02)).cuda()
+    v0 = torch.from_numpy(np.random.default_rng(6).standard_normal((b, nat, 3)) * 0.02).cuda()
+    masses = torch.from_numpy(np.where(S.atomic_numbers(nat) == 1, 1.0, 12.0)).cuda()
+    runs = {}
+    for use_graph in (True, False):
+        sim = md.BatchedNVE(pm, x0, v0, masses, dt=0.01, use_graph=use_graph)
+        e0 = (sim.epot + sim.ekin).clone()
+        out = sim.run(300, record_every=50)
+        etot = out["energies"].sum(1)                       # (records, B)
+        drift = (etot - e0).abs().max().item()
+        assert drift < 2e-4 * max(1.0, sim.ekin.abs().max().item() * 50), drift
+        runs[use_graph] = (out["xyz"].clone(), etot.clone())
+    assert torch.equal(runs[True][0], runs[False][0]) and torch.equal(runs[True][1], runs[False][1])
