@@ -289,17 +289,20 @@ struct GradArgs {
   double *K;
   int64_t ldk;
   double *P;             // [ntr][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
+  int ES;                // doubles per E block: Nat*Nat*3 rounded up to even (16-byte aligned blocks for bulk copies)
 };
 
 // E(a,c)[t] = X_d (x_c - x_a)_t / R^2   (KREG.f90:121)
 __global__ void __launch_bounds__(128) jacobian_rows_kernel(int nat, int64_t n, const double *__restrict__ xyz,
-                                                            const double *__restrict__ xeq, double *__restrict__ E) {
+                                                            const double *__restrict__ xeq, double *__restrict__ E,
+                                                            int ES) {
   const int64_t total = n * nat * nat;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = e / (nat * nat);
     const int ac = (int)(e - p * nat * nat);
     const int a = ac / nat, c = ac % nat;
-    double *out = E + e * 3;
+    double *out = E + p * ES + ac * 3;
+    if (ac == 0 && (nat * nat * 3) < ES) E[p * ES + ES - 1] = 0.0;  // pad element
     if (a == c) {
       out[0] = out[1] = out[2] = 0.0;
       continue;
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   const int tid = threadIdx.x;
 
   fill_exp_table(tab, tid, 256);
-  for (int e = tid; e < NAT * NAT * 3; e += 256) Ei[e] = a.E[i * (NAT * NAT * 3) + e];
+  for (int e = tid; e < NAT * NAT * 3; e += 256) Ei[e] = a.E[i * a.ES + e];
   for (int e = tid; e < D; e += 256) Xi[e] = a.Xc[i * a.XS + e];
   __syncthreads();
   for (int e = tid; e < nj * D; e += 256) {
@@ -400,7 +403,12 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   __syncthreads();
   // pair terms -> workspace (coalesced)
   double *P = a.P + (i * a.ntr + j0) * PW;
-  for (int e = tid; e < nj * PW; e += 256) P[e] = Us[e];
+  {
+    // only pairs whose gradient-gradient block is emitted (j <= i unless mirrored) are read back by grad_emit_kernel
+    const int64_t jgg = full ? a.ntr : i + 1;
+    const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
+    for (int e = tid; e < np * PW; e += 256) P[e] = Us[e];
+  }
   // value-gradient rows: K[rbase + q][j] = (k/s^2) u_i^(j)[q], consecutive threads -> consecutive j
   if (a.nv) {
     for (int e = tid; e < G3 * JT; e += 256) {
@@ -417,27 +425,31 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
 
 // CTA = ONE geometry i x up to NJB*TJ geometries j, walked TJ at a time; thread = matrix column (j, b, u) of the current
 // step.  This thread's 3 Nat values E_i(b, .)[.] live in registers for the whole strip; per step the pair terms, the X_j
-// rows and the E_j blocks arrive by cp.async into the other shared buffer while the current step's 3 Nat stores are
-// issued.  One barrier per step; shared-memory reads are 16-byte wide where the layout allows.
+// rows and the E_j blocks of the TJ geometries -- three contiguous global ranges -- arrive as three TMA bulk copies
+// (cp.async.bulk, one elected thread, mbarrier completion) into the other shared buffer while the current step's
+// 3 Nat stores per thread are issued.  One barrier per step; shared reads are 16-byte wide where the layout allows.
 template <int NAT>
 struct EmitSmem {
   using C = GradCfg<NAT>;
-  static constexpr int DS = (C::D + 1) & ~1;
-  static constexpr int EJ = NAT * NAT * 3 + ((NAT * NAT * 3) & 1);  // one E_j block, padded to an even length
-  static constexpr int OFF_P = 0;                                    // [2][TJ*PW]
-  static constexpr int OFF_X = OFF_P + 2 * C::TJ * C::PW;            // [2][TJ*DS]
-  static constexpr int OFF_E = OFF_X + 2 * C::TJ * DS;               // [2][TJ*EJ]
-  static constexpr int OFF_XI = OFF_E + 2 * C::TJ * EJ;              // [DS]
-  static constexpr int DOUBLES = OFF_XI + DS;
+  static constexpr int EJ = (NAT * NAT * 3 + 1) & ~1;   // one E_j block (== GradArgs::ES)
+  static constexpr int XSMAX = ((C::D + 3) / 4) * 4 + 48;  // >= XS for any chunking (XS = 4*KC*nchunks)
+  static constexpr int OFF_P = 0;                                 // [2][TJ*PW]
+  static constexpr int OFF_X = OFF_P + 2 * C::TJ * C::PW;         // [2][TJ*XS]   (XS taken at run time, <= XSMAX)
+  static constexpr int OFF_E = OFF_X + 2 * C::TJ * XSMAX;         // [2][TJ*EJ]
+  static constexpr int OFF_XI = OFF_E + 2 * C::TJ * EJ;           // [XSMAX]
+  static constexpr int OFF_BAR = OFF_XI + XSMAX;                  // 2 mbarriers
+  static constexpr int DOUBLES = OFF_BAR + 2;
 };
 
 template <int NAT>
 __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) grad_emit_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
   using SM = EmitSmem<NAT>;
-  constexpr int G3 = C::G3, G3P = C::G3P, PW = C::PW, TJ = C::TJ, NJB = C::NJB, D = C::D, DS = SM::DS, EJ = SM::EJ;
-  extern __shared__ __align__(16) double esm[];
+  constexpr int G3 = C::G3, G3P = C::G3P, PW = C::PW, TJ = C::TJ, NJB = C::NJB, D = C::D, EJ = SM::EJ;
+  extern __shared__ __align__(128) double esm[];
   double *Pb = esm + SM::OFF_P, *Xj = esm + SM::OFF_X, *Ejs = esm + SM::OFF_E, *Xi = esm + SM::OFF_XI;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(esm + SM::OFF_BAR);
+  const int XS = a.XS;
 
   const int64_t i = blockIdx.y;
   const bool full = a.fill == KREG_FILL_FULL;
@@ -455,51 +467,41 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) gr
   const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
   const int64_t ld = a.ldk;
 
-  auto prefetch = [&](int n) {
-    const int64_t jb = jb0 + (int64_t)n * TJ;
-    const int npair = (int)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
-    const int buf = n & 1;
-    // pair terms: TJ * PW contiguous doubles (pairs past the end of the set read as zero -> k = 0)
-    const double *P = a.P + (i * a.ntr + jb) * PW;
-    for (int e = tid; e < TJ * PW / 2; e += C::THREADS)
-      cp_async16(Pb + buf * TJ * PW + 2 * e, P + (2 * e < npair * PW ? 2 * e : 0), 2 * e < npair * PW);
-    // X_j rows (XS is a multiple of 4 doubles: every 16-byte piece is aligned)
-    for (int e = tid; e < TJ * (DS / 2); e += C::THREADS) {
-      const int jj = e / (DS / 2), c2i = e % (DS / 2);
-      const bool ok = jj < npair && 2 * c2i < a.XS;
-      cp_async16(Xj + buf * TJ * DS + jj * DS + 2 * c2i, a.Xc + (ok ? (jb + jj) * a.XS + 2 * c2i : 0), ok);
-    }
-    // E_j blocks: the TJ blocks are contiguous in global memory (NAT*NAT*3 doubles each); 8-byte pieces because an
-    // odd block length breaks 16-byte alignment
-    for (int e = tid; e < TJ * NAT * NAT * 3; e += C::THREADS) {
-      const int jj = e / (NAT * NAT * 3), r = e % (NAT * NAT * 3);
-      const bool ok = jj < npair;
-      const unsigned sz = ok ? 8u : 0u;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(Ejs + buf * TJ * EJ + jj * EJ + r)),
-                   "l"(a.E + (ok ? (jb + jj) * (NAT * NAT * 3) + r : 0)), "r"(sz)
-                   : "memory");
-    }
-    cp_async_commit();
-  };
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  for (int e = tid; e < D; e += C::THREADS) Xi[e] = a.Xc[i * XS + e];
+  __syncthreads();
 
-  for (int e = tid; e < D; e += C::THREADS) Xi[e] = a.Xc[i * a.XS + e];
-  prefetch(0);
+  auto prefetch = [&](int n) {  // called by thread 0 only
+    const int64_t jb = jb0 + (int64_t)n * TJ;
+    const unsigned npair = (unsigned)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
+    const int buf = n & 1;
+    const unsigned bp = npair * PW * 8, bx = npair * (unsigned)XS * 8, be = npair * EJ * 8;
+    mbar_arrive_expect_tx(&bar[buf], bp + bx + be);
+    bulk_g2s(Pb + buf * TJ * PW, a.P + (i * a.ntr + jb) * PW, bp, &bar[buf]);
+    bulk_g2s(Xj + buf * TJ * SM::XSMAX, a.Xc + jb * XS, bx, &bar[buf]);
+    bulk_g2s(Ejs + buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
+  };
+  if (tid == 0) prefetch(0);
   double e27[G3P];  // E_i(b, c)[t] for all (c, t);  E_i(a, b)[t] = -E_i(b, a)[t]
   if (colthread) {
 #pragma unroll
-    for (int z = 0; z < G3; z++) e27[z] = a.E[(i * NAT * NAT + (int64_t)b * NAT) * 3 + z];
+    for (int z = 0; z < G3; z++) e27[z] = a.E[i * a.ES + b * G3 + z];
   }
 
   for (int n = 0; n < nsteps; n++) {
-    cp_async_wait_all();
-    __syncthreads();  // step n's operands (and, for n = 0, X_i) are visible; everyone left buffer (n+1)&1
-    if (n + 1 < nsteps) prefetch(n + 1);
+    __syncthreads();  // everyone left buffer (n+1)&1 (read during step n-1)
+    if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    mbar_wait(&bar[n & 1], (n >> 1) & 1);  // step n's operands have landed
     const int64_t j = jb0 + (int64_t)n * TJ + jl;
     if (!colthread || j >= jend) continue;
     const int buf = n & 1;
     const double *pb = Pb + buf * TJ * PW + jl * PW;
-    const double *xj = Xj + buf * TJ * DS + jl * DS;
-    const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * NAT * 3 + u;  // E_j(b, c)[u] at ejb[3c]
+    const double *xj = Xj + buf * TJ * SM::XSMAX + jl * XS;
+    const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * G3 + u;  // E_j(b, c)[u] at ejb[3c]
     double nej[NAT];
 #pragma unroll
     for (int c = 0; c < NAT; c++) nej[c] = -ejb[3 * c];
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) gr
       }
     } else {
       // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal; operands re-read
-      const double *eig = a.E + (i * NAT * NAT + (int64_t)b * NAT) * 3;
+      const double *eig = a.E + i * a.ES + b * G3;
 #pragma unroll 1
       for (int q = 0; q < G3; q++) {
         const int aa = q / 3, t = q % 3;
@@ -610,7 +612,7 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
   w.off_center = take(sh.D);
   w.off_X = take((size_t)n * w.XS);
   w.off_bias = take((size_t)n);
-  w.off_E = with_grad ? take((size_t)n * nat * nat * 3) : off;
+  w.off_E = with_grad ? take((size_t)n * ((nat * nat * 3 + 1) & ~1)) : off;
   w.off_P = with_grad ? take((size_t)n * n * ((3 * nat + 3) & ~1)) : off;
   w.total = off;
   return w;
@@ -682,7 +684,7 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     {
       const int64_t total = ntrain * natoms * natoms;
       int blocks = (int)((total + 127) / 128);
-      jacobian_rows_kernel<<<blocks, 128, 0, st>>>(natoms, ntrain, xyz_train, xeq, E);
+      jacobian_rows_kernel<<<blocks, 128, 0, st>>>(natoms, ntrain, xyz_train, xeq, E, (natoms * natoms * 3 + 1) & ~1);
       KREG_LAUNCH_CHECK();
     }
     GradArgs g;
@@ -702,6 +704,7 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     g.K = K;
     g.ldk = ldk;
     g.P = reinterpret_cast<double *>(ws + w.off_P);
+    g.ES = (natoms * natoms * 3 + 1) & ~1;
     rc = launch_grad(natoms, g, st);
     if (rc) return rc;
   }
