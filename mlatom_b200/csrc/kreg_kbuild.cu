@@ -333,20 +333,38 @@ struct GradCfg {
   static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);  // geometries j per emit CTA
   static constexpr int COLS = TJ * G3;
   static constexpr int THREADS = ((COLS + 31) / 32) * 32;
-  static constexpr int JT = 64;               // geometries j per pair-terms CTA
+  static constexpr int JT = NAT <= 12 ? 64 : 16;  // geometries j per pair-terms CTA (shared-memory budget)
   static constexpr int NJB = 8;               // steps (of TJ geometries) walked by one emit CTA
+};
+
+// shared-memory carve-up of pair_terms_kernel (doubles), sized for the run-time descriptor row stride XS.  The X_j
+// staging rows are dead once X_j - X_i has been formed, so the output block Us reuses their space.
+template <int NAT>
+struct PairSmem {
+  using C = GradCfg<NAT>;
+  static constexpr int ES = (NAT * NAT * 3 + 1) & ~1;
+  static constexpr int DP = C::D | 1;                          // odd row stride: conflict-free column reads
+  static constexpr int DLN = (C::JT * DP + 1) & ~1;
+  __host__ __device__ static int stage(int XS) { return C::JT * XS > C::JT * C::PW ? C::JT * XS : C::JT * C::PW; }
+  __host__ __device__ static int off_xi() { return ES; }                                   // [XS]      X_i
+  __host__ __device__ static int off_xj(int XS) { return ES + XS; }                        // [JT][XS]  X_j rows / Us
+  __host__ __device__ static int off_dl(int XS) { return off_xj(XS) + stage(XS); }         // [JT][DP]  X_j - X_i
+  __host__ __device__ static int off_tab(int XS) { return off_dl(XS) + DLN; }              // [64]
+  __host__ __device__ static int off_bar(int XS) { return off_tab(XS) + 64; }
+  __host__ __device__ static int doubles(int XS) { return off_bar(XS) + 2; }
 };
 
 template <int NAT>
 __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
-  constexpr int G3 = C::G3, PW = C::PW, D = C::D, JT = C::JT, DP = D | 1;  // odd row stride: conflict-free columns
-  extern __shared__ __align__(16) double psm[];
-  double *Ei = psm;                    // [NAT*NAT*3]  E_i(a,c)[t]
-  double *Xi = Ei + NAT * NAT * 3;     // [D]
-  double *Dl = Xi + ((D + 1) & ~1);    // [JT][DP]     X_j - X_i
-  double *Us = Dl + JT * DP;           // [JT][PW]     k/s^2, u_i^(j)
-  double *tab = Us + JT * PW;          // [64]
+  using SM = PairSmem<NAT>;
+  constexpr int G3 = C::G3, PW = C::PW, D = C::D, JT = C::JT, DP = SM::DP;
+  extern __shared__ __align__(128) double psm[];
+  const int XS = a.XS;
+  double *Ei = psm, *Xi = psm + SM::off_xi(), *Xjb = psm + SM::off_xj(XS), *Dl = psm + SM::off_dl(XS);
+  double *Us = Xjb;  // reused after the X_j - X_i pass
+  double *tab = psm + SM::off_tab(XS);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(psm + SM::off_bar(XS));
 
   const int64_t i = blockIdx.y;
   const int64_t rbase = a.nv + i * G3;
@@ -358,13 +376,22 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   const int nj = (int)(jend - j0 < JT ? jend - j0 : JT);
   const int tid = threadIdx.x;
 
+  // one round of TMA bulk loads: E_i, X_i, and the nj rows X_j (contiguous in global memory)
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_fence_init();
+    const unsigned be = SM::ES * 8, bx = (unsigned)XS * 8, bj = (unsigned)nj * XS * 8;
+    mbar_arrive_expect_tx(&bar[0], be + bx + bj);
+    bulk_g2s(Ei, a.E + i * a.ES, be, &bar[0]);
+    bulk_g2s(Xi, a.Xc + i * XS, bx, &bar[0]);
+    bulk_g2s(Xjb, a.Xc + j0 * XS, bj, &bar[0]);
+  }
   fill_exp_table(tab, tid, 256);
-  for (int e = tid; e < NAT * NAT * 3; e += 256) Ei[e] = a.E[i * a.ES + e];
-  for (int e = tid; e < D; e += 256) Xi[e] = a.Xc[i * a.XS + e];
-  __syncthreads();
+  __syncthreads();  // barrier initialised (and table filled) before anyone waits on it
+  mbar_wait(&bar[0], 0);
   for (int e = tid; e < nj * D; e += 256) {
     const int jj = e / D, d = e % D;
-    Dl[jj * DP + d] = a.Xc[(j0 + jj) * a.XS + d] - Xi[d];
+    Dl[jj * DP + d] = Xjb[jj * XS + d] - Xi[d];
   }
   __syncthreads();
   {  // k_ij / s^2: four lanes per pair (JT * 4 == blockDim: every lane takes part in the shuffles)
@@ -562,8 +589,7 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
   using C = GradCfg<NAT>;
   {
     auto kern = pair_terms_kernel<NAT>;
-    constexpr int DP = C::D | 1;
-    const size_t smem = (size_t)(NAT * NAT * 3 + ((C::D + 1) & ~1) + C::JT * DP + C::JT * C::PW + 64) * sizeof(double);
+    const size_t smem = (size_t)PairSmem<NAT>::doubles(a.XS) * sizeof(double);
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((a.ntr + C::JT - 1) / C::JT), (unsigned)a.ntr);
     kern<<<grid, 256, smem, st>>>(a);
