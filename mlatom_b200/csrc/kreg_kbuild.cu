@@ -389,9 +389,12 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   fill_exp_table(tab, tid, 256);
   __syncthreads();  // barrier initialised (and table filled) before anyone waits on it
   mbar_wait(&bar[0], 0);
-  for (int e = tid; e < nj * D; e += 256) {
-    const int jj = e / D, d = e % D;
-    Dl[jj * DP + d] = Xjb[jj * XS + d] - Xi[d];
+  // X_j - X_i into the odd-stride buffer: (256 / JT) lanes per geometry, no integer division
+  {
+    constexpr int LPG = 256 / JT;
+    const int jj = tid / LPG, sub = tid % LPG;
+    if (jj < nj)
+      for (int d = sub; d < D; d += LPG) Dl[jj * DP + d] = Xjb[jj * XS + d] - Xi[d];
   }
   __syncthreads();
   {  // k_ij / s^2: four lanes per pair (JT * 4 == blockDim: every lane takes part in the shuffles)
@@ -408,24 +411,32 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
     }
   }
   // u_i^(j)[(a,t)] = sum_c E_i(a,c)[t] D_j[d_ac]: thread = (j, atom a) produces the three components t, reading each
-  // D_j[d_ac] once (conflict-free columns, odd stride) and E_i(a, .)[.] as warp-wide broadcasts
-  for (int e = tid; e < JT * NAT; e += 256) {
-    const int aa = e / JT, jj = e % JT;
-    if (jj >= nj) continue;
-    const double *dd = Dl + jj * DP;
-    const double *ea = Ei + aa * NAT * 3;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int c = 0; c < NAT; c++)
-      if (c != aa) {
-        const double dl = dd[pair_index(NAT, aa < c ? aa : c, aa < c ? c : aa)];
-        s0 = fma(ea[c * 3 + 0], dl, s0);
-        s1 = fma(ea[c * 3 + 1], dl, s1);
-        s2 = fma(ea[c * 3 + 2], dl, s2);
+  // D_j[d_ac] once (conflict-free columns, odd stride) and E_i(a, .)[.] as warp-wide broadcasts.  The atom index is
+  // uniform per warp and unrolled, so every descriptor index is a compile-time constant.
+  {
+    constexpr int GROUPS = 256 / JT;  // atoms handled concurrently
+    const int jj = tid % JT, grp = tid / JT;
+    if (jj < nj) {
+      const double *dd = Dl + jj * DP;
+#pragma unroll
+      for (int aa = 0; aa < NAT; aa++) {
+        if (aa % GROUPS != grp) continue;
+        const double *ea = Ei + aa * NAT * 3;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NAT; c++)
+          if (c != aa) {
+            const double dl = dd[pair_index(NAT, aa < c ? aa : c, aa < c ? c : aa)];
+            s0 = fma(ea[c * 3 + 0], dl, s0);
+            s1 = fma(ea[c * 3 + 1], dl, s1);
+            s2 = fma(ea[c * 3 + 2], dl, s2);
+          }
+        double *out = Us + jj * PW + 2 + aa * 3;
+        out[0] = s0;
+        out[1] = s1;
+        out[2] = s2;
       }
-    double *out = Us + jj * PW + 2 + aa * 3;
-    out[0] = s0;
-    out[1] = s1;
-    out[2] = s2;
+    }
   }
   __syncthreads();
   // pair terms -> workspace (coalesced)
