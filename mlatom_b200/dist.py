@@ -140,8 +140,13 @@ def allgather_losses(local: dict, n_points: int) -> List[float]:
     backend = dist.get_backend()
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     vals = vals.to(dev)
-    filled = torch.nan_to_num(vals, nan=0.0)
     mask = (~torch.isnan(vals)).to(torch.float64)
+    # +inf (a grid point whose matrix was not positive definite) must survive the sum: reduce finite values and
+    # the "is infinite" flags separately
+    inf = torch.isinf(vals).to(torch.float64)
+    filled = torch.nan_to_num(vals, nan=0.0, posinf=0.0, neginf=0.0)
     dist.all_reduce(filled)
     dist.all_reduce(mask)
-    return torch.where(mask > 0, filled, torch.full_like(filled, float("nan"))).cpu().tolist()
+    dist.all_reduce(inf)
+    out = torch.where(inf > 0, torch.full_like(filled, float("inf")), filled)
+    return torch.where(mask > 0, out, torch.full_like(filled, float("nan"))).cpu().tolist()

@@ -305,14 +305,25 @@ class kreg:
         lam_list = slices[names.index("lambda")] if "lambda" in names else [current["lambda"]]
         fixed_lam_g = self.hyperparameters["lambdaGradXYZ"].value if "lambdaGradXYZ" in self.hyperparameters.keys() else None
         m = nv + ng
+        # grid points are independent: with torch.distributed initialised every rank takes a round-robin share of the
+        # (sigma, lambda) points (grouped by sigma so K(sigma) is still assembled once per sigma it needs) and the
+        # losses are all-gathered; single process: all points
+        from . import dist as kdist
+
+        points = [(si, li) for si in range(len(sig_list)) for li in range(len(lam_list))]
+        mine = set(kdist.grid_shard(points))
         k0 = torch.empty((m, m), dtype=torch.float64, device=dev)
         work = torch.empty_like(k0)
         diag = torch.arange(m, device=dev)
-        table = {}
-        for sigma in sig_list:
+        local = {}
+        for si, sigma in enumerate(sig_list):
+            todo = [li for li in range(len(lam_list)) if points.index((si, li)) in mine]
+            if not todo:
+                continue
             engine.build_kernel_matrix(xyz, xeq, sigma, 0.0, 0.0, use_values=nv > 0, use_gradients=ng > 0,
                                        fill=FILL_LOWER, out=k0)
-            for lam in lam_list:
+            for li in todo:
+                lam = lam_list[li]
                 lam_g = lam if fixed_lam_g is None else fixed_lam_g
                 work.copy_(k0)
                 work[diag[:nv], diag[:nv]] += lam
@@ -332,6 +343,10 @@ class kreg:
                     if err.code <= 0:
                         raise
                     total = float("inf")  # not positive definite at this (lambda, sigma)
-                key = tuple(lam if n == "lambda" else sigma for n in names)
-                table[key] = total
+                local[points.index((si, li))] = total
+        losses = kdist.allgather_losses(local, len(points))
+        table = {}
+        for idx, (si, li) in enumerate(points):
+            key = tuple(lam_list[li] if n == "lambda" else sig_list[si] for n in names)
+            table[key] = losses[idx]
         return table
