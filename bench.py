@@ -203,6 +203,35 @@ def cfg1_side_by_side(engine, dev):
             "max_rel_energy_difference": float(np.abs(e_host - e_cpu).max() / np.abs(e_cpu).max())}
 
 
+def kreg_so_baseline(eq, xyz_tr, alpha, seconds=6.0):
+    """The reference AS SHIPPED: its prebuilt KREG.so (the default 'KREG_API' backend; kreg_mp_predict_,
+    KREG.f90:534-596) through the oracle/_ref shims, all host threads, bounded sample.  None if oracle/_ref is absent."""
+    from mlatom_b200 import synthetic as S
+    from oracle import ref_kreg as R
+
+    if not R.available():
+        return None
+    threads = os.cpu_count() or 1
+    R.set_threads(threads)
+    xeq = R.get_xeq(eq)
+    x_tr = R.calc_re_descriptors(xyz_tr, xeq)
+
+    def run(n):
+        xte = S.geometries(eq, n, seed=2)
+        t0 = time.perf_counter()
+        x_te = R.calc_re_descriptors(xte, xeq)
+        R.predict(xyz_tr, x_tr, xte, x_te, alpha, SIGMA, NTRAIN, 0, True, True)
+        return time.perf_counter() - t0
+
+    n0 = threads
+    t = run(n0)
+    n = int(max(n0, min(NTEST, n0 * seconds / max(t, 1e-6)))) // threads * threads
+    t = run(max(n, threads))
+    return {"value": max(n, threads) / t, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{max(n, threads)} of {NTEST} test geometries, full Ntrain={NTRAIN}, {t:.1f} s wall",
+            "what": "reference's prebuilt mlatom/fortran/np2/KREG.so (ifort), E and gradient passes as shipped"}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm on the host CPU (MLatomF itself cannot be built here:
     no Fortran compiler, binary absent from the checkout)."""
@@ -412,6 +441,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         base, _, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
         line["cpu_baseline"] = base
+        shipped = kreg_so_baseline(eq, xyz_tr, alpha.cpu().numpy())
+        if shipped:
+            line["cpu_baseline_reference_as_shipped"] = shipped
         line["cfg1"] = cfg1_side_by_side(engine, dev)
     print(json.dumps(line))
     if world > 1:
