@@ -146,8 +146,6 @@ __global__ void __launch_bounds__(kThreads, (MT <= 2 && !A_IN_SMEM && NAT <= 9) 
     for (int a = 0; a < NAT; a++)
 #pragma unroll
       for (int b = a + 1; b < NAT; b++) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int d = pair_index(NAT, a, b);
         double x = __ldg(args.xeq + d) / sqrt(rij2_exact(mm + 3 * a, mm + 3 * b)) - __ldg(args.center + d);
         tile[r * TS + d] = x;

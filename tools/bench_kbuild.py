@@ -54,8 +54,6 @@ def main():
     y = torch.from_numpy(np.concatenate([e_h - prior] + ([g_h.reshape(-1)] if args.grads else []))).to(dev)
     align = 3 * nat if args.grads else 1
     slabs = kd.triangle_row_slabs(m, ws, align)
-    if args.grads:  # keep value rows [0, nv) with the first slab boundary that follows them
-        slabs = [(a, b) for a, b in slabs]
 
     def build_rows(r0, r1, out, row_offset):
         engine.build_kernel_matrix(xyz, xeq, args.sigma, args.lam, args.lam, use_values=True, use_gradients=args.grads,
