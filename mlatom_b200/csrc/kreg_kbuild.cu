@@ -345,7 +345,8 @@ struct PairSmem {
   static constexpr int ES = (NAT * NAT * 3 + 1) & ~1;
   static constexpr int DP = C::D | 1;                          // odd row stride: conflict-free column reads
   static constexpr int DLN = (C::JT * DP + 1) & ~1;
-  __host__ __device__ static int stage(int XS) { return C::JT * XS > C::JT * C::PW ? C::JT * XS : C::JT * C::PW; }
+  static constexpr int PWS = C::PW | 1;                        // odd shared-memory stride of the output block
+  __host__ __device__ static int stage(int XS) { return C::JT * XS > C::JT * PWS ? C::JT * XS : C::JT * PWS; }
   __host__ __device__ static int off_xi() { return ES; }                                   // [XS]      X_i
   __host__ __device__ static int off_xj(int XS) { return ES + XS; }                        // [JT][XS]  X_j rows / Us
   __host__ __device__ static int off_dl(int XS) { return off_xj(XS) + stage(XS); }         // [JT][DP]  X_j - X_i
@@ -358,7 +359,7 @@ template <int NAT>
 __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
   using SM = PairSmem<NAT>;
-  constexpr int G3 = C::G3, PW = C::PW, D = C::D, JT = C::JT, DP = SM::DP;
+  constexpr int G3 = C::G3, PW = C::PW, PWS = SM::PWS, D = C::D, JT = C::JT, DP = SM::DP;
   extern __shared__ __align__(128) double psm[];
   const int XS = a.XS;
   double *Ei = psm, *Xi = psm + SM::off_xi(), *Xjb = psm + SM::off_xj(XS), *Dl = psm + SM::off_dl(XS);
@@ -406,8 +407,8 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
     d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
     if (sub == 0 && jj < nj) {
       const double k = (j0 + jj == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
-      Us[jj * PW] = k * a.inv_s2;
-      Us[jj * PW + 1] = 0.0;
+      Us[jj * PWS] = k * a.inv_s2;
+      Us[jj * PWS + 1] = 0.0;
     }
   }
   // u_i^(j)[(a,t)] = sum_c E_i(a,c)[t] D_j[d_ac]: thread = (j, atom a) produces the three components t, reading each
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
             s1 = fma(ea[c * 3 + 1], dl, s1);
             s2 = fma(ea[c * 3 + 2], dl, s2);
           }
-        double *out = Us + jj * PW + 2 + aa * 3;
+        double *out = Us + jj * PWS + 2 + aa * 3;
         out[0] = s0;
         out[1] = s1;
         out[2] = s2;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
     // only pairs whose gradient-gradient block is emitted (j <= i unless mirrored) are read back by grad_emit_kernel
     const int64_t jgg = full ? a.ntr : i + 1;
     const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
-    for (int e = tid; e < np * PW; e += 256) P[e] = Us[e];
+    for (int e = tid; e < np * PW; e += 256) P[e] = Us[(e / PW) * PWS + e % PW];
   }
   // value-gradient rows: K[rbase + q][j] = (k/s^2) u_i^(j)[q], consecutive threads -> consecutive j
   if (a.nv) {
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
       const int q = e / JT, jj = e % JT;
       const int64_t row = rbase + q;
       if (jj < nj && row >= a.row_begin && row < a.row_end) {
-        const double v = Us[jj * PW] * Us[jj * PW + 2 + q];
+        const double v = Us[jj * PWS] * Us[jj * PWS + 2 + q];
         a.K[row * a.ldk + j0 + jj] = v;
         if (full) a.K[(j0 + jj) * a.ldk + row] = v;
       }
