@@ -319,3 +319,61 @@ def test_edge_cases(eng):
 
     with pytest.raises(KregError):
         eng.xeq(dev(np.random.default_rng(0).standard_normal((40, 3))))
+
+
+def test_full_size_kernel_matrices(eng, oracle):
+    """BASELINE configs[2] and [4] at full size: 50k x 50k values K (20 GB buffer) and the 56 000-dim
+    gradient-augmented K (25 GB).  Checked through size-independent properties: sampled rows against the independent
+    rectangular-block path, exact 1 + lambda diagonal, and sampled geometry-pair blocks against the CPU oracle run on
+    just those two geometries."""
+    nat = 9
+    eq = S.equilibrium(nat)
+    xeq_h = oracle.xeq(eq)
+    xeq = dev(xeq_h)
+    rng = np.random.default_rng(11)
+    # ---- cfg3: values block, Ntrain = 50 000 ----
+    ntr, lam = 50000, 1e-6
+    xyz_h = S.geometries(eq, ntr, 1)
+    xyz = dev(xyz_h)
+    k = eng.build_kernel_matrix(xyz, xeq, 1.0, lam, lam)
+    diag = torch.diagonal(k)
+    assert torch.all(diag == 1.0 + lam)
+    rows = np.sort(rng.choice(ntr, size=48, replace=False))
+    blk = eng.kernel_block(xyz[torch.as_tensor(rows).cuda()].contiguous(), xyz, xeq, 1.0)
+    for n, i in enumerate(rows):
+        a, b = k[i, :i], blk[n, :i]
+        assert (a - b).abs().max().item() <= K_RTOL if i else True
+    # against the oracle on a few rows (independent arithmetic)
+    X = oracle.descriptors(xyz_h[rows[:4]], xeq_h)
+    Xall = oracle.descriptors(xyz_h[:2000], xeq_h)
+    ref = np.exp(-((X[:, None, :] - Xall[None, :, :]) ** 2).sum(-1) / 2.0)
+    got = blk[:4, :2000].cpu().numpy()
+    mask = np.ones_like(ref, dtype=bool)
+    for n, i in enumerate(rows[:4]):
+        if i < 2000:
+            mask[n, i] = False
+    assert np.abs(got - ref)[mask].max() <= K_RTOL
+    del k, blk
+    torch.cuda.empty_cache()
+    # ---- cfg5: gradient-augmented, 2000 geometries -> M = 56 000 ----
+    ntr, g3 = 2000, 3 * nat
+    xyz_h = S.geometries(eq, ntr, 1)
+    k = eng.build_kernel_matrix(dev(xyz_h), xeq, 1.0, lam, 2 * lam, use_gradients=True)
+    m = ntr + g3 * ntr
+    assert k.shape == (m, m)
+    d = torch.diagonal(k)
+    assert torch.all(d[:ntr] == 1.0 + lam)
+    for _ in range(6):
+        j, i = np.sort(rng.choice(ntr, size=2, replace=False))
+        pair = xyz_h[[j, i]]
+        Xp = oracle.descriptors(pair, xeq_h)
+        ref = oracle.kernel_matrix(pair, Xp, 1.0, 2, 2 * g3)  # rows/cols: [v_j, v_i, g_j(27), g_i(27)]
+        gi = slice(ntr + i * g3, ntr + (i + 1) * g3)
+        gj = slice(ntr + j * g3, ntr + (j + 1) * g3)
+        scale = np.abs(ref).max()
+        assert abs(k[i, j].item() - ref[1, 0]) <= K_RTOL
+        assert np.abs(k[gi, j].cpu().numpy() - ref[2 + g3:, 0]).max() <= K_RTOL * scale          # d k(i,j) / d M_i
+        assert np.abs(k[gj, i].cpu().numpy() - ref[2:2 + g3, 1]).max() <= K_RTOL * scale         # d k(j,i) / d M_j
+        assert np.abs(k[gi, gj].cpu().numpy() - ref[2 + g3:, 2:2 + g3]).max() <= K_RTOL * scale  # grad-grad (i, j)
+        own = k[gi, gi].cpu().numpy() - 2 * lam * np.eye(g3)
+        assert np.abs(np.tril(own) - np.tril(ref[2 + g3:, 2 + g3:])).max() <= K_RTOL * scale      # diagonal block
