@@ -219,9 +219,9 @@ def test_kernel_block_vs_oracle(eng, oracle):
 # ---- properties at full size (no oracle needed) -------------------------------------------
 
 def test_full_size_properties(eng):
-    """cfg2-shaped run (Nat=9, Ntr=10k) on 50k geometries: finite-difference consistency of E and dE,
-    permutation equivariance over the batch, and host-pipeline == device path."""
-    nat, ntr, nte = 9, 10000, 50000
+    """BASELINE configs[1] at full size (Nat=9, Ntrain=10k, 1M test geometries): finite-difference consistency of E
+    and dE, permutation equivariance over the batch, and host-pipeline == device path."""
+    nat, ntr, nte = 9, 10000, 1000000
     eq = S.equilibrium(nat)
     xtr = S.geometries(eq, ntr, 1)
     alpha = np.random.default_rng(0).standard_normal(ntr) * 1e-2
