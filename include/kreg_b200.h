@@ -81,7 +81,9 @@ int kreg_descriptors(int natoms, int64_t npoints, const double *xyz, const doubl
 
 /* Kernel-matrix assembly ------------------------------------------------------------------ */
 
-/* Scratch bytes needed by kreg_build_kernel_matrix. */
+/* Scratch bytes needed by kreg_build_kernel_matrix for a training set of `ntrain` geometries (centred descriptors,
+ * and for gradient models the descriptor Jacobians plus 3*natoms+1 doubles per geometry pair).
+ * kreg_kernel_block needs kreg_build_workspace_bytes(natoms, na, 0) + kreg_build_workspace_bytes(natoms, nb, 0). */
 size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr);
 
 /* Replaces KREG.kreg.calc_kernel_matrix + the diagonal shift of calcAlpha
@@ -91,7 +93,8 @@ size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr);
  *   ntrval  in {0, ntrain}; ntrgr in {0, 3*natoms*ntrain}  (kreg_api.py:52-72); M = ntrval+ntrgr.
  *   K points at element (0,0) of an M x ldk row-major matrix (ldk >= M); only rows in the range
  *   are touched, so ranks can assemble disjoint row slabs of one matrix.
- *   fill = KREG_FILL_LOWER writes j <= i only; KREG_FILL_FULL mirrors as the reference does. */
+ *   fill = KREG_FILL_LOWER writes j <= i only; KREG_FILL_FULL mirrors as the reference does (for gradient models
+ *   only together with the whole row range; a partial range returns KREG_E_BADARG). */
 int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrval, int64_t ntrgr,
                              const double *xyz_train, const double *xeq, double sigma,
                              double lambdav, double lambdagradxyz, int64_t row_begin,
