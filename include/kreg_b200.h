@@ -164,6 +164,14 @@ int kreg_predict(int natoms, int64_t ntrain, const void *packed, const double *c
                  int64_t npoints, const double *xyz, int flags, double *E, double *G,
                  void *workspace, size_t workspace_bytes, void *stream);
 
+/* Replaces YhessXYZest_KRR (KREG.f90:393-420 with d2KdMiatdMibu :180-221; predict :588-594): the Hessian of the
+ * predicted energy exactly as the reference defines it -- values part of alpha only, products of first derivatives of
+ * the descriptor only (no d2X/dM2 term).  X_train[ntrain][D] are the plain RE descriptors (kreg_descriptors),
+ * alpha_val the first NtrVal coefficients (ntrain = 0 gives zeros, as the reference does for gradient-only models).
+ * H[p][3Nat][3Nat], symmetric. */
+int kreg_hessian(int natoms, int64_t ntrain, const double *X_train, const double *alpha_val, const double *xeq,
+                 double sigma, int64_t npoints, const double *xyz, double *H, void *stream);
+
 /* Test geometries one CTA of kreg_predict handles for this molecule size / model kind (<0: unsupported size).
  * Callers that split a batch into chunks (host streaming, multi-stream pipelines) should use multiples of
  * SM count x this value so that every chunk fills whole waves. */

@@ -58,6 +58,7 @@ PROTOTYPES = {
     ),
     "kreg_pack_model_x": (
         c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kreg_hessian": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_int64, c_void_p, c_void_p, c_void_p]),
     "kreg_predict_tile_rows": (c_int, [c_int, c_int]),
     "kreg_predict_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int64]),
     "kreg_predict": (

@@ -138,6 +138,18 @@ def solve(k: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return alpha
 
 
+def hessian(x_train: torch.Tensor, alpha_val: Optional[torch.Tensor], xeq_: torch.Tensor, sigma: float,
+            xyz: torch.Tensor) -> torch.Tensor:
+    """Reference-defined Hessian of the predicted energy (KREG.f90:180-221, 393-420): (N, 3Nat, 3Nat)."""
+    xyz = _dev(xyz, xeq_.device)
+    n, nat, _ = xyz.shape
+    out = torch.zeros((n, 3 * nat, 3 * nat), dtype=F64, device=xyz.device)
+    ntr = 0 if alpha_val is None else int(alpha_val.numel())
+    call("kreg_hessian", nat, ntr, _ptr(x_train), _ptr(alpha_val), _ptr(xeq_), float(sigma), n, _ptr(xyz), _ptr(out),
+         _stream())
+    return out
+
+
 def precompute_v(xyz_tr: torch.Tensor, xeq_: torch.Tensor, alpha_grad: torch.Tensor) -> torch.Tensor:
     """v_j = J_j alpha_grad,j. alpha_grad (Ntr, Nat, 3) -> (Ntr, D)."""
     ntr, nat, _ = xyz_tr.shape

@@ -10,7 +10,7 @@ unchanged.  Differences that are deliberate:
   * ``self.K`` is not kept after training (it is factorised in place; the reference holds K and a
     copy, 2 x Ksize^2 doubles, KREG.f90:613-616);
   * the Hessian buffer the reference always allocates (kreg_api.py:116, 5.8 GB at 1M geometries) does
-    not exist; ``hessian_to_predict`` raises NotImplementedError (SURVEY.md 8f row 4);
+    not exist; Hessians are computed only when ``hessian_to_predict`` is given (kreg_hessian);
   * failures raise Python exceptions instead of Fortran ``stop`` killing the interpreter
     (mlatom/fortran/stopper.f90:13).
 """
@@ -203,18 +203,31 @@ class KREG_API:
         torch.cuda.synchronize(model.device)
         return (None if e is None else e.numpy()), (None if g is None else g.numpy())
 
+    def hessian_arrays(self, xyz) -> np.ndarray:
+        """Hessian as the reference defines it (values part of alpha, no d2X/dM2 term; KREG.f90:180-221, 393-420)."""
+        self._ensure_model()
+        req = np.asarray(self.Req, dtype=np.float64)
+        nv = int(self.NtrVal)
+        x_tr = self._t(np.asarray(self.X)[:nv] if nv else np.zeros((0, int(self.Xsize))))
+        a_v = self._t(np.asarray(self.alpha).reshape(-1)[:nv]) if nv else None
+        h = engine.hessian(x_tr, a_v, engine.xeq(self._t(req)), float(self.sigma), self._t(xyz))
+        return h.cpu().numpy()
+
     def predict(self, molecular_database=None, molecule=None, property_to_predict=None,
                 xyz_derivative_property_to_predict=None, hessian_to_predict=None):
         """Same contract as kreg_api.py:92-131: results are written INTO the molecules; the XYZ property
         is the gradient dE/dxyz (not the force)."""
-        if hessian_to_predict is not None:
-            raise NotImplementedError("Hessian prediction is not part of the B200 KREG path")
         mol_db = _as_database(molecular_database, molecule)
         want_e = property_to_predict is not None
         want_g = xyz_derivative_property_to_predict is not None
-        if not (want_e or want_g):
+        if not (want_e or want_g or hessian_to_predict is not None):
             return
         xyz = np.asarray(mol_db.xyz_coordinates, dtype=np.float64)
+        if hessian_to_predict is not None:
+            # one (3Nat, 3Nat) array per molecule, stored like the reference does (kreg_api.py:130-131)
+            mol_db.add_scalar_properties(self.hessian_arrays(xyz), property_name=hessian_to_predict)
+        if not (want_e or want_g):
+            return
         e, g = self.predict_arrays(xyz, want_e, want_g)
         if want_e:
             mol_db.add_scalar_properties(e, property_name=property_to_predict)

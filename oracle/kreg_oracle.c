@@ -230,6 +230,56 @@ void kro_predict_kregf90(int nat, int ntr, int ntrval, int ntrgr, const double *
   }
 }
 
+/* KREG.f90:180-221 d2KdMiatdMibu: second derivative of k(X_i, X_j) with respect to two coordinates of the SAME geometry
+ * M_i.  As in the reference only products of first derivatives of the descriptor appear (no d2X/dM2 term). */
+static double d2KdMiatdMibu(int nat, int D, int a, int t, int b, int u, const double *xi, const double *xj,
+                            const double *xyzi, double sigma) {
+  double out1 = 0.0, out2 = 0.0;
+  for (int c = 0; c < nat; c++) {
+    if (a != c) {
+      int d = pair_index(nat, a, c);
+      double ri = rij(xyzi + 3 * a, xyzi + 3 * c);
+      double dXdMiat = xi[d] * (xyzi[3 * c + t] - xyzi[3 * a + t]) / (ri * ri);
+      double in1 = 0.0, in2 = 0.0;
+      for (int g = 0; g < nat; g++) {
+        if (b != g) {
+          int e = pair_index(nat, b, g);
+          double rg = rij(xyzi + 3 * b, xyzi + 3 * g);
+          double dXdMibu = xi[e] * (xyzi[3 * g + u] - xyzi[3 * b + u]) / (rg * rg);
+          in1 = in1 + dXdMibu * (xj[d] - xi[d]) * (xj[e] - xi[e]);
+          if (d == e) in2 = in2 - dXdMibu;
+        }
+      }
+      out1 = out1 + in1 * dXdMiat;
+      out2 = out2 + in2 * dXdMiat;
+    }
+  }
+  out1 = out1 / (sigma * sigma);
+  return (out1 + out2) * kernel(D, xi, xj, sigma) / (sigma * sigma);
+}
+
+/* KREG.f90:393-420 YhessXYZest_KRR driven by predict :588-594: values part of alpha only.
+ * H[p][dim2][dim1] == Fortran YhessXYZest(dim1, dim2, p), dim = 3*atom + xyz. */
+void kro_hessian_kregf90(int nat, int ntrval, const double *X_tr, const double *alpha, double sigma, long np,
+                         const double *xyz_te, const double *X_te, double *H) {
+  const int D = nat * (nat - 1) / 2;
+  const int G3 = 3 * nat;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < np; i++) {
+    const double *xp = X_te + (size_t)i * D;
+    const double *mp = xyz_te + (size_t)i * nat * 3;
+    for (int a = 0; a < nat; a++)
+      for (int t = 0; t < 3; t++)
+        for (int b = 0; b < nat; b++)
+          for (int u = 0; u < 3; u++) {
+            double h = 0.0;
+            for (int j = 0; j < ntrval; j++)
+              h = h + alpha[j] * d2KdMiatdMibu(nat, D, a, t, b, u, xp, X_tr + (size_t)j * D, mp, sigma);
+            H[(size_t)i * G3 * G3 + (size_t)(3 * b + u) * G3 + (3 * a + t)] = h;
+          }
+  }
+}
+
 /* ---- prediction: MLatomF "Optimized Code" form -------------------------------------- */
 
 /* A_KRR.f90:985-1029 calcEst_KRR driving Yest_KRR (A_KRR_kernel.f90:225-245) and

@@ -162,3 +162,14 @@ def predict_factored(x_tr, alpha_v, v, sigma, prior, xyz_te, x_te, calc_grad=Tru
         _d(xyz_te), _d(x_te), c_int(calc_grad), _d(e), _d(g), _d(s),
     )
     return (e, g, s) if want_scale else (e, g)
+
+
+def hessian_kregf90(x_tr, alpha, sigma, ntrval, xyz_te, x_te):
+    """Literal KREG.f90 Hessian (values part of alpha only). Returns (Np, 3Nat, 3Nat)."""
+    x_tr, xyz_te, x_te = _c(x_tr), _c(xyz_te), _c(x_te)
+    npred, nat, _ = xyz_te.shape
+    a = _c(alpha).reshape(-1)
+    h = np.zeros((npred, 3 * nat, 3 * nat))
+    load().kro_hessian_kregf90(c_int(nat), c_int(ntrval), _d(x_tr), _d(a), c_double(sigma), c_long(npred), _d(xyz_te),
+                               _d(x_te), _d(h))
+    return h

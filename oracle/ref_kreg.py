@@ -163,8 +163,9 @@ def train(xyz, x, ytrain, sigma, lambdav, lambdagradxyz, ntrval, ntrgr, calc_ker
     return k, alpha
 
 
-def predict(xyz_tr, x_tr, xyz_te, x_te, alpha, sigma, ntrval, ntrgr, calc_val=True, calc_grad=True):
-    """kreg_mp_predict_ (KREG.f90:534-596). Returns (Yest (Np,), Ygrad (Np,Nat,3)); no prior added."""
+def predict(xyz_tr, x_tr, xyz_te, x_te, alpha, sigma, ntrval, ntrgr, calc_val=True, calc_grad=True, calc_hess=False):
+    """kreg_mp_predict_ (KREG.f90:534-596). Returns (Yest (Np,), Ygrad (Np,Nat,3)) -- plus Yhess (Np,3Nat,3Nat) when
+    calc_hess; no prior added."""
     lib = load()
     ntr, natoms, _ = xyz_tr.shape
     npred = xyz_te.shape[0]
@@ -172,13 +173,15 @@ def predict(xyz_tr, x_tr, xyz_te, x_te, alpha, sigma, ntrval, ntrgr, calc_val=Tr
     ac2d = get_ac2darray(natoms)
     yest = np.zeros(npred)
     ygrad = np.zeros((npred, natoms, 3))  # bytes == F(3,Nat,Np)
-    yhess = np.zeros(1)
+    yhess = np.zeros((npred, 3 * natoms, 3 * natoms)) if calc_hess else np.zeros(1)  # bytes == F(3Nat,3Nat,Np)
     a = np.ascontiguousarray(alpha, dtype=np.float64).reshape(-1)
     assert a.shape[0] == ntrval + ntrgr
     lib.kreg_mp_predict_(
         _ci(natoms), _ci(xsize), _ci(ntr), _ci(npred), _ci(ntrval), _ci(ntrgr), _p(ac2d, c_int),
         _p(np.ascontiguousarray(x_tr)), _p(xyz_to_f(xyz_tr)), _p(np.ascontiguousarray(x_te)),
-        _p(xyz_to_f(xyz_te)), _p(a), _logical(calc_val), _logical(calc_grad), _logical(False),
+        _p(xyz_to_f(xyz_te)), _p(a), _logical(calc_val), _logical(calc_grad), _logical(calc_hess),
         _p(yest), _p(ygrad), _p(yhess), _cd(sigma),
     )
+    if calc_hess:
+        return yest, ygrad, yhess
     return yest, ygrad

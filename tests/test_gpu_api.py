@@ -67,7 +67,7 @@ def test_kreg_train_predict_vs_oracle(M, oracle, tmp_path, nat, ntr, use_grads, 
     assert np.abs(g2 - g_ref).max() <= 1e-8
 
 
-def test_model_file_roundtrip_and_tensor_path(M, tmp_path):
+def test_model_file_roundtrip_and_tensor_path(M, oracle, tmp_path):
     db, xyz, e, g = make_db(9, 80, 1)
     model = M.kreg(model_file=str(tmp_path / "rt.npz"), hyperparameters={"sigma": 1.0, "lambda": 1e-6})
     model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients")
@@ -82,8 +82,14 @@ def test_model_file_roundtrip_and_tensor_path(M, tmp_path):
     again.predict(molecule=mol, calculate_energy=True, calculate_energy_gradients=True)
     assert mol.energy == e3[3] and np.array_equal(mol.get_energy_gradients(), g3[3])
     assert mol.atoms[0].energy_gradients.shape == (3,)
-    with pytest.raises(NotImplementedError):
-        again.predict(molecule=mol, calculate_hessian=True)
+    # Hessian as the reference defines it (KREG.f90:393-420), stored per molecule like kreg_api.py:130-131
+    again.predict(molecule=mol, calculate_hessian=True)
+    api = again.kreg_api
+    X = np.asarray(api.X)
+    xq = oracle.descriptors(xte[3:4], oracle.xeq(np.asarray(api.Req)))
+    h_ref = oracle.hessian_kregf90(X, np.asarray(api.alpha).reshape(-1), float(api.sigma), int(api.NtrVal), xte[3:4], xq)[0]
+    assert mol.hessian.shape == (27, 27)
+    assert np.abs(mol.hessian - h_ref).max() <= 1e-9 * max(1.0, np.abs(h_ref).max())
 
 
 def test_grid_search_fused_equals_pointwise_on_device(M, tmp_path):

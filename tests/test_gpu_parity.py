@@ -14,6 +14,7 @@ from mlatom_b200 import synthetic as S  # noqa: E402
 
 E_RTOL = 1e-10
 G_TOL = 1e-8
+H_TOL = 1e-9  # Hessian: same arithmetic as the gradient sums, one more contraction
 K_RTOL = 1e-13
 
 
@@ -89,6 +90,34 @@ def test_golden_predict_from_reference_alpha(golden, eng):
     assert np.abs(e2.cpu().numpy() - e).max() <= 1e-12 * np.abs(ref_e).max()
     none, g2 = model.predict(dev(g["xyz_test"]), energy=False, gradient=True)
     assert none is None and np.array_equal(g2.cpu().numpy(), gr)
+
+
+def test_golden_hessian(golden, eng):
+    """kreg_hessian against the reference's YhessXYZest (golden H_test, KREG.f90:393-420) at the reference's alpha."""
+    g = golden
+    nv = int(g["ntrval"])
+    xeq = eng.xeq(dev(g["eq"]))
+    x_tr = eng.descriptors(dev(g["xyz_train"][:max(nv, 1)]), xeq)[:nv]
+    h = eng.hessian(x_tr, dev(g["alpha"][:nv]) if nv else None, xeq, g["sigma"], dev(g["xyz_test"])).cpu().numpy()
+    ref = g["H_test"]
+    assert h.shape == ref.shape
+    assert np.abs(h - ref).max() <= H_TOL * max(1.0, np.abs(ref).max())
+    assert np.abs(h - h.transpose(0, 2, 1)).max() <= H_TOL * max(1.0, np.abs(ref).max())
+    if nv == 0:
+        assert not h.any()
+
+
+@pytest.mark.parametrize("nat,ntr,nte", [(2, 5, 3), (3, 33, 4), (12, 100, 7), (16, 64, 3), (21, 40, 2)])
+def test_hessian_vs_oracle(eng, oracle, nat, ntr, nte):
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 11), S.geometries(eq, nte, 12)
+    xeq_o = oracle.xeq(eq)
+    X_tr, X_te = oracle.descriptors(xtr, xeq_o), oracle.descriptors(xte, xeq_o)
+    alpha = np.random.default_rng(5).standard_normal(ntr)
+    sigma = 0.7 * np.sqrt(nat)
+    ref = oracle.hessian_kregf90(X_tr, alpha, sigma, ntr, xte, X_te)
+    h = eng.hessian(dev(X_tr), dev(alpha), eng.xeq(dev(eq)), sigma, dev(xte)).cpu().numpy()
+    assert np.abs(h - ref).max() <= H_TOL * max(1.0, np.abs(ref).max())
 
 
 def test_golden_train_residual_and_prediction(golden, eng):

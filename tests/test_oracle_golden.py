@@ -46,6 +46,16 @@ def test_predict_literal_bit_exact(golden, oracle):
     assert np.array_equal(gr, g["G_test"])
 
 
+def test_hessian_literal_bit_exact(golden, oracle):
+    """YhessXYZest_KRR (KREG.f90:393-420): values part of alpha only; zero for gradient-only models."""
+    g = golden
+    h = oracle.hessian_kregf90(g["X_train"], g["alpha"], g["sigma"], g["ntrval"], g["xyz_test"], g["X_test"])
+    assert h.shape == g["H_test"].shape == (g["ntest"], 3 * g["natoms"], 3 * g["natoms"])
+    assert np.array_equal(h, g["H_test"])
+    if g["ntrval"] == 0:
+        assert not h.any()
+
+
 def test_predict_mlatomf_and_factored(golden, oracle):
     g = golden
     nv = g["ntrval"]

@@ -57,13 +57,13 @@ def main():
         ytrain = np.concatenate(parts)
         k = R.calc_kernel_matrix(xyz_tr, x_tr, sigma, ntrval, ntrgr)
         _, alpha = R.train(xyz_tr, x_tr, ytrain, sigma, lam, lam, ntrval, ntrgr)
-        e_te, g_te = R.predict(xyz_tr, x_tr, xyz_te, x_te, alpha, sigma, ntrval, ntrgr)
+        e_te, g_te, h_te = R.predict(xyz_tr, x_tr, xyz_te, x_te, alpha, sigma, ntrval, ntrgr, calc_hess=True)
         np.savez_compressed(
             os.path.join(outdir, name + ".npz"),
             natoms=nat, ntrain=ntr, ntest=nte, ntrval=ntrval, ntrgr=ntrgr, sigma=sigma, lambdav=lam,
             lambdagradxyz=lam, prior=prior, eq=eq, xyz_train=xyz_tr, xyz_test=xyz_te, y_train=e_tr,
             ygrad_train=g_tr, ytrain=ytrain, ac2d=R.get_ac2darray(nat), xeq=xeq, X_train=x_tr, X_test=x_te, K=k,
-            alpha=alpha, E_test=e_te, G_test=g_te,
+            alpha=alpha, E_test=e_te, G_test=g_te, H_test=h_te,
         )
         print(f"{name}: M={ntrval + ntrgr} K{k.shape} |E|max={np.abs(e_te).max():.3e} |G|max={np.abs(g_te).max():.3e}")
 
