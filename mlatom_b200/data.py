@@ -116,3 +116,51 @@ class molecular_database:
             self.molecules[i].add_xyz_vectorial_property(vectors[i], xyz_vectorial_property=xyz_vectorial_property)
 
     add_xyz_derivative_properties = add_xyz_vectorial_properties
+
+    # ---- text files (mlatom/data.py:1568-1578, 1869-1882, 1944-1990, 2120-2130), through the array parsers ----
+    def read_from_xyz_file(self, filename: str, append: bool = False) -> "molecular_database":
+        from . import textio
+
+        z, xyz = textio.read_xyz(filename)
+        mols = [molecule.from_arrays(z[i], xyz[i]) for i in range(len(z))]
+        self.molecules = (self.molecules + mols) if append else mols
+        return self
+
+    @classmethod
+    def from_xyz_file(cls, filename: str) -> "molecular_database":
+        return cls().read_from_xyz_file(filename)
+
+    def add_scalar_properties_from_file(self, filename: str, property_name: str = "y") -> None:
+        from . import textio
+
+        self.add_scalar_properties(textio.read_y(filename), property_name=property_name)
+
+    def add_xyz_vectorial_properties_from_file(self, filename: str, xyz_vectorial_property: str = "xyz_vector") -> None:
+        from . import textio
+
+        self.add_xyz_vectorial_properties(textio.read_xyz_vectors(filename), xyz_vectorial_property=xyz_vectorial_property)
+
+    add_xyz_derivative_properties_from_file = add_xyz_vectorial_properties_from_file
+
+    def write_file_with_xyz_coordinates(self, filename: str) -> None:
+        from . import textio
+
+        z = np.array([m.atomic_numbers for m in self.molecules])
+        textio.write_xyz(filename, z, self.xyz_coordinates)
+
+    def write_file_with_properties(self, filename: str, property_to_write: str = "y") -> None:
+        from . import textio
+
+        textio.write_y(filename, self.get_properties(property_to_write))
+
+    def write_file_with_xyz_vectorial_properties(self, filename: str, xyz_vectorial_property_to_write: str = "xyz_vector") -> None:
+        from . import textio
+
+        textio.write_xyz_vectors(filename, self.get_xyz_vectorial_properties(xyz_vectorial_property_to_write))
+
+    def write_file_with_xyz_derivative_properties(self, filename: str, xyz_derivative_property_to_write: str = "xyz_derivatives") -> None:
+        self.write_file_with_xyz_vectorial_properties(filename, xyz_derivative_property_to_write)
+
+    def write_file_energy_gradients(self, filename: str) -> None:
+        self.write_file_with_xyz_vectorial_properties(filename, "energy_gradients")
+

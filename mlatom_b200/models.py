@@ -263,6 +263,15 @@ class kreg:
                     params, _ = optimize_grid(lambda p: table[tuple(p)], slices)
                 else:
                     params, _ = optimize_grid(loss_at, slices)
+            elif algo in ("log2grid", "lggrid"):
+                # MLatomF's own optimiser (sigma=opt lambda=opt with lgOptDepth levels); not offered by the reference's
+                # Python class, available here because the fused path makes it cheap
+                if not set(names) <= {"lambda", "sigma"}:
+                    raise NotImplementedError("log2grid optimises 'sigma' and/or 'lambda'")
+                best, _, self.grid_trace = self._log2_grid_search(names, optimization_algorithm_kwargs, training_kwargs,
+                                                                  prediction_kwargs, subtraining_molecular_database,
+                                                                  validation_molecular_database)
+                params = [best[n] for n in names]
             else:
                 import scipy.optimize
 
@@ -276,35 +285,25 @@ class kreg:
             self.model_file = saved_name
         self.validation_loss = loss_at([self.hyperparameters[k].value for k in names])
 
-    def _fused_grid_losses(self, names, slices, training_kwargs, prediction_kwargs, sub_db, val_db):
-        """All (lambda, sigma) grid losses with K(sigma) built once per sigma (SURVEY.md 8f row 1)."""
+    def _fused_evaluator(self, training_kwargs, prediction_kwargs, sub_db, val_db):
+        """Everything of the hold-out loss that does not depend on (sigma, lambda), resident on the device."""
         tk, _, p_learn, g_learn, _, _ = self._names(training_kwargs, prediction_kwargs)
         api = KREG_API(self.device)
         dev = api._dev()
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
         if self.equilibrium_molecule is None:
             self.equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=sub_db)
-        xeq = engine.xeq(t(self.equilibrium_molecule.xyz_coordinates))
-        xyz, xyz_val = t(sub_db.xyz_coordinates), t(val_db.xyz_coordinates)
-        ntr, nat = int(xyz.shape[0]), int(xyz.shape[1])
         _, _, prior = self._lambdas_and_prior(tk.get("prior"))
-        parts, prior_value = [], 0.0
-        if p_learn is not None:
-            y = np.asarray(sub_db.get_properties(p_learn), dtype=np.float64)
-            prior_value = float(np.mean(y)) if isinstance(prior, str) and prior.casefold() == "mean" else float(prior or 0.0)
-            parts.append(y - prior_value)
-        if g_learn is not None:
-            parts.append(np.asarray(sub_db.get_xyz_vectorial_properties(g_learn), dtype=np.float64).reshape(-1))
-        ytrain = t(np.concatenate(parts))
-        nv, ng = (ntr if p_learn is not None else 0), (3 * nat * ntr if g_learn is not None else 0)
-        y_val = np.asarray(val_db.get_properties(p_learn)) if p_learn is not None else None
-        g_val = np.asarray(val_db.get_xyz_vectorial_properties(g_learn)) if g_learn is not None else None
+        fixed_lam_g = self.hyperparameters["lambdaGradXYZ"].value if "lambdaGradXYZ" in self.hyperparameters.keys() else None
+        return _FusedHoldout(t, self.equilibrium_molecule.xyz_coordinates, sub_db, val_db, p_learn, g_learn, prior,
+                             fixed_lam_g)
 
+    def _fused_grid_losses(self, names, slices, training_kwargs, prediction_kwargs, sub_db, val_db):
+        """All (lambda, sigma) grid losses with K(sigma) built once per sigma (SURVEY.md 8f row 1)."""
+        ev = self._fused_evaluator(training_kwargs, prediction_kwargs, sub_db, val_db)
         current = {k: self.hyperparameters[k].value for k in ("lambda", "sigma")}
         sig_list = slices[names.index("sigma")] if "sigma" in names else [current["sigma"]]
         lam_list = slices[names.index("lambda")] if "lambda" in names else [current["lambda"]]
-        fixed_lam_g = self.hyperparameters["lambdaGradXYZ"].value if "lambdaGradXYZ" in self.hyperparameters.keys() else None
-        m = nv + ng
         # grid points are independent: with torch.distributed initialised every rank takes a round-robin share of the
         # (sigma, lambda) points (grouped by sigma so K(sigma) is still assembled once per sigma it needs) and the
         # losses are all-gathered; single process: all points
@@ -312,41 +311,132 @@ class kreg:
 
         points = [(si, li) for si in range(len(sig_list)) for li in range(len(lam_list))]
         mine = set(kdist.grid_shard(points))
-        k0 = torch.empty((m, m), dtype=torch.float64, device=dev)
-        work = torch.empty_like(k0)
-        diag = torch.arange(m, device=dev)
         local = {}
         for si, sigma in enumerate(sig_list):
             todo = [li for li in range(len(lam_list)) if points.index((si, li)) in mine]
             if not todo:
                 continue
-            engine.build_kernel_matrix(xyz, xeq, sigma, 0.0, 0.0, use_values=nv > 0, use_gradients=ng > 0,
-                                       fill=FILL_LOWER, out=k0)
+            ev.set_sigma(sigma)
             for li in todo:
-                lam = lam_list[li]
-                lam_g = lam if fixed_lam_g is None else fixed_lam_g
-                work.copy_(k0)
-                work[diag[:nv], diag[:nv]] += lam
-                work[diag[nv:], diag[nv:]] += lam_g
-                try:
-                    alpha = engine.solve(work, ytrain)
-                    model = engine.PackedModel.from_training_set(xyz, xeq, alpha, sigma, prior_value, nv, ng)
-                    e, g = model.predict(xyz_val, p_learn is not None, g_learn is not None)
-                    total = 1.0
-                    if p_learn is not None:
-                        total *= rmse(e.cpu().numpy(), y_val)
-                    if g_learn is not None:
-                        total *= rmse(g.cpu().numpy(), g_val)
-                    if p_learn is not None and g_learn is not None:
-                        total = float(np.sqrt(total))
-                except KregError as err:
-                    if err.code <= 0:
-                        raise
-                    total = float("inf")  # not positive definite at this (lambda, sigma)
-                local[points.index((si, li))] = total
+                local[points.index((si, li))] = ev.loss(lam_list[li])
         losses = kdist.allgather_losses(local, len(points))
         table = {}
         for idx, (si, li) in enumerate(points):
             key = tuple(lam_list[li] if n == "lambda" else sig_list[si] for n in names)
             table[key] = losses[idx]
         return table
+
+    def _log2_grid_search(self, names, kwargs, training_kwargs, prediction_kwargs, sub_db, val_db):
+        """MLatomF's recursive logarithmic grid (optLog2Grid / optLambdaLog2Grid, A_KRR.f90:1049-1376): sigma on a
+        log2 grid; for every sigma, lambda on its own log2 grid re-using K(sigma); after each level the range shrinks
+        to one grid step either side of the best point; ``depth`` levels (lgOptDepth, default 3); ties keep the first
+        minimum.  Returns ({name: value}, loss, trace)."""
+        depth = int(kwargs.get("depth", 3))
+        pts = kwargs.get("points", {})
+        default_pts = {"sigma": 11, "lambda": 6}  # the ranges MLatomF spans by default at unit log2 steps (-35..-6, 2..9)
+        npts = {k: int(pts.get(k, kwargs.get("grid_size", default_pts[k]))) for k in ("sigma", "lambda")}
+        lg = lambda k: (float(np.log2(self.hyperparameters[k].minval)), float(np.log2(self.hyperparameters[k].maxval)))
+        ev = self._fused_evaluator(training_kwargs, prediction_kwargs, sub_db, val_db)
+        trace = []
+
+        def level_points(lo, hi, n):
+            step = 0.0 if n == 1 else (hi - lo) / (n - 1)
+            return step, [lo + step * i for i in range(n)]
+
+        def best_lambda(sigma):
+            if "lambda" not in names:
+                lam = self.hyperparameters["lambda"].value
+                return lam, ev.loss(lam)
+            lo, hi = lg("lambda")  # reset for every sigma (getLambda, A_KRR.f90:963-981)
+            best = None
+            for _ in range(depth):
+                step, grid = level_points(lo, hi, npts["lambda"])
+                lvl = None
+                for x in grid:
+                    err = ev.loss(2.0 ** x)
+                    trace.append((sigma, 2.0 ** x, err))
+                    if lvl is None or err < lvl[1]:
+                        lvl = (x, err)
+                best = lvl
+                lo, hi = best[0] - step, best[0] + step
+            return 2.0 ** best[0], best[1]
+
+        if "sigma" not in names:
+            ev.set_sigma(self.hyperparameters["sigma"].value)
+            lam, err = best_lambda(self.hyperparameters["sigma"].value)
+            return {"lambda": lam}, err, trace
+        lo, hi = lg("sigma")
+        best = None
+        for _ in range(depth):
+            step, grid = level_points(lo, hi, npts["sigma"])
+            lvl = None
+            for x in grid:
+                sigma = 2.0 ** x
+                ev.set_sigma(sigma)
+                lam, err = best_lambda(sigma)
+                if lvl is None or err < lvl[2]:
+                    lvl = (x, lam, err)
+            best = lvl
+            lo, hi = best[0] - step, best[0] + step
+        out = {"sigma": 2.0 ** best[0]}
+        if "lambda" in names:
+            out["lambda"] = best[1]
+        return out, best[2], trace
+
+
+class _FusedHoldout:
+    """Hold-out validation loss as a function of lambda at a fixed sigma, everything resident in HBM: K(sigma) is
+    assembled once by ``set_sigma``; ``loss(lambda)`` shifts the diagonal of a copy, factorises it, predicts the
+    validation set and returns the reference's loss (RMSE, geometric mean of scalar and vectorial parts,
+    model_cls.py:577-585).  A matrix that is not positive definite at some lambda scores +inf."""
+
+    def __init__(self, t, eq_xyz, sub_db, val_db, p_learn, g_learn, prior, fixed_lam_g):
+        self.p_learn, self.g_learn, self.fixed_lam_g = p_learn, g_learn, fixed_lam_g
+        self.xeq = engine.xeq(t(eq_xyz))
+        self.xyz, self.xyz_val = t(sub_db.xyz_coordinates), t(val_db.xyz_coordinates)
+        ntr, nat = int(self.xyz.shape[0]), int(self.xyz.shape[1])
+        parts, self.prior_value = [], 0.0
+        if p_learn is not None:
+            y = np.asarray(sub_db.get_properties(p_learn), dtype=np.float64)
+            self.prior_value = float(np.mean(y)) if isinstance(prior, str) and prior.casefold() == "mean" else float(prior or 0.0)
+            parts.append(y - self.prior_value)
+        if g_learn is not None:
+            parts.append(np.asarray(sub_db.get_xyz_vectorial_properties(g_learn), dtype=np.float64).reshape(-1))
+        self.ytrain = t(np.concatenate(parts))
+        self.nv, self.ng = (ntr if p_learn is not None else 0), (3 * nat * ntr if g_learn is not None else 0)
+        self.y_val = np.asarray(val_db.get_properties(p_learn)) if p_learn is not None else None
+        self.g_val = np.asarray(val_db.get_xyz_vectorial_properties(g_learn)) if g_learn is not None else None
+        m = self.nv + self.ng
+        dev = self.xyz.device
+        self.k0 = torch.empty((m, m), dtype=torch.float64, device=dev)
+        self.work = torch.empty_like(self.k0)
+        self.diag = torch.arange(m, device=dev)
+        self.sigma = None
+
+    def set_sigma(self, sigma):
+        self.sigma = float(sigma)
+        engine.build_kernel_matrix(self.xyz, self.xeq, self.sigma, 0.0, 0.0, use_values=self.nv > 0,
+                                   use_gradients=self.ng > 0, fill=FILL_LOWER, out=self.k0)
+
+    def loss(self, lam):
+        nv, diag, work = self.nv, self.diag, self.work
+        lam_g = lam if self.fixed_lam_g is None else self.fixed_lam_g
+        work.copy_(self.k0)
+        work[diag[:nv], diag[:nv]] += lam
+        work[diag[nv:], diag[nv:]] += lam_g
+        try:
+            alpha = engine.solve(work, self.ytrain)
+        except KregError as err:
+            if err.code <= 0:
+                raise
+            return float("inf")  # not positive definite at this (lambda, sigma)
+        model = engine.PackedModel.from_training_set(self.xyz, self.xeq, alpha, self.sigma, self.prior_value, nv, self.ng)
+        e, g = model.predict(self.xyz_val, self.p_learn is not None, self.g_learn is not None)
+        total = 1.0
+        if self.p_learn is not None:
+            total *= rmse(e.cpu().numpy(), self.y_val)
+        if self.g_learn is not None:
+            total *= rmse(g.cpu().numpy(), self.g_val)
+        if self.p_learn is not None and self.g_learn is not None:
+            total = float(np.sqrt(total))
+        return total

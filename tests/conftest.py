@@ -41,3 +41,24 @@ def oracle():
 
     kreg_oracle.load()
     return kreg_oracle
+
+
+def reference_mlatom_data():
+    """The reference's own mlatom.data module (build container only; h5py is absent here and only needed for
+    features these tests do not touch, so an empty stand-in module satisfies the import)."""
+    import os
+    import sys
+    import types
+
+    if not os.path.isdir("/root/reference/mlatom"):
+        return None
+    os.environ["MLATOM_NO_VERSION_CHECK"] = "1"
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    try:
+        import mlatom.data as ref_data
+    except Exception:  # pragma: no cover - reference not importable here
+        return None
+    return ref_data
+

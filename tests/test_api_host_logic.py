@@ -95,17 +95,9 @@ def make_db(mod, nat, n, seed, with_labels=True):
 
 
 def reference_mlatom():
-    if not os.path.isdir("/root/reference/mlatom"):
-        return None
-    os.environ["MLATOM_NO_VERSION_CHECK"] = "1"
-    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
-    if "/root/reference" not in sys.path:
-        sys.path.insert(0, "/root/reference")
-    try:
-        import mlatom.data as ref_data
-    except Exception:  # pragma: no cover - reference not importable here
-        return None
-    return ref_data
+    from conftest import reference_mlatom_data
+
+    return reference_mlatom_data()
 
 
 @pytest.mark.parametrize("use_grads", [False, True])
@@ -215,3 +207,53 @@ def test_grid_search_fused_equals_pointwise(fake_engine, tmp_path):
         res.append((model.hyperparameters["lambda"].value, model.hyperparameters["sigma"].value, model.validation_loss))
     assert res[0][:2] == res[1][:2]
     assert abs(res[0][2] - res[1][2]) <= 1e-9 * res[1][2]
+
+
+def test_log2_grid_search_follows_mlatomf_recursion(fake_engine, tmp_path):
+    """optLog2Grid / optLambdaLog2Grid (A_KRR.f90:1049-1376): nested log2 grids, zoom +-1 step around the best,
+    lgOptDepth levels, first minimum wins -- restated here with one train+predict per point."""
+    nat = 5
+    sub, _, _, _ = make_db(D, nat, 12, 1)
+    val, _, _, _ = make_db(D, nat, 7, 3)
+    tk = {"property_to_learn": "energy", "prior": "mean"}
+    pk = {"property_to_predict": "estimated_energy"}
+    lam_rng, sig_rng, nl, ns, depth = (2.0 ** -30, 2.0 ** -6), (0.5, 8.0), 3, 4, 2
+
+    model = M.kreg(model_file=str(tmp_path / "lg"))
+    model.hyperparameters["lambda"].minval, model.hyperparameters["lambda"].maxval = lam_rng
+    model.hyperparameters["sigma"].minval, model.hyperparameters["sigma"].maxval = sig_rng
+    model.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="log2grid",
+                                   optimization_algorithm_kwargs={"depth": depth, "points": {"lambda": nl, "sigma": ns}},
+                                   training_kwargs=tk, prediction_kwargs=pk,
+                                   subtraining_molecular_database=sub, validation_molecular_database=val)
+    got = (model.hyperparameters["lambda"].value, model.hyperparameters["sigma"].value, model.validation_loss)
+    assert len(model.grid_trace) > 0
+
+    ref = M.kreg(model_file=str(tmp_path / "lgref"))
+
+    def loss(lam, sigma):
+        ref.hyperparameters["lambda"].value, ref.hyperparameters["sigma"].value = lam, sigma
+        return ref.calculate_validation_loss(training_kwargs=dict(tk), prediction_kwargs=dict(pk),
+                                             subtraining_molecular_database=sub, validation_molecular_database=val)
+
+    def zoom(lo, hi, n, f):
+        best = None
+        for _ in range(depth):
+            step = 0.0 if n == 1 else (hi - lo) / (n - 1)
+            lvl = None
+            for i in range(n):
+                x = lo + step * i
+                r = f(x)
+                if lvl is None or r[0] < lvl[1][0]:
+                    lvl = (x, r)
+            best = lvl
+            lo, hi = best[0] - step, best[0] + step
+        return best
+
+    def at_sigma(lg_sigma):
+        x, r = zoom(np.log2(lam_rng[0]), np.log2(lam_rng[1]), nl, lambda lg_lam: (loss(2.0 ** lg_lam, 2.0 ** lg_sigma),))
+        return (r[0], 2.0 ** x)
+
+    xs, (err, lam) = zoom(np.log2(sig_rng[0]), np.log2(sig_rng[1]), ns, at_sigma)
+    assert got[0] == lam and got[1] == 2.0 ** xs
+    assert abs(got[2] - err) <= 1e-9 * err
