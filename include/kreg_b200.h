@@ -43,7 +43,7 @@ extern "C" {
 #define KREG_E_CUDA (-4)        /* a CUDA runtime / cuSOLVER call failed (see kreg_last_error) */
 
 #define KREG_MIN_NATOMS 2
-#define KREG_MAX_NATOMS 21 /* largest molecule whose accumulators + test tile fit one SM (D = 210) */
+#define KREG_MAX_NATOMS 24 /* largest molecule whose accumulators + test tile fit one SM (D = 276) */
 
 /* kreg_build_kernel_matrix `fill` argument: which part of the symmetric K is written */
 #define KREG_FILL_LOWER 0 /* K[i][j], j <= i (row-major lower == column-major upper, potrf 'U') */

@@ -141,7 +141,7 @@ extern "C" int kreg_hessian(int natoms, int64_t ntrain, const double *X_train, c
     return launch_hessian_nat<N>(ntrain, X_train, alpha_val, xeq, inv_s2, npoints, xyz, H, st);
     KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9)
     KREG_CASE(10) KREG_CASE(11) KREG_CASE(12) KREG_CASE(13) KREG_CASE(14) KREG_CASE(15) KREG_CASE(16) KREG_CASE(17)
-    KREG_CASE(18) KREG_CASE(19) KREG_CASE(20) KREG_CASE(21)
+    KREG_CASE(18) KREG_CASE(19) KREG_CASE(20) KREG_CASE(21) KREG_CASE(22) KREG_CASE(23) KREG_CASE(24)
 #undef KREG_CASE
     default:
       return KREG_E_UNSUPPORTED;

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(32) pack_model_kernel(int nat, int64_t ntrain,
   int launch_predict_##r(int nat, const PredictArgs &a, bool has_v, int sms, void *ws, size_t ws_bytes, bool query, \
                          size_t *need, cudaStream_t st);                                                            \
   int tile_rows_##r(int nat, bool has_v);
-KREG_DECL_RANGE(r0) KREG_DECL_RANGE(r1) KREG_DECL_RANGE(r2) KREG_DECL_RANGE(r3)
+KREG_DECL_RANGE(r0) KREG_DECL_RANGE(r1) KREG_DECL_RANGE(r2) KREG_DECL_RANGE(r3) KREG_DECL_RANGE(r4)
 #undef KREG_DECL_RANGE
 
 static int launch_predict(int nat, const PredictArgs &a, bool has_v, int sms, void *ws, size_t ws_bytes, bool query,
@@ -165,14 +165,16 @@ static int launch_predict(int nat, const PredictArgs &a, bool has_v, int sms, vo
   if (nat <= 9) return launch_predict_r0(nat, a, has_v, sms, ws, ws_bytes, query, need, st);
   if (nat <= 15) return launch_predict_r1(nat, a, has_v, sms, ws, ws_bytes, query, need, st);
   if (nat <= 20) return launch_predict_r2(nat, a, has_v, sms, ws, ws_bytes, query, need, st);
-  return launch_predict_r3(nat, a, has_v, sms, ws, ws_bytes, query, need, st);
+  if (nat <= 22) return launch_predict_r3(nat, a, has_v, sms, ws, ws_bytes, query, need, st);
+  return launch_predict_r4(nat, a, has_v, sms, ws, ws_bytes, query, need, st);
 }
 
 static int tile_rows(int nat, bool has_v) {
   if (nat <= 9) return tile_rows_r0(nat, has_v);
   if (nat <= 15) return tile_rows_r1(nat, has_v);
   if (nat <= 20) return tile_rows_r2(nat, has_v);
-  return tile_rows_r3(nat, has_v);
+  if (nat <= 22) return tile_rows_r3(nat, has_v);
+  return tile_rows_r4(nat, has_v);
 }
 
 }  // namespace kreg

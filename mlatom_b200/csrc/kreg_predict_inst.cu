@@ -1,9 +1,9 @@
 // kreg_predict_inst.cu -- instantiates the prediction kernels for one range of molecule sizes.
-// Compiled four times with -DKREG_INST=0..3 (Makefile); each object exports one pair of range functions.
+// Compiled five times with -DKREG_INST=0..4 (Makefile); each object exports one pair of range functions.
 #include "kreg_predict_kernel.cuh"
 
 #ifndef KREG_INST
-#error "compile with -DKREG_INST=0..3"
+#error "compile with -DKREG_INST=0..4"
 #endif
 
 namespace kreg {
@@ -17,9 +17,12 @@ namespace kreg {
 #elif KREG_INST == 2
 #define KREG_RANGE_CASES KREG_CASE(16) KREG_CASE(17) KREG_CASE(18) KREG_CASE(19) KREG_CASE(20)
 #define KREG_RANGE_NAME(x) x##_r2
-#else
-#define KREG_RANGE_CASES KREG_CASE(21)
+#elif KREG_INST == 3
+#define KREG_RANGE_CASES KREG_CASE(21) KREG_CASE(22)
 #define KREG_RANGE_NAME(x) x##_r3
+#else
+#define KREG_RANGE_CASES KREG_CASE(23) KREG_CASE(24)
+#define KREG_RANGE_NAME(x) x##_r4
 #endif
 
 // returns KREG_E_UNSUPPORTED when `nat` is not in this object's range

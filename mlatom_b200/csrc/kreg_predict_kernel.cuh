@@ -13,11 +13,12 @@ namespace kreg {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, int NW = kWarps>
 struct PredictCfg {
   static constexpr TcShape sh = TcShape(NAT);
   static constexpr int D = sh.D, KS = sh.KS, KS2 = sh.KS2, NT = sh.NT;
-  static constexpr int ROWS = kWarps * MT * 8;
+  static constexpr int WARPS = NW, THREADS = NW * 32;
+  static constexpr int ROWS = NW * MT * 8;
   static constexpr int TS = (NT * 8 > KS * 4 ? NT * 8 : KS * 4) + (A_IN_SMEM ? 4 : 0);  // +4: conflict-free A loads
   static constexpr int CHUNK = sh.chunk_doubles(HAS_V);
   static constexpr int STAGE = CHUNK * GPS;
@@ -95,9 +96,10 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
   }
 }
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
-__global__ void __launch_bounds__(kThreads, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
-  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps>
+__global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
+  constexpr int kWarps = NW, kThreads = NW * 32;  // shadow the defaults: this kernel's own CTA shape
   constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
   extern __shared__ __align__(128) double smem[];
   double *ring = smem + C::SM_RING;
@@ -320,15 +322,15 @@ static void plan_slices(int ngroups, int64_t blocks, int sms, int *nslices, int 
   *nslices = (all_stages + per - 1) / per;
 }
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW>
 static int launch_predict_g(PredictArgs a, cudaStream_t st) {
-  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
-  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G>;
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
+  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G, NW>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
   const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
   dim3 grid((unsigned)blocks, (unsigned)(a.nslices > 1 ? a.nslices : 1));
-  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(a);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
   KREG_LAUNCH_CHECK();
   if (a.nslices > 1) {
     auto fin = predict_finish_kernel<NAT, C::ROWS, C::TS>;
@@ -341,19 +343,19 @@ static int launch_predict_g(PredictArgs a, cudaStream_t st) {
 }
 
 // Workspace (bytes) the small-batch mode needs for this launch; 0 when the batch is large enough to run unsplit.
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, int NW>
 static size_t predict_ws_cfg(int ngroups, int64_t npoints, int sms, int *nslices, int *stages_per_slice) {
-  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>;
+  using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
   const int64_t blocks = (npoints + C::ROWS - 1) / C::ROWS;
   plan_slices<GPS>(ngroups, blocks, sms, nslices, stages_per_slice);
   return *nslices > 1 ? (size_t)*nslices * blocks * C::ROWS * C::TS * sizeof(double) : 0;
 }
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, int NW = kWarps>
 static int launch_predict_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes, bool query, size_t *need,
                               cudaStream_t st) {
   int nslices, per;
-  const size_t bytes = predict_ws_cfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE>(a.ngroups, a.npoints, sms, &nslices, &per);
+  const size_t bytes = predict_ws_cfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>(a.ngroups, a.npoints, sms, &nslices, &per);
   if (query) {
     *need = bytes;
     return KREG_OK;
@@ -367,8 +369,8 @@ static int launch_predict_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes,
     a.partial = static_cast<double *>(ws);
   }
   // energy-only requests skip the second GEMM entirely (the split mode always carries the full accumulators)
-  return (a.G || a.nslices > 1) ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true>(a, st)
-                                : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false>(a, st);
+  return (a.G || a.nslices > 1) ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true, NW>(a, st)
+                                : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false, NW>(a, st);
 }
 
 template <int NAT>
@@ -383,10 +385,15 @@ static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *w
   } else if constexpr (sh.D <= 66) {
     return has_v ? launch_predict_cfg<NAT, 1, true, false, 1, 4>(a, sms, ws, ws_bytes, query, need, st)
                  : launch_predict_cfg<NAT, 2, false, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st);
-  } else {
+  } else if constexpr (sh.D <= 210) {
     // large molecules: accumulators fill the register file; test-row fragments stay in shared memory
     return has_v ? launch_predict_cfg<NAT, 1, true, true, 1, 2>(a, sms, ws, ws_bytes, query, need, st)
                  : launch_predict_cfg<NAT, 1, false, true, 1, 3>(a, sms, ws, ws_bytes, query, need, st);
+  } else {
+    // 22-24 atoms (D <= 276): the 64-row test tile plus a two-stage ring no longer fit next to a gradient model's
+    // chunks (72 KB each), so those run with four warps (32 test rows) per CTA; value models keep eight warps
+    return has_v ? launch_predict_cfg<NAT, 1, true, true, 1, 2, 4>(a, sms, ws, ws_bytes, query, need, st)
+                 : launch_predict_cfg<NAT, 1, false, true, 1, 2>(a, sms, ws, ws_bytes, query, need, st);
   }
 }
 
@@ -395,7 +402,7 @@ template <int NAT>
 static int tile_rows_nat(bool has_v) {
   constexpr TcShape sh(NAT);
   const int mt = sh.D <= 36 ? 2 : sh.D <= 66 ? (has_v ? 1 : 2) : 1;
-  return kWarps * mt * 8;
+  return (sh.D > 210 && has_v ? 4 : kWarps) * mt * 8;
 }
 
 }  // namespace kreg

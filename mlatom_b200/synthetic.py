@@ -54,21 +54,29 @@ ASPIRIN_EQ = np.array(
 ASPIRIN_Z = np.array([8, 8, 8, 8, 6, 6, 6, 6, 6, 6, 6, 6, 6, 1, 1, 1, 1, 1, 1, 1, 1], dtype=np.int32)
 
 
+# three more hydrogens around the aspirin frame (>= 1.1 Angstrom from every other atom): 22-24 atom test molecules
+EXTRA_EQ = np.array([[5.3045, 0.1554, 0.3], [-4.9374, 0.5554, -0.2], [0.0982, 4.0372, 0.5]])
+
+
 def equilibrium(natoms: int) -> np.ndarray:
-    """Equilibrium geometry for `natoms` atoms: ethanol (9), aspirin (21), or the first
-    `natoms` atoms of aspirin for other sizes (used by edge-case tests)."""
+    """Equilibrium geometry for `natoms` atoms: ethanol (9), aspirin (21), the first `natoms` atoms of aspirin for
+    smaller sizes, aspirin plus up to three far hydrogens for 22-24 (edge-case tests)."""
     if natoms == 9:
         return ETHANOL_EQ.copy()
     if natoms == 21:
         return ASPIRIN_EQ.copy()
     if 2 <= natoms < 21:
         return ASPIRIN_EQ[:natoms].copy()
+    if 21 < natoms <= 24:
+        return np.vstack([ASPIRIN_EQ, EXTRA_EQ[: natoms - 21]])
     raise ValueError("no synthetic equilibrium geometry for %d atoms" % natoms)
 
 
 def atomic_numbers(natoms: int) -> np.ndarray:
     if natoms == 9:
         return ETHANOL_Z.copy()
+    if natoms > 21:
+        return np.concatenate([ASPIRIN_Z, np.ones(natoms - 21, dtype=ASPIRIN_Z.dtype)])
     return ASPIRIN_Z[:natoms].copy()
 
 

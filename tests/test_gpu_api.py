@@ -116,8 +116,10 @@ def test_grid_search_fused_equals_pointwise_on_device(M, tmp_path):
 
 
 def test_log2_grid_search_on_device(M, tmp_path):
-    """MLatomF's recursive log2 grid (A_KRR.f90:1049-1376) on the fused device path: the first level is a plain grid,
-    every later level can only lower the loss; the winner retrains to the loss the search reported."""
+    """MLatomF's recursive log2 grid (A_KRR.f90:1049-1376) on the fused device path.  With an odd number of points
+    every zoomed level contains the previous winner, so deeper searches can only lower the loss and the result is the
+    minimum of everything visited (with an even number the reference -- and this -- may move off the previous best);
+    the winner retrains to the loss the search reported."""
     sub, _, _, _ = make_db(9, 60, 1)
     val, _, _, _ = make_db(9, 40, 3)
     kw = dict(hyperparameters=["lambda", "sigma"], optimization_algorithm="log2grid",
@@ -128,12 +130,12 @@ def test_log2_grid_search_on_device(M, tmp_path):
         model = M.kreg(model_file=str(tmp_path / f"lg{depth}"))
         model.hyperparameters["lambda"].minval, model.hyperparameters["lambda"].maxval = 2.0 ** -35, 2.0 ** -6
         model.hyperparameters["sigma"].minval, model.hyperparameters["sigma"].maxval = 0.25, 16.0
-        model.optimize_hyperparameters(optimization_algorithm_kwargs={"depth": depth, "points": {"lambda": 3, "sigma": 4}}, **kw)
+        model.optimize_hyperparameters(optimization_algorithm_kwargs={"depth": depth, "points": {"lambda": 3, "sigma": 5}}, **kw)
         best = min(t[2] for t in model.grid_trace)
         assert abs(model.validation_loss - best) <= 1e-8 * best
         assert 0.25 / 4 <= model.hyperparameters["sigma"].value <= 64.0
         losses.append(model.validation_loss)
-        assert len(model.grid_trace) == sum(4 * 3 * depth for _ in range(depth))
+        assert len(model.grid_trace) == depth * 5 * depth * 3
     assert losses[1] <= losses[0] * (1 + 1e-12)
 
 

@@ -107,7 +107,7 @@ def test_golden_hessian(golden, eng):
         assert not h.any()
 
 
-@pytest.mark.parametrize("nat,ntr,nte", [(2, 5, 3), (3, 33, 4), (12, 100, 7), (16, 64, 3), (21, 40, 2)])
+@pytest.mark.parametrize("nat,ntr,nte", [(2, 5, 3), (3, 33, 4), (12, 100, 7), (16, 64, 3), (21, 40, 2), (24, 37, 3)])
 def test_hessian_vs_oracle(eng, oracle, nat, ntr, nte):
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 11), S.geometries(eq, nte, 12)
@@ -144,7 +144,8 @@ def test_golden_train_residual_and_prediction(golden, eng):
 # ---- seeded comparisons with the oracle at larger sizes -------------------------------------
 
 @pytest.mark.parametrize("nat,ntr,nte,sigma", [(9, 777, 1500, 1.0), (9, 64, 300, 0.03125), (3, 50, 257, 0.7),
-                                                (12, 130, 200, 1.5), (21, 200, 333, 2.0), (2, 9, 5, 1.0)])
+                                                (12, 130, 200, 1.5), (21, 200, 333, 2.0), (2, 9, 5, 1.0),
+                                                (24, 210, 301, 2.2), (22, 64, 100, 2.0)])
 def test_predict_values_model_vs_oracle(eng, oracle, nat, ntr, nte, sigma):
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
@@ -161,7 +162,7 @@ def test_predict_values_model_vs_oracle(eng, oracle, nat, ntr, nte, sigma):
 
 
 @pytest.mark.parametrize("nat,ntr,nte,with_values", [(9, 40, 130, True), (9, 33, 70, False), (5, 61, 90, True),
-                                                     (21, 17, 40, True)])
+                                                     (21, 17, 40, True), (24, 19, 70, True), (23, 9, 33, False)])
 def test_predict_gradient_model_vs_oracle(eng, oracle, nat, ntr, nte, with_values):
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
@@ -280,7 +281,8 @@ def test_full_size_properties(eng):
     assert (eh - e.cpu()).abs().max() <= 1e-12 * e.abs().max().item() and (gh - g.cpu()).abs().max() <= 1e-11
 
 
-@pytest.mark.parametrize("nat,ntr,use_grads", [(9, 2000, False), (9, 300, True), (21, 600, False), (5, 100, False)])
+@pytest.mark.parametrize("nat,ntr,use_grads", [(9, 2000, False), (9, 300, True), (21, 600, False), (5, 100, False),
+                                               (24, 500, False), (24, 40, True)])
 def test_small_batch_latency_mode_vs_oracle(eng, oracle, nat, ntr, use_grads):
     """Single-geometry / small-batch predictions (MD, geometry optimisation) split the training set over the chip;
     they must agree with the oracle and with the same geometries predicted inside a large batch."""
@@ -306,9 +308,9 @@ def test_small_batch_latency_mode_vs_oracle(eng, oracle, nat, ntr, use_grads):
         assert (e_only - e).abs().max().item() <= 1e-12 * max(1.0, np.abs(sc).max())
 
 
-@pytest.mark.parametrize("nat", list(range(2, 22)))
+@pytest.mark.parametrize("nat", list(range(2, 25)))
 def test_every_supported_molecule_size(eng, oracle, nat):
-    """Natoms = 2..21 (KREG_MIN/MAX_NATOMS): K blocks and E/dE for a gradient-trained model against the oracle."""
+    """Natoms = 2..24 (KREG_MIN/MAX_NATOMS): K blocks and E/dE for a gradient-trained model against the oracle."""
     ntr, nte = 11, 23
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
