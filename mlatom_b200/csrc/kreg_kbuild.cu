@@ -462,6 +462,117 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   }
 }
 
+// Small molecules (D <= 45): one THREAD per geometry pair.  X_j - X_i lives in that thread's registers (LDS.128 from rows
+// whose stride is an odd number of 16-byte units: conflict-free), E_i arrives as warp-wide broadcasts, d^2 needs no
+// shuffles, and the value-gradient rows go straight from registers to K (lanes = consecutive j: coalesced).  Only the
+// pair terms for grad_emit_kernel are staged through shared memory.  About a third of the shared-memory wavefronts of
+// the cooperative kernel above, which is what bounds it (profiles/r01_gradk_ncu.txt: L1 91 %).
+template <int NAT>
+struct PairSmall {
+  using C = GradCfg<NAT>;
+  static constexpr int JT = 128;                                 // pairs (= threads) per CTA
+  static constexpr int D = C::D;
+  static constexpr int D2 = (D + 1) & ~1;                        // doubles copied per descriptor row (16-byte multiple)
+  static constexpr int XP = ((D2 / 2) % 2) ? D2 : D2 + 2;        // shared row stride: odd count of 16-byte units
+  static constexpr int ES = (NAT * NAT * 3 + 1) & ~1;
+  static constexpr int PWS = C::PW | 1;
+  static constexpr int OFF_XI = ES;
+  static constexpr int OFF_XJ = OFF_XI + D2;
+  static constexpr int OFF_US = OFF_XJ + JT * XP;
+  static constexpr int OFF_TAB = (OFF_US + JT * PWS + 1) & ~1;
+  static constexpr int OFF_BAR = OFF_TAB + 64;
+  static constexpr int DOUBLES = OFF_BAR + 2;
+};
+
+template <int NAT>
+__global__ void __launch_bounds__(128) pair_terms_small_kernel(const GradArgs a) {
+  using C = GradCfg<NAT>;
+  using SM = PairSmall<NAT>;
+  constexpr int G3 = C::G3, PW = C::PW, PWS = SM::PWS, D = C::D, D2 = SM::D2, XP = SM::XP, JT = SM::JT;
+  extern __shared__ __align__(128) double qsm[];
+  double *Ei = qsm, *Xi = qsm + SM::OFF_XI, *Xj = qsm + SM::OFF_XJ, *Us = qsm + SM::OFF_US, *tab = qsm + SM::OFF_TAB;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(qsm + SM::OFF_BAR);
+
+  const int64_t i = blockIdx.y;
+  const int64_t rbase = a.nv + i * G3;
+  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t jend = (a.nv || full) ? a.ntr : i + 1;  // value-gradient rows need every j
+  const int64_t j0 = (int64_t)blockIdx.x * JT;
+  if (j0 >= jend) return;
+  const int nj = (int)(jend - j0 < JT ? jend - j0 : JT);
+  const int tid = threadIdx.x;
+  const bool active = tid < nj;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bar[0], (unsigned)((SM::ES + D2 + nj * D2) * 8));
+    bulk_g2s(Ei, a.E + i * a.ES, SM::ES * 8, &bar[0]);
+    bulk_g2s(Xi, a.Xc + i * a.XS, D2 * 8, &bar[0]);
+  }
+  fill_exp_table(tab, tid, JT);
+  __syncthreads();  // barrier armed (and table filled) before anyone adds copies to it or waits on it
+  if (active) bulk_g2s(Xj + tid * XP, a.Xc + (j0 + tid) * a.XS, D2 * 8, &bar[0]);  // one padded row per thread
+  mbar_wait(&bar[0], 0);
+
+  if (active) {
+    double dl[D2];
+    {
+      const double2 *row = reinterpret_cast<const double2 *>(Xj + tid * XP);
+      const double2 *xi2 = reinterpret_cast<const double2 *>(Xi);
+#pragma unroll
+      for (int p = 0; p < D2 / 2; p++) {
+        const double2 r = row[p], x = xi2[p];
+        dl[2 * p] = r.x - x.x;
+        dl[2 * p + 1] = r.y - x.y;
+      }
+    }
+    double d2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; d++) d2 = fma(dl[d], dl[d], d2);
+    const double k = (j0 + tid == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
+    const double ks = k * a.inv_s2;
+    double *us = Us + tid * PWS;
+    us[0] = ks;
+    us[1] = 0.0;
+    double *kcol = a.K + rbase * a.ldk + j0 + tid;  // K[rbase + q][j]
+    const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
+#pragma unroll
+    for (int aa = 0; aa < NAT; aa++) {
+      const double *ea = Ei + aa * NAT * 3;
+      double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int c = 0; c < NAT; c++)
+        if (c != aa) {
+          const double v = dl[pair_index(NAT, aa < c ? aa : c, aa < c ? c : aa)];
+          s[0] = fma(ea[c * 3 + 0], v, s[0]);
+          s[1] = fma(ea[c * 3 + 1], v, s[1]);
+          s[2] = fma(ea[c * 3 + 2], v, s[2]);
+        }
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int q = aa * 3 + t;
+        us[2 + q] = s[t];
+        if (a.nv) {
+          const int64_t row = rbase + q;
+          if (interior || (row >= a.row_begin && row < a.row_end)) {
+            const double v = ks * s[t];
+            kcol[(int64_t)q * a.ldk] = v;
+            if (full) a.K[(j0 + tid) * a.ldk + row] = v;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // pair terms -> workspace (coalesced); only pairs whose gradient-gradient block is emitted are read back
+  double *P = a.P + (i * a.ntr + j0) * PW;
+  const int64_t jgg = full ? a.ntr : i + 1;
+  const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
+  for (int e = tid; e < np * PW; e += JT) P[e] = Us[(e / PW) * PWS + e % PW];
+}
+
 // CTA = ONE geometry i x up to NJB*TJ geometries j, walked TJ at a time; thread = matrix column (j, b, u) of the current
 // step.  This thread's 3 Nat values E_i(b, .)[.] live in registers for the whole strip; per step the pair terms, the X_j
 // rows and the E_j blocks of the TJ geometries -- three contiguous global ranges -- arrive as three TMA bulk copies
@@ -599,7 +710,15 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) gr
 template <int NAT>
 static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
   using C = GradCfg<NAT>;
-  {
+  if constexpr (C::D <= 45) {
+    using SM = PairSmall<NAT>;
+    auto kern = pair_terms_small_kernel<NAT>;
+    const size_t smem = (size_t)SM::DOUBLES * sizeof(double);
+    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((a.ntr + SM::JT - 1) / SM::JT), (unsigned)a.ntr);
+    kern<<<grid, SM::JT, smem, st>>>(a);
+    KREG_LAUNCH_CHECK();
+  } else {
     auto kern = pair_terms_kernel<NAT>;
     const size_t smem = (size_t)PairSmem<NAT>::doubles(a.XS) * sizeof(double);
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
