@@ -478,14 +478,15 @@ struct PairSmall {
   static constexpr int PWS = C::PW | 1;
   static constexpr int OFF_XI = ES;
   static constexpr int OFF_XJ = OFF_XI + D2;
-  static constexpr int OFF_US = OFF_XJ + JT * XP;
-  static constexpr int OFF_TAB = (OFF_US + JT * PWS + 1) & ~1;
+  static constexpr int OFF_US = OFF_XJ;                          // the pair-term block reuses the X_j rows (dead once in registers)
+  static constexpr int STAGE = JT * XP > JT * PWS ? JT * XP : JT * PWS;
+  static constexpr int OFF_TAB = (OFF_XJ + STAGE + 1) & ~1;
   static constexpr int OFF_BAR = OFF_TAB + 64;
   static constexpr int DOUBLES = OFF_BAR + 2;
 };
 
 template <int NAT>
-__global__ void __launch_bounds__(128) pair_terms_small_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(128, 5) pair_terms_small_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
   using SM = PairSmall<NAT>;
   constexpr int G3 = C::G3, PW = C::PW, PWS = SM::PWS, D = C::D, D2 = SM::D2, XP = SM::XP, JT = SM::JT;
@@ -516,18 +517,19 @@ __global__ void __launch_bounds__(128) pair_terms_small_kernel(const GradArgs a)
   if (active) bulk_g2s(Xj + tid * XP, a.Xc + (j0 + tid) * a.XS, D2 * 8, &bar[0]);  // one padded row per thread
   mbar_wait(&bar[0], 0);
 
+  double dl[D2];
   if (active) {
-    double dl[D2];
-    {
-      const double2 *row = reinterpret_cast<const double2 *>(Xj + tid * XP);
-      const double2 *xi2 = reinterpret_cast<const double2 *>(Xi);
+    const double2 *row = reinterpret_cast<const double2 *>(Xj + tid * XP);
+    const double2 *xi2 = reinterpret_cast<const double2 *>(Xi);
 #pragma unroll
-      for (int p = 0; p < D2 / 2; p++) {
-        const double2 r = row[p], x = xi2[p];
-        dl[2 * p] = r.x - x.x;
-        dl[2 * p + 1] = r.y - x.y;
-      }
+    for (int p = 0; p < D2 / 2; p++) {
+      const double2 r = row[p], x = xi2[p];
+      dl[2 * p] = r.x - x.x;
+      dl[2 * p + 1] = r.y - x.y;
     }
+  }
+  __syncthreads();  // every X_j row is in registers: its shared-memory space becomes the output block
+  if (active) {
     double d2 = 0.0;
 #pragma unroll
     for (int d = 0; d < D; d++) d2 = fma(dl[d], dl[d], d2);
