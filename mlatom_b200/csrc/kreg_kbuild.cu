@@ -324,17 +324,31 @@ __global__ void __launch_bounds__(128) jacobian_rows_kernel(int nat, int64_t n, 
 //                       loads, one barrier, then 3 Nat stores per thread.  Small, short-lived CTAs (4 per SM) write
 //                       flat 3 Nat-row strips -- the schedule that measured fastest for this layout
 //                       (profiles/r01_store_pattern.txt).
+// tuning knobs of grad_emit_kernel (tools/build_variant.sh builds A/B variants with other values)
+#ifndef KREG_EMIT_NJB
+#define KREG_EMIT_NJB 8
+#endif
+#ifndef KREG_EMIT_TJEVEN
+#define KREG_EMIT_TJEVEN 1
+#endif
+#ifndef KREG_EMIT_MAXCOLS
+#define KREG_EMIT_MAXCOLS 256
+#endif
 template <int NAT>
 struct GradCfg {
   static constexpr int G3 = 3 * NAT;
   static constexpr int G3P = (G3 + 1) & ~1;   // E_i rows padded to an even length
   static constexpr int PW = (G3 + 3) & ~1;    // doubles per pair in the workspace: [k/s^2, pad, u_i[0..G3)] (+pad)
   static constexpr int D = NAT * (NAT - 1) / 2;
-  static constexpr int TJ = (256 / G3) < 1 ? 1 : (256 / G3 > 16 ? 16 : 256 / G3);  // geometries j per emit CTA
+  static constexpr int TJ0 = (KREG_EMIT_MAXCOLS / G3) < 2 ? 2 : (KREG_EMIT_MAXCOLS / G3 > 16 ? 16 : KREG_EMIT_MAXCOLS / G3);
+  // geometries j per emit step: even, so that with an even ldk every CTA's row segments start and end on 32-byte
+  // sectors (Nat = 9: 216 columns = 54 sectors; 243 columns left partial sectors at both ends of every segment and
+  // cost 5 % of the whole assembly, profiles/r01_store_pattern.txt)
+  static constexpr int TJ = KREG_EMIT_TJEVEN ? (TJ0 & ~1) : TJ0;
   static constexpr int COLS = TJ * G3;
   static constexpr int THREADS = ((COLS + 31) / 32) * 32;
   static constexpr int JT = NAT <= 12 ? 64 : 16;  // geometries j per pair-terms CTA (shared-memory budget)
-  static constexpr int NJB = 8;               // steps (of TJ geometries) walked by one emit CTA
+  static constexpr int NJB = KREG_EMIT_NJB;   // steps (of TJ geometries) walked by one emit CTA
 };
 
 // shared-memory carve-up of pair_terms_kernel (doubles), sized for the run-time descriptor row stride XS.  The X_j
@@ -594,7 +608,7 @@ struct EmitSmem {
 };
 
 template <int NAT>
-__global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) grad_emit_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<NAT>::THREADS <= 256 ? 2 : 1)) grad_emit_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
   using SM = EmitSmem<NAT>;
   constexpr int G3 = C::G3, G3P = C::G3P, PW = C::PW, TJ = C::TJ, NJB = C::NJB, D = C::D, EJ = SM::EJ;
@@ -648,62 +662,58 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 ? 2 : 1)) gr
     __syncthreads();  // everyone left buffer (n+1)&1 (read during step n-1)
     if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
     mbar_wait(&bar[n & 1], (n >> 1) & 1);  // step n's operands have landed
-    const int64_t j = jb0 + (int64_t)n * TJ + jl;
-    if (!colthread || j >= jend) continue;
+    const int64_t jb = jb0 + (int64_t)n * TJ;
+    const int64_t j = jb + jl;
+    const bool work = colthread && j < jend;
     const int buf = n & 1;
-    const double *pb = Pb + buf * TJ * PW + jl * PW;
-    const double *xj = Xj + buf * TJ * SM::XSMAX + jl * XS;
-    const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * G3 + u;  // E_j(b, c)[u] at ejb[3c]
-    double nej[NAT];
+    const double *pb = Pb + buf * TJ * PW + (colthread ? jl : 0) * PW;
+    double nej[NAT], kjd[3], kj = 0.0, c2 = 0.0;
+    if (work) {
+      const double *xj = Xj + buf * TJ * SM::XSMAX + jl * XS;
+      const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * G3 + u;  // E_j(b, c)[u] at ejb[3c]
 #pragma unroll
-    for (int c = 0; c < NAT; c++) nej[c] = -ejb[3 * c];
-    const double kj = pb[0];
-    double sj = 0.0;  // -u_j[col] = -sum_c E_j(b,c)[u] (X_j - X_i)[d_bc]
+      for (int c = 0; c < NAT; c++) nej[c] = -ejb[3 * c];
+      kj = pb[0];
+      double sj = 0.0;  // -u_j[col] = -sum_c E_j(b,c)[u] (X_j - X_i)[d_bc]
 #pragma unroll
-    for (int c = 0; c < NAT; c++)
-      if (c != b) {
-        const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
-        sj = fma(nej[c], xj[d] - Xi[d], sj);
-      }
-    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
-    double kjd[3];  // diagonal 3x3 block (a == b): (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u]
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      double acc = 0.0;
-#pragma unroll
-      for (int c = 0; c < NAT; c++) acc = fma(e27[c * 3 + t], nej[c], acc);
-      kjd[t] = -acc * kj;
-    }
-    const double2 *u2 = reinterpret_cast<const double2 *>(pb + 2);
-    double *dst = a.K + rbase * ld + a.nv + j * G3 + col;
-    if (interior && j != i) {
-      // the common case: (k/s^2) [ E_i(a,b)[t] E_j(b,a)[u] - u_i[q] u_j[col] / s^2 ]
-#pragma unroll
-      for (int q2 = 0; q2 < G3P / 2; q2++) {
-        const double2 uq = u2[q2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int q = 2 * q2 + h;
-          if (q < G3) {
-            const int aa = q / 3, t = q % 3;
-            double v = fma(h ? uq.y : uq.x, c2, kj * (e27[q] * nej[aa]));
-            if (aa == b) v += kjd[t];
-            *dst = v;
-            dst += ld;
-          }
+      for (int c = 0; c < NAT; c++)
+        if (c != b) {
+          const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
+          sj = fma(nej[c], xj[d] - Xi[d], sj);
         }
+      c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+#pragma unroll
+      for (int t = 0; t < 3; t++) {  // diagonal 3x3 block (a == b): (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u]
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < NAT; c++) acc = fma(e27[c * 3 + t], nej[c], acc);
+        kjd[t] = -acc * kj;
       }
-    } else {
-      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal; operands re-read
-      const double *eig = a.E + i * a.ES + b * G3;
+    }
+    if (work) {
+      double *dst = a.K + rbase * ld + a.nv + j * G3 + col;
+      if (interior && j != i) {
+#pragma unroll
+        for (int q = 0; q < G3; q++) {
+          const int aa = q / 3, t = q % 3;
+          double v = fma(pb[2 + q], c2, kj * (e27[q] * nej[aa]));
+          if (aa == b) v += kjd[t];
+          *dst = v;
+          dst += ld;
+        }
+      } else {
+        // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal; operands re-read
+        const double *eig = a.E + i * a.ES + b * G3;
+        const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * G3 + u;
 #pragma unroll 1
-      for (int q = 0; q < G3; q++) {
-        const int aa = q / 3, t = q % 3;
-        double v = fma(pb[2 + q], c2, kj * (eig[q] * -ejb[3 * aa]));
-        if (aa == b) v += (t == 0 ? kjd[0] : t == 1 ? kjd[1] : kjd[2]);
-        if (j == i && q == col) v += a.lambdag;
-        const int64_t r = rbase + q;
-        if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * ld] = v;
+        for (int q = 0; q < G3; q++) {
+          const int aa = q / 3, t = q % 3;
+          double v = fma(pb[2 + q], c2, kj * (eig[q] * -ejb[3 * aa]));
+          if (aa == b) v += (t == 0 ? kjd[0] : t == 1 ? kjd[1] : kjd[2]);
+          if (j == i && q == col) v += a.lambdag;
+          const int64_t r = rbase + q;
+          if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * ld] = v;
+        }
       }
     }
   }
@@ -742,9 +752,13 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
 #define KREG_CASE(N) \
   case N:            \
     return launch_grad_nat<N>(a, st);
+#ifdef KREG_ONLY_NAT9  /* experiment builds (tools/ab_kbuild.sh): one instantiation, seconds to compile */
+    KREG_CASE(9)
+#else
     KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9)
     KREG_CASE(10) KREG_CASE(11) KREG_CASE(12) KREG_CASE(13) KREG_CASE(14) KREG_CASE(15) KREG_CASE(16) KREG_CASE(17)
     KREG_CASE(18) KREG_CASE(19) KREG_CASE(20) KREG_CASE(21) KREG_CASE(22) KREG_CASE(23) KREG_CASE(24)
+#endif
 #undef KREG_CASE
     default:
       return KREG_E_UNSUPPORTED;
