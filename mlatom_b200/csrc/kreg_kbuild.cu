@@ -334,6 +334,9 @@ __global__ void __launch_bounds__(128) jacobian_rows_kernel(int nat, int64_t n, 
 #ifndef KREG_EMIT_MAXCOLS
 #define KREG_EMIT_MAXCOLS 256
 #endif
+#ifndef KREG_EMIT_MINB
+#define KREG_EMIT_MINB 2
+#endif
 template <int NAT>
 struct GradCfg {
   static constexpr int G3 = 3 * NAT;
@@ -608,7 +611,7 @@ struct EmitSmem {
 };
 
 template <int NAT>
-__global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<NAT>::THREADS <= 256 ? 2 : 1)) grad_emit_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<NAT>::THREADS <= 256 ? KREG_EMIT_MINB : 1)) grad_emit_kernel(const GradArgs a) {
   using C = GradCfg<NAT>;
   using SM = EmitSmem<NAT>;
   constexpr int G3 = C::G3, G3P = C::G3P, PW = C::PW, TJ = C::TJ, NJB = C::NJB, D = C::D, EJ = SM::EJ;
