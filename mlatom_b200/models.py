@@ -100,6 +100,28 @@ class kreg:
             json.dump(model_dict, f, indent=4)
 
     # -- equilibrium geometry (mlatom/models.py:439-457) ---------------------------------------------
+    def get_descriptor(self, molecule=None, molecular_database=None, descriptor_name="re", equilibrium_molecule=None):
+        """RE descriptor of every molecule, stored as ``mol.<descriptor_name>`` and ``mol.descriptor`` like the
+        reference does (mlatom/models.py:402-437) -- computed by ``kreg_descriptors`` on the device, one batch."""
+        if molecular_database is not None:
+            db = molecular_database
+        elif molecule is not None:
+            db = _data.molecular_database([molecule])
+        else:
+            raise ValueError("Either molecule or molecular_database should be provided in input")
+        if getattr(self, "reference_distance_matrix", None) is None:
+            if equilibrium_molecule is None:
+                equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=db)
+            self.reference_distance_matrix = equilibrium_molecule.get_internuclear_distance_matrix()
+            self._reference_xyz = np.asarray(equilibrium_molecule.xyz_coordinates, dtype=np.float64)
+        api = self.__dict__.get("kreg_api") or KREG_API(self.device)
+        dev = api._dev()
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        x = engine.descriptors(t(db.xyz_coordinates), engine.xeq(t(self._reference_xyz))).cpu().numpy()
+        for mol, row in zip(db.molecules, x):
+            setattr(mol, descriptor_name, row)
+            mol.descriptor = row
+
     def get_equilibrium_molecule(self, molecular_database=None):
         first = molecular_database.molecules[0].__dict__
         for name in ("energy", "y"):

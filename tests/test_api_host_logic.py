@@ -257,3 +257,30 @@ def test_log2_grid_search_follows_mlatomf_recursion(fake_engine, tmp_path):
     xs, (err, lam) = zoom(np.log2(sig_rng[0]), np.log2(sig_rng[1]), ns, at_sigma)
     assert got[0] == lam and got[1] == 2.0 ** xs
     assert abs(got[2] - err) <= 1e-9 * err
+
+
+def test_get_descriptor_like_the_reference(fake_engine):
+    """models.py:402-437: RE descriptor stored on every molecule; the reference distance matrix is cached."""
+    db, xyz, e, _ = make_db(D, 5, 6, 1)
+    model = M.kreg()
+    model.get_descriptor(molecular_database=db)
+    eq = xyz[int(np.argmin(e))]
+    pairs = np.triu_indices(5, 1)
+    dist = lambda m: np.linalg.norm(m[:, None] - m[None], axis=-1)[pairs]
+    for mol, m in zip(db.molecules, xyz):
+        assert np.allclose(mol.re, dist(eq) / dist(m), rtol=1e-14) and mol.descriptor is mol.re
+    assert np.allclose(model.reference_distance_matrix, np.linalg.norm(eq[:, None] - eq[None], axis=-1))
+    one = D.molecule.from_arrays(S.atomic_numbers(5), xyz[2])
+    model.get_descriptor(molecule=one, descriptor_name="x")     # cached reference geometry, no energies needed
+    assert np.array_equal(one.x, db.molecules[2].re)
+    with pytest.raises(ValueError):
+        model.get_descriptor()
+    ref_data = reference_mlatom()
+    if ref_data is not None:  # the reference class itself on the reference's data objects
+        import mlatom.models as RM
+
+        rdb, _, _, _ = make_db(ref_data, 5, 6, 1)
+        rmodel = RM.kreg.__new__(RM.kreg)
+        RM.kreg.get_descriptor(rmodel, molecular_database=rdb)
+        for a, b in zip(rdb.molecules, db.molecules):
+            assert np.allclose(a.re, b.re, rtol=1e-14, atol=0)
