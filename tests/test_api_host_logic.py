@@ -284,3 +284,23 @@ def test_get_descriptor_like_the_reference(fake_engine):
         RM.kreg.get_descriptor(rmodel, molecular_database=rdb)
         for a, b in zip(rdb.molecules, db.molecules):
             assert np.allclose(a.re, b.re, rtol=1e-14, atol=0)
+
+
+def test_al_threshold_metric_matches_reference_formula():
+    """al_utils.py:1436-1455 + stats.py:122-128 ('max' and 'm+<n>mad' with MAD = 1.4826 median|v - median v|)."""
+    from mlatom_b200 import al
+
+    v = np.abs(np.random.default_rng(3).standard_normal(101))
+    med = np.median(v)
+    mad = 1.4826 * np.median(np.abs(v - med))
+    assert al.threshold_metric(v, "max") == v.max()
+    assert abs(al.threshold_metric(v, "m+3mad") - (med + 3 * mad)) <= 1e-15
+    assert abs(al.threshold_metric(list(v), "M+2.5MAD") - (med + 2.5 * mad)) <= 1e-15
+    assert al.threshold_metric(v[:1], "m+3mad") == 0.0
+    with pytest.raises(ValueError):
+        al.threshold_metric(v, "m+mad")
+    if os.path.isdir("/root/reference/mlatom"):
+        sys.path.insert(0, "/root/reference")
+        from mlatom import stats as ref_stats
+
+        assert abs(al.median_absolute_deviation(v) - ref_stats.calc_median_absolute_deviation(v)) <= 1e-16

@@ -225,3 +225,55 @@ def test_batched_md_on_device_conserves_energy(M):
         assert drift < 2e-4 * max(1.0, sim.ekin.abs().max().item() * 50), drift
         runs[use_graph] = (out["xyz"].clone(), etot.clone())
     assert torch.equal(runs[True][0], runs[False][0]) and torch.equal(runs[True][1], runs[False][1])
+
+
+def test_active_learning_sampler_on_device(M):
+    """al_utils.py:246-322, 1409-1455 on device tensors: main (E + gradients) and auxiliary (E only) models, uq =
+    |E - E_aux|, threshold = median + 3 MAD of validation deviations; trajectories freeze at their first uncertain
+    geometry; graph replay == eager stepping."""
+    from mlatom_b200 import al, md
+
+    nat, ntr = 9, 150
+    eq = S.equilibrium(nat)
+    xtr = S.geometries(eq, ntr, 1, spread=0.05)
+    e, g = S.pair_potential(xtr, eq)
+    db = D.molecular_database.from_arrays(S.atomic_numbers(nat), xtr, energy=e, energy_gradients=g)
+    main = M.kreg(hyperparameters={"sigma": 1.0, "lambda": 1e-8})
+    main.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients",
+               save_model=False)
+    aux = M.kreg(hyperparameters={"sigma": 1.0, "lambda": 1e-8})
+    aux.train(molecular_database=db, property_to_learn="energy", save_model=False)
+    pm, pa = main.kreg_api._ensure_model(), aux.kreg_api._ensure_model()
+
+    pair = al.UncertaintyPair(pm, pa)
+    xval = torch.from_numpy(S.geometries(eq, 200, 9, spread=0.05)).cuda()
+    out = pair.predict(xval)
+    e_m, _ = pm.predict(xval)
+    e_a, _ = pa.predict(xval, True, False)
+    assert torch.equal(out["energy"], e_m) and torch.equal(out["uq"], (e_m - e_a).abs())
+    thr = pair.calibrate(xval, "m+3mad")
+    uq = out["uq"].cpu().numpy()
+    assert abs(thr - (np.median(uq) + 3 * 1.4826 * np.median(np.abs(uq - np.median(uq))))) <= 1e-15
+    assert al.threshold_metric(uq, "max") == uq.max() and al.threshold_metric(uq[:1], "m+2.5mad") == 0.0
+    with pytest.raises(ValueError):
+        al.threshold_metric(uq, "mean")
+    assert pair.predict(xval)["uncertain"].dtype == torch.bool
+
+    b = 96
+    x0 = torch.from_numpy(S.geometries(eq, b, 5, spread=0.02)).cuda()
+    v0 = torch.from_numpy(np.random.default_rng(6).standard_normal((b, nat, 3)) * 0.06).cuda()   # hot: leaves the data
+    masses = torch.from_numpy(np.where(S.atomic_numbers(nat) == 1, 1.0, 12.0)).cuda()
+    runs = {}
+    for use_graph in (True, False):
+        sim = md.BatchedNVE(pm, x0, v0, masses, dt=0.01, use_graph=use_graph, aux_model=pa, uq_threshold=thr)
+        mid = sim.run(150)
+        x_mid, stop_mid = mid["xyz"].clone(), mid["stop_step"].clone()
+        fin = sim.run(150)
+        runs[use_graph] = (fin["xyz"].clone(), fin["stop_step"].clone(), fin["uq"].clone())
+        frozen = stop_mid >= 0
+        assert frozen.any() and not frozen.all(), "the test needs both stopped and running trajectories"
+        # frozen trajectories did not move during the second leg and keep their stop step
+        assert torch.equal(fin["xyz"][frozen], x_mid[frozen]) and torch.equal(fin["stop_step"][frozen], stop_mid[frozen])
+        assert (fin["uq"][fin["uncertain"]] > thr).all() and (fin["uq"][~fin["uncertain"]] <= thr).all()
+        assert int(fin["stop_step"].max()) <= 300
+    assert all(torch.equal(a, c) for a, c in zip(runs[True], runs[False]))
