@@ -214,7 +214,11 @@ static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   const int64_t ti0 = a.row_begin / kTileI, ti1 = (r1 - 1) / kTileI;
   const int64_t ntj = (a.nb + kTileJ - 1) / kTileJ;
   const int64_t tiles = ntj * (ti1 - ti0 + 1) / ((a.symmetric && !a.all_cols) ? 2 : 1);
-  a.njt = tiles > 40000 ? 16 : tiles > 5000 ? 8 : tiles > 1000 ? 4 : 2;
+#ifdef KREG_NJT_OVERRIDE
+  a.njt = KREG_NJT_OVERRIDE;
+#else
+  a.njt = tiles > 200000 ? 16 : tiles > 50000 ? 8 : tiles > 1000 ? 4 : 2;  // measured: 10k rows 4 (0.25 vs 0.27 ms), 50k flat
+#endif
   dim3 grid((unsigned)((ntj + a.njt - 1) / a.njt), (unsigned)(ti1 - ti0 + 1));
   if (multi) {
     auto kern = values_tile_kernel<KC, true>;
