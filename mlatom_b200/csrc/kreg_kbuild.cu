@@ -674,13 +674,13 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
     const bool work = colthread && j < jend;
     const int buf = n & 1;
     const double *pb = Pb + buf * TJ * PW + (colthread ? jl : 0) * PW;
-    double nej[NAT], kjd[3], kj = 0.0, c2 = 0.0;
     if (work) {
+      double nej[NAT], kjd[3];
       const double *xj = Xj + buf * TJ * SM::XSMAX + jl * XS;
       const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * G3 + u;  // E_j(b, c)[u] at ejb[3c]
 #pragma unroll
       for (int c = 0; c < NAT; c++) nej[c] = -ejb[3 * c];
-      kj = pb[0];
+      const double kj = pb[0];
       double sj = 0.0;  // -u_j[col] = -sum_c E_j(b,c)[u] (X_j - X_i)[d_bc]
 #pragma unroll
       for (int c = 0; c < NAT; c++)
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
           const int d = pair_index(NAT, b < c ? b : c, b < c ? c : b);
           sj = fma(nej[c], xj[d] - Xi[d], sj);
         }
-      c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+      const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
 #pragma unroll
       for (int t = 0; t < 3; t++) {  // diagonal 3x3 block (a == b): (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u]
         double acc = 0.0;
@@ -696,8 +696,6 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
         for (int c = 0; c < NAT; c++) acc = fma(e27[c * 3 + t], nej[c], acc);
         kjd[t] = -acc * kj;
       }
-    }
-    if (work) {
       double *dst = a.K + rbase * ld + a.nv + j * G3 + col;
       if (interior && j != i) {
 #pragma unroll
@@ -711,7 +709,6 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
       } else {
         // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal; operands re-read
         const double *eig = a.E + i * a.ES + b * G3;
-        const double *ejb = Ejs + buf * TJ * EJ + jl * EJ + b * G3 + u;
 #pragma unroll 1
         for (int q = 0; q < G3; q++) {
           const int aa = q / 3, t = q % 3;
