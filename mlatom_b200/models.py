@@ -4,9 +4,9 @@ B200 KREG kernels.
 The constructor, ``train`` and ``predict`` signatures, the hyper-parameter objects, the ``.npz`` model
 file and the convention that predictions are written into the molecule objects (gradients, not forces)
 are those of the reference, so ``ml.md``, ``ml.optimize_geometry`` and the active-learning drivers can
-use this class in place of ``ml.models.kreg``.  ``ml_program`` is accepted for compatibility;
-'KREG_API' (default) and 'B200' select this backend, 'MLatomF' is refused (the Fortran program is not
-part of this package)."""
+use this class in place of ``ml.models.kreg``.  ``ml_program`` keeps its meaning as far as a user can see it:
+'KREG_API' (default; also 'B200') stores models as ``.npz``, 'MLatomF' as MLatomF's unformatted ``.unf`` file (the
+Fortran program itself is not part of this package; its files are read and written, its arithmetic is the device path)."""
 from __future__ import annotations
 
 import json
@@ -66,14 +66,21 @@ class kreg:
         self.ml_program = ml_program
         self.device = device
         self.prior = prior
-        if ml_program.casefold() not in ("kreg_api", "b200"):
-            raise ValueError(f"ml_program={ml_program!r} is not available in mlatom_b200 (use 'KREG_API')")
+        if ml_program.casefold() not in ("kreg_api", "b200", "mlatomf"):
+            raise ValueError(f"ml_program={ml_program!r} is not available in mlatom_b200 (use 'KREG_API' or 'MLatomF')")
+        # 'MLatomF' (models.py:376-378, 478-496, 542-546) selects MLatomF's model-file format, the unformatted .unf of
+        # MLmodel.f90:819-967, instead of the .npz; the arithmetic is the same device path either way (the two
+        # reference programs implement the same equations)
+        self._unf = ml_program.casefold() == "mlatomf"
         if self.model_file is not None:
-            if self.model_file[-4:] != ".npz":
+            if not self._unf and self.model_file[-4:] != ".npz":
                 self.model_file += ".npz"
             if os.path.exists(self.model_file):
                 self.kreg_api = KREG_API(device)
-                self.kreg_api.load_model(self.model_file)
+                if self._unf:
+                    self.kreg_api.load_unf(self.model_file)
+                else:
+                    self.kreg_api.load_model(self.model_file)
         self.hyperparameters = type(self).hyperparameters.copy()
         self.hyperparameters.update(hyperparameters)
         self.nthreads = nthreads
@@ -151,8 +158,8 @@ class kreg:
         self.hyperparameters.update(hyperparameters)
         if save_model:
             if self.model_file is None:
-                self.model_file = f"kreg_{uuid.uuid4()}.npz"
-            elif self.model_file[-4:] != ".npz":
+                self.model_file = f"kreg_{uuid.uuid4()}" + (".unf" if self._unf else ".npz")
+            elif not self._unf and self.model_file[-4:] != ".npz":
                 self.model_file += ".npz"
         self.kreg_api = KREG_API(self.device)
         self.kreg_api.nthreads = self.nthreads
@@ -163,7 +170,10 @@ class kreg:
                             self.equilibrium_molecule, property_to_learn=property_to_learn,
                             xyz_derivative_property_to_learn=xyz_derivative_property_to_learn, prior=prior)
         if save_model:
-            self.kreg_api.save_model(self.model_file)
+            if self._unf:
+                self.kreg_api.save_unf(self.model_file, atomic_numbers=np.asarray(self.equilibrium_molecule.atomic_numbers))
+            else:
+                self.kreg_api.save_model(self.model_file)
 
     def predict(self, molecular_database=None, molecule=None, calculate_energy=False, calculate_energy_gradients=False,
                 calculate_hessian=False, property_to_predict=None, xyz_derivative_property_to_predict=None,

@@ -175,7 +175,35 @@ def test_hyperparameter_objects():
     m2 = M.kreg(hyperparameters={"sigma": 2.0, "lambdaGradXYZ": 1e-3})
     assert m2.hyperparameters["lambdaGradXYZ"].value == 1e-3
     with pytest.raises(ValueError):
-        M.kreg(ml_program="MLatomF")
+        M.kreg(ml_program="PyTorch")
+
+
+def test_ml_program_mlatomf_uses_unf_model_files(fake_engine, tmp_path):
+    """models.py:376-378, 478-496, 542-546: with ml_program='MLatomF' the model file is MLatomF's .unf (MLmodel.f90
+    layout); training, reloading and predicting give what the .npz flavour gives."""
+    db, xyz, e, g = make_db(D, 5, 12, 1)
+    test_db, xte, _, _ = make_db(D, 5, 5, 2, with_labels=False)
+    out = {}
+    for prog in ("KREG_API", "MLatomF"):
+        path = str(tmp_path / ("m_" + prog + (".unf" if prog == "MLatomF" else "")))
+        model = M.kreg(model_file=path, ml_program=prog, hyperparameters={"sigma": 0.9, "lambda": 1e-6})
+        model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients",
+                    prior="mean")
+        assert os.path.exists(model.model_file) and model.model_file.endswith(".unf" if prog == "MLatomF" else ".npz")
+        again = M.kreg(model_file=model.model_file, ml_program=prog)
+        tdb = test_db if prog == "KREG_API" else make_db(D, 5, 5, 2, with_labels=False)[0]
+        again.predict(molecular_database=tdb, calculate_energy=True, calculate_energy_gradients=True)
+        out[prog] = (tdb.get_properties("energy"), tdb.get_xyz_vectorial_properties("energy_gradients"))
+    assert np.allclose(out["KREG_API"][0], out["MLatomF"][0], rtol=1e-13, atol=0)
+    assert np.allclose(out["KREG_API"][1], out["MLatomF"][1], rtol=1e-12, atol=1e-13)
+    auto = M.kreg(ml_program="MLatomF", hyperparameters={"sigma": 0.9, "lambda": 1e-6})
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        auto.train(molecular_database=db, property_to_learn="energy")
+        assert auto.model_file.startswith("kreg_") and auto.model_file.endswith(".unf") and os.path.exists(auto.model_file)
+    finally:
+        os.chdir(cwd)
 
 
 def test_optimize_grid_visiting_order_and_ties():
