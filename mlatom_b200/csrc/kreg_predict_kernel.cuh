@@ -73,27 +73,80 @@ __device__ __forceinline__ void predict_row_epilogue(const PredictArgs &args, co
   }
 }
 
-// Small-batch mode, second kernel: sum the slices' accumulators in slice order, then the usual epilogue.
+// The same epilogue with one LANE per atom (latency path: a single thread walking all D pairs is a chain of D square
+// roots and divisions).  Atom a accumulates its partners in the order c = 0..Nat-1, which is the order in which the
+// serial version reaches them, so both give bit-identical gradients.
+template <int NAT>
+__device__ __forceinline__ void predict_row_epilogue_warp(const PredictArgs &args, const double *y, int64_t p, int lane) {
+  constexpr int D = NAT * (NAT - 1) / 2;
+  const double esum = y[D];
+  if (lane == 0 && args.E) args.E[p] = args.prior + esum;
+  if (!args.G || lane >= NAT) return;
+  const double *m = args.xyz + p * (NAT * 3);
+  const int a = lane;
+  double gr[3] = {0.0, 0.0, 0.0};
+  for (int c = 0; c < NAT; c++) {
+    if (c == a) continue;
+    const int lo = a < c ? a : c, hi = a < c ? c : a;
+    const int d = pair_index(NAT, lo, hi);
+    const double r2 = rij2_exact(m + 3 * lo, m + 3 * hi);
+    const double x = __ldg(args.xeq + d) / sqrt(r2);
+    const double xc = x - __ldg(args.center + d);
+    const double gd = (y[d] - xc * esum) * args.inv_s2;
+    const double f = gd * x / r2;
+    // the serial version adds f (m_hi - m_lo) to the lower atom and -f (m_hi - m_lo) to the higher one
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const double dx = m[3 * hi + t] - m[3 * lo + t];
+      gr[t] = fma(a == lo ? f : -f, dx, gr[t]);
+    }
+  }
+  double *out = args.G + p * (NAT * 3) + 3 * a;
+  out[0] = gr[0];
+  out[1] = gr[1];
+  out[2] = gr[2];
+}
+
+// Small-batch mode, second kernel: sum the slices' accumulators, then the epilogue.  One CTA per geometry, so that a
+// batch of a few dozen geometries is reduced by as many SMs; a row's TS accumulators are consecutive doubles in every
+// slice.  The slice loop is split over P threads per element (thread k takes slices k, k+P, ...) and the P partial
+// sums are added in the order k = 0..P-1: a fixed order for a given molecule size, and no chain of `nslices` dependent
+// loads.  Epilogue: one warp, a lane per atom.
 template <int NAT, int ROWS, int TS>
 __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictArgs args) {
-  extern __shared__ __align__(16) double ftile[];  // [ROWS][TS]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+  __shared__ __align__(16) double ftile[TS];
+  __shared__ double part[kThreads];
+  const int tid = threadIdx.x;
+  const int64_t row = (int64_t)blockIdx.x * ROWS + blockIdx.y;
+  if (row >= args.npoints) return;
   const size_t slice_stride = (size_t)gridDim.x * ROWS * TS;
-  for (int r = warp; r < ROWS; r += kWarps) {
-    if (row0 + r >= args.npoints) break;
-    const double *src = args.partial + ((size_t)blockIdx.x * ROWS + r) * TS;
-    for (int c = lane; c < TS; c += 32) {
+  const double *__restrict__ src = args.partial + (size_t)row * TS;
+  constexpr int P = TS >= kThreads ? 1 : (kThreads / TS > 16 ? 16 : kThreads / TS);
+  if (P == 1) {
+    for (int e = tid; e < TS; e += kThreads) {
       double s = 0.0;
-      for (int sl = 0; sl < args.nslices; sl++) s += src[(size_t)sl * slice_stride + c];
-      ftile[r * TS + c] = s;
+#pragma unroll 4
+      for (int sl = 0; sl < args.nslices; sl++) s += src[(size_t)sl * slice_stride + e];
+      ftile[e] = s;
+    }
+  } else {
+    if (tid < TS * P) {
+      const int e = tid % TS, k = tid / TS;
+      double s = 0.0;
+#pragma unroll 4
+      for (int sl = k; sl < args.nslices; sl += P) s += src[(size_t)sl * slice_stride + e];
+      part[k * TS + e] = s;
+    }
+    __syncthreads();
+    if (tid < TS) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < P; k++) s += part[k * TS + tid];
+      ftile[tid] = s;
     }
   }
   __syncthreads();
-  for (int r = tid; r < ROWS; r += kThreads) {
-    const int64_t p = row0 + r;
-    if (p < args.npoints) predict_row_epilogue<NAT, true>(args, ftile + r * TS, p);
-  }
+  if (tid < 32) predict_row_epilogue_warp<NAT>(args, ftile, row, tid);
 }
 
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps>
@@ -136,6 +189,35 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
   }
 
   // ---- prologue: centred descriptors of this CTA's test rows -> shared tile ----
+  const int64_t rows_left = args.npoints - row0;
+  if (rows_left * 4 <= C::ROWS) {
+    // sparse tile (latency mode: a handful of geometries): one thread per (row, atom pair) instead of a chain of D
+    // square roots and divisions per thread; the norm is then summed in the same d order, so the numbers are the same
+    const int nvalid = (int)rows_left;
+    for (int e = tid; e < nvalid * D; e += kThreads) {
+      const int r = e / D;
+      int d = e - r * D, a = 0;
+      while (d >= NAT - 1 - a) {
+        d -= NAT - 1 - a;
+        a++;
+      }
+      const int b = a + 1 + d;
+      d = e - r * D;
+      const double *m = args.xyz + (row0 + r) * (NAT * 3);
+      tile[r * TS + d] = __ldg(args.xeq + d) / sqrt(rij2_exact(m + 3 * a, m + 3 * b)) - __ldg(args.center + d);
+    }
+    for (int e = tid; e < C::ROWS * TS; e += kThreads) {
+      const int r = e / TS, d = e - r * TS;
+      if (r >= nvalid || d >= D) tile[e] = 0.0;  // padding columns and unused rows (their results are not stored)
+    }
+    __syncthreads();
+    for (int r = tid; r < C::ROWS; r += kThreads) {
+      double n = 0.0;
+      if (r < nvalid)
+        for (int d = 0; d < D; d++) n = fma(tile[r * TS + d], tile[r * TS + d], n);
+      bias[r] = -0.5 * args.c1 * n;
+    }
+  } else
   for (int r = tid; r < C::ROWS; r += kThreads) {
     int64_t p = row0 + r;
     if (p >= args.npoints) p = args.npoints - 1;  // duplicate a valid row; its results are not stored
@@ -334,9 +416,7 @@ static int launch_predict_g(PredictArgs a, cudaStream_t st) {
   KREG_LAUNCH_CHECK();
   if (a.nslices > 1) {
     auto fin = predict_finish_kernel<NAT, C::ROWS, C::TS>;
-    const size_t smem = (size_t)C::ROWS * C::TS * sizeof(double);
-    KREG_CUDA_TRY(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fin<<<(unsigned)blocks, kThreads, smem, st>>>(a);
+    fin<<<dim3((unsigned)blocks, C::ROWS), kThreads, 0, st>>>(a);
     KREG_LAUNCH_CHECK();
   }
   return KREG_OK;
