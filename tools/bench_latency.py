@@ -35,5 +35,12 @@ for n in (1, 8, 64, 512, 4096, 18944):
         t0 = time.perf_counter()
         for _ in range(500): gp(xh)
         rec["graph_host_to_host_us"] = round((time.perf_counter() - t0) / 500 * 1e6, 1)
+        if n <= 64:
+            for zc in (False, True):
+                gp = engine.GraphPredictor(model, n, zero_copy=zc)
+                for _ in range(20): gp(xh)
+                t0 = time.perf_counter()
+                for _ in range(500): gp(xh)
+                rec["graph_zero_copy_us" if zc else "graph_copies_us"] = round((time.perf_counter() - t0) / 500 * 1e6, 1)
     out[n] = rec
 print(json.dumps({"natoms": nat, "ntrain": ntr, "latency_by_batch": out}))
