@@ -60,6 +60,9 @@ int kreg_abi_version(void);
 const char *kreg_last_error(void);
 /* 0 if the current CUDA device can run the kernels (compute capability 10.x). */
 int kreg_device_check(void);
+/* Blocks the calling host thread until `stream` has drained (cudaStreamSynchronize): lets a ctypes caller finish a
+ * latency-critical step (one MD step) without going through a framework's stream objects. */
+int kreg_stream_synchronize(void *stream);
 
 /* FP64 issue-rate probe used as the roofline denominator for the prediction kernel
  * (MEASURED_PEAKS.json holds no FP64 figure).  kind: 0 = DFMA, 1 = DMMA (mma.sync m8n8k4 f64).

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "kreg_abi_version": (c_int, []),
     "kreg_last_error": (c_char_p, []),
     "kreg_device_check": (c_int, []),
+    "kreg_stream_synchronize": (c_int, [c_void_p]),
     "kreg_measure_fp64_peak": (c_int, [c_int, c_int, c_double, POINTER(c_double)]),
     "kreg_xeq": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "kreg_descriptors": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

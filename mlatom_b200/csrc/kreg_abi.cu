@@ -68,6 +68,11 @@ extern "C" int kreg_device_check(void) {
   return KREG_OK;
 }
 
+extern "C" int kreg_stream_synchronize(void *stream) {
+  KREG_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return KREG_OK;
+}
+
 extern "C" int kreg_measure_fp64_peak(int kind, int reps, double ms_target, double *tflops_host) {
   if (!tflops_host || reps < 1 || (kind != 0 && kind != 1)) return KREG_E_BADARG;
   int rc = kreg_device_check();

@@ -19,7 +19,15 @@ from ._lib import FILL_FULL, FILL_LOWER, PREDICT_ENERGY, PREDICT_GRADIENT, KregE
 F64 = torch.float64
 
 
+try:  # the raw handle of the current stream without building a torch.cuda.Stream object (7 us per call saved)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover - older / newer torch without the private getter
+    _raw_stream = None
+
+
 def _stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -327,6 +335,7 @@ class GraphPredictor:
         self.x_host = torch.zeros((n, nat, 3), dtype=F64).pin_memory()
         self.e_host = torch.zeros(n, dtype=F64).pin_memory()
         self.g_host = torch.zeros((n, nat, 3), dtype=F64).pin_memory()
+        self._x_np, self._e_np, self._g_np = self.x_host.numpy(), self.e_host.numpy(), self.g_host.numpy()
         self.x = torch.zeros((n, nat, 3), dtype=F64, device=dev)
         self.e = torch.zeros(n, dtype=F64, device=dev)
         self.g = torch.zeros((n, nat, 3), dtype=F64, device=dev)
@@ -342,6 +351,13 @@ class GraphPredictor:
             with torch.cuda.graph(self.graph):
                 self._body()
 
+    def _current_stream(self) -> int:
+        """Raw handle of the stream the replay was just enqueued on (the capture device's current stream)."""
+        idx = self.model.device.index
+        if _raw_stream is not None:
+            return _raw_stream(torch.cuda.current_device() if idx is None else idx)
+        return torch.cuda.current_stream(self.model.device).cuda_stream
+
     def _body(self):
         if self.zero_copy:  # two graph nodes instead of five: no copy operations around the kernels
             self.model.predict(self.x_host, self.energy, self.gradient, out_e=self.e_host, out_g=self.g_host)
@@ -355,7 +371,7 @@ class GraphPredictor:
 
     def __call__(self, xyz: np.ndarray):
         """xyz (n, Nat, 3) numpy -> (E (n,), dE/dxyz (n, Nat, 3)) numpy views of the pinned result buffers."""
-        self.x_host.numpy()[...] = xyz
+        self._x_np[...] = xyz
         self.graph.replay()
-        torch.cuda.current_stream(self.model.device).synchronize()
-        return (self.e_host.numpy() if self.energy else None), (self.g_host.numpy() if self.gradient else None)
+        call("kreg_stream_synchronize", self._current_stream())
+        return (self._e_np if self.energy else None), (self._g_np if self.gradient else None)
