@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
   if (tid < 32) predict_row_epilogue_warp<NAT>(args, ftile, row, tid);
 }
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps>
+// SPLIT = small-batch (latency) mode: the training set is divided over gridDim.y slices and the raw accumulators go to
+// predict_finish_kernel.  A separate instantiation, so that none of its code perturbs the throughput kernel.
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps, bool SPLIT = false>
 __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
   constexpr int kWarps = NW, kThreads = NW * 32;  // shadow the defaults: this kernel's own CTA shape
@@ -166,8 +168,8 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
   const int g = lane >> 2, q = lane & 3;
   const int64_t row0 = (int64_t)blockIdx.x * C::ROWS;
   const int all_stages = (args.ngroups + GPS - 1) / GPS;
-  const int stage0 = args.nslices > 1 ? (int)blockIdx.y * args.stages_per_slice : 0;  // first ring stage of this slice
-  const int total_stages = args.nslices > 1 ? min(args.stages_per_slice, all_stages - stage0) : all_stages;
+  const int stage0 = SPLIT ? (int)blockIdx.y * args.stages_per_slice : 0;  // first ring stage of this slice
+  const int total_stages = SPLIT ? min(args.stages_per_slice, all_stages - stage0) : all_stages;
 
   // ---- barrier init + first TMA bulk copies (overlap with the descriptor prologue) ----
   if (tid == 0) {
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
 
   // ---- prologue: centred descriptors of this CTA's test rows -> shared tile ----
   const int64_t rows_left = args.npoints - row0;
-  if (rows_left * 4 <= C::ROWS) {
+  if (SPLIT && rows_left * 4 <= C::ROWS) {
     // sparse tile (latency mode: a handful of geometries): one thread per (row, atom pair) instead of a chain of D
     // square roots and divisions per thread; the norm is then summed in the same d order, so the numbers are the same
     const int nvalid = (int)rows_left;
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
     }
   }
   __syncthreads();
-  if (WANT_G && args.nslices > 1) {
+  if (SPLIT) {
     // small-batch mode: hand the raw accumulators of the valid rows to predict_finish_kernel
     double *dst = args.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::ROWS * TS;
     const int64_t left = args.npoints - row0;
@@ -404,17 +406,17 @@ static void plan_slices(int ngroups, int64_t blocks, int sms, int *nslices, int 
   *nslices = (all_stages + per - 1) / per;
 }
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW, bool SPLIT = false>
 static int launch_predict_g(PredictArgs a, cudaStream_t st) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
-  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G, NW>;
+  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G, NW, SPLIT>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
   const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
-  dim3 grid((unsigned)blocks, (unsigned)(a.nslices > 1 ? a.nslices : 1));
+  dim3 grid((unsigned)blocks, (unsigned)(SPLIT ? a.nslices : 1));
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
   KREG_LAUNCH_CHECK();
-  if (a.nslices > 1) {
+  if (SPLIT) {
     auto fin = predict_finish_kernel<NAT, C::ROWS, C::TS>;
     fin<<<dim3((unsigned)blocks, C::ROWS), kThreads, 0, st>>>(a);
     KREG_LAUNCH_CHECK();
@@ -449,7 +451,8 @@ static int launch_predict_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes,
     a.partial = static_cast<double *>(ws);
   }
   // energy-only requests skip the second GEMM entirely (the split mode always carries the full accumulators)
-  return (a.G || a.nslices > 1) ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true, NW>(a, st)
+  if (a.nslices > 1) return launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true, NW, true>(a, st);
+  return a.G ? launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true, NW>(a, st)
                                 : launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, false, NW>(a, st);
 }
 
