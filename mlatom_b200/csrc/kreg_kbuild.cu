@@ -28,8 +28,8 @@ struct ValuesArgs {
   const double *biasA;  // -c1 n_i / 2
   const double *biasB;
   int64_t na, nb;
-  int XS;       // row stride (doubles), multiple of 4*KC
-  int nchunks;  // XS / (4*KC)
+  int XS;       // row stride (doubles), >= 4*KC*nchunks, = 4 mod 8
+  int nchunks;  // K-chunks of 4*KC descriptor elements
   double c1;
   double lambda;  // added where i == j when `symmetric`
   int symmetric;  // 1: XA == XB (K build): exact 1+lambda on the diagonal, tiles above the diagonal skipped unless `all_cols`
@@ -48,6 +48,74 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, boo
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Epilogue of one 128 x 64 tile, shared by both values kernels: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly
+// 1 + lambda, 16-byte stores (64 B runs per row); the accumulators are cleared for the next tile.
+__device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
+                                                     const double *bA, const double *bB, const double *tab, int wi,
+                                                     int wj, int g, int q, bool lower_only) {
+  const bool diag_tile = a.symmetric && j0 + kTileJ - 1 >= i0;  // touches the diagonal block: computed directly
+  // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
+  const bool interior = !diag_tile && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
+                        j0 + kTileJ <= a.nb && (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
+  if (interior) {
+    double *row = a.K + (i0 + wi * 32 + g) * a.ldk + j0 + wj * 32 + 2 * q;
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+      const double bi = bA[wi * 32 + mt * 8 + g];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const int cj = wj * 32 + nt * 8 + 2 * q;
+        const double2 bj = *reinterpret_cast<const double2 *>(bB + cj);
+        const double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bj.x), 0.0), tab);
+        const double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bj.y), 0.0), tab);
+        S[mt][nt][0] = S[mt][nt][1] = 0.0;
+        *reinterpret_cast<double2 *>(row + nt * 8) = make_double2(k0, k1);
+        if (a.mirror) {
+          double *t = a.K + (j0 + cj) * a.ldk + i0 + wi * 32 + mt * 8 + g;
+          t[0] = k0;
+          t[a.ldk] = k1;
+        }
+      }
+      row += 8 * a.ldk;
+    }
+    return;
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int ri = wi * 32 + mt * 8 + g;
+    const int64_t i = i0 + ri;
+    const bool row_ok = i < a.na && i >= a.row_begin && i < a.row_end;
+    const double bi = bA[ri];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int cj = wj * 32 + nt * 8 + 2 * q;
+      const int64_t j = j0 + cj;
+      double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bB[cj]), 0.0), tab);
+      double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bB[cj + 1]), 0.0), tab);
+      S[mt][nt][0] = S[mt][nt][1] = 0.0;
+      if (a.symmetric) {
+        if (i == j) k0 = 1.0 + a.lambda;
+        if (i == j + 1) k1 = 1.0 + a.lambda;
+      }
+      if (row_ok) {
+        double *dst = a.K + i * a.ldk + j;
+        const bool w0 = j < a.nb && (!lower_only || j <= i);
+        const bool w1 = j + 1 < a.nb && (!lower_only || j + 1 <= i);
+        if (w0 && w1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          *reinterpret_cast<double2 *>(dst) = make_double2(k0, k1);
+        } else {
+          if (w0) dst[0] = k0;
+          if (w1) dst[1] = k1;
+        }
+      }
+      if (a.mirror && !diag_tile && i < a.na) {
+        if (j < a.nb) a.K[j * a.ldk + i] = k0;
+        if (j + 1 < a.nb) a.K[(j + 1) * a.ldk + i] = k1;
+      }
+    }
+  }
+}
 
 // CTA tile 128 x 64, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 32 = 4 x 4 DMMA tiles, <= 128 registers so
 // two CTAs share an SM.  A CTA keeps its 128-row A tile and walks `njt` consecutive column tiles; the next
@@ -136,70 +204,112 @@ __global__ void __launch_bounds__(256, 2) values_tile_kernel(const ValuesArgs a)
     }
     if (ch != a.nchunks - 1) continue;
 
-    // epilogue: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly 1 + lambda, 16-byte stores (64 B runs per row)
-    const int64_t j0 = (tj_lo + step / a.nchunks) * kTileJ;
-    const double *bB = bBt + ((step / a.nchunks) & 1) * kTileJ;
-    const bool diag_tile = a.symmetric && j0 + kTileJ - 1 >= i0;  // touches the diagonal block: computed directly
-    // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
-    const bool interior = !diag_tile && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
-                          j0 + kTileJ <= a.nb && (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
-    if (interior) {
-      double *row = a.K + (i0 + wi * 32 + g) * a.ldk + j0 + wj * 32 + 2 * q;
-#pragma unroll
-      for (int mt = 0; mt < 4; mt++) {
-        const double bi = bA[wi * 32 + mt * 8 + g];
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-          const int cj = wj * 32 + nt * 8 + 2 * q;
-          const double2 bj = *reinterpret_cast<const double2 *>(bB + cj);
-          const double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bj.x), 0.0), tab);
-          const double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bj.y), 0.0), tab);
-          S[mt][nt][0] = S[mt][nt][1] = 0.0;
-          *reinterpret_cast<double2 *>(row + nt * 8) = make_double2(k0, k1);
-          if (a.mirror) {
-            double *t = a.K + (j0 + cj) * a.ldk + i0 + wi * 32 + mt * 8 + g;
-            t[0] = k0;
-            t[a.ldk] = k1;
-          }
-        }
-        row += 8 * a.ldk;
-      }
-      continue;
+    values_tile_epilogue(a, S, i0, (tj_lo + step / a.nchunks) * kTileJ, bA, bBt + ((step / a.nchunks) & 1) * kTileJ, tab, wi,
+                         wj, g, q, lower_only);
+  }
+}
+
+// Single-chunk descriptors (KS <= 12, i.e. D <= 48): the same tile shape, but the column tiles (descriptor rows + column
+// biases: two contiguous ranges of the workspace, whose row stride already is the conflict-free one) arrive through a
+// ring of TMA bulk copies with full/empty mbarriers, like the prediction kernel's model stream.  No CTA-wide barrier in
+// the steady state: a warp that has finished a tile's exponentials moves on to the next tile's tensor-core work while
+// the other warps are still in their epilogues.
+template <int KC>
+__global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a) {
+  constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
+  constexpr int A_DBL = kTileI * XSP, B_DBL = kTileJ * XSP, NST = KC <= 9 ? 3 : 2;
+  extern __shared__ __align__(128) double sm[];
+  double *As = sm;                         // [128][XSP]
+  double *Bs = As + A_DBL;                 // [NST][64][XSP]
+  double *bBs = Bs + NST * B_DBL;          // [NST][64]
+  double *bA = bBs + NST * kTileJ;         // [128]
+  double *tab = bA + kTileI;               // [64]
+  uint64_t *full = reinterpret_cast<uint64_t *>(tab + 64);  // [NST], then empty[NST], then fullA
+  uint64_t *empty = full + NST;
+  uint64_t *fullA = empty + NST;
+
+  const int64_t ti = (int64_t)blockIdx.y + a.row_begin / kTileI;
+  const int64_t i0 = ti * kTileI;
+  if (i0 >= a.na) return;
+  int64_t tj_lo = (int64_t)blockIdx.x * a.njt;
+  int64_t tj_hi = tj_lo + a.njt;
+  const int64_t ntj = (a.nb + kTileJ - 1) / kTileJ;
+  if (tj_hi > ntj) tj_hi = ntj;
+  if (a.symmetric && !a.all_cols) {
+    const int64_t last = (i0 + kTileI - 1) / kTileJ + 1;  // tiles entirely above the diagonal are not needed
+    if (tj_hi > last) tj_hi = last;
+  }
+  if (tj_lo >= tj_hi) return;
+  const int nsteps = (int)(tj_hi - tj_lo);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wi = warp >> 1, wj = warp & 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
     }
+    mbar_init(fullA, 1);
+    mbar_fence_init();
+  }
+  fill_exp_table(tab, tid, 256);
+  __syncthreads();
+
+  // rows past the end of the matrix are not copied: their shared-memory rows hold whatever was there, their results
+  // are never stored.  Byte counts stay multiples of 16 (bias ranges are rounded up to an even count; the workspace
+  // arrays are padded to 256 bytes).
+  auto issue_B = [&](int step) {  // thread 0 only
+    const int s = step % NST;
+    const int64_t j0 = (tj_lo + step) * kTileJ;
+    const unsigned rows = (unsigned)(a.nb - j0 < kTileJ ? a.nb - j0 : kTileJ);
+    const unsigned bx = rows * XSP * 8, bb = ((rows + 1) & ~1u) * 8;
+    mbar_arrive_expect_tx(&full[s], bx + bb);
+    bulk_g2s(Bs + s * B_DBL, a.XB + j0 * a.XS, bx, &full[s]);
+    bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
+  };
+  if (tid == 0) {
+    const unsigned rows = (unsigned)(a.na - i0 < kTileI ? a.na - i0 : kTileI);
+    const unsigned bx = rows * XSP * 8, bb = ((rows + 1) & ~1u) * 8;
+    mbar_arrive_expect_tx(fullA, bx + bb);
+    bulk_g2s(As, a.XA + i0 * a.XS, bx, fullA);
+    bulk_g2s(bA, a.biasA + i0, bb, fullA);
+    for (int s = 0; s < NST && s < nsteps; s++) issue_B(s);
+  }
+
+  double S[4][4][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) {
-      const int ri = wi * 32 + mt * 8 + g;
-      const int64_t i = i0 + ri;
-      const bool row_ok = i < a.na && i >= a.row_begin && i < a.row_end;
-      const double bi = bA[ri];
+  for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
-        const int cj = wj * 32 + nt * 8 + 2 * q;
-        const int64_t j = j0 + cj;
-        double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bB[cj]), 0.0), tab);
-        double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bB[cj + 1]), 0.0), tab);
-        S[mt][nt][0] = S[mt][nt][1] = 0.0;
-        if (a.symmetric) {
-          if (i == j) k0 = 1.0 + a.lambda;
-          if (i == j + 1) k1 = 1.0 + a.lambda;
-        }
-        if (row_ok) {
-          double *dst = a.K + i * a.ldk + j;
-          const bool w0 = j < a.nb && (!lower_only || j <= i);
-          const bool w1 = j + 1 < a.nb && (!lower_only || j + 1 <= i);
-          if (w0 && w1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            *reinterpret_cast<double2 *>(dst) = make_double2(k0, k1);
-          } else {
-            if (w0) dst[0] = k0;
-            if (w1) dst[1] = k1;
-          }
-        }
-        if (a.mirror && !diag_tile && i < a.na) {
-          if (j < a.nb) a.K[j * a.ldk + i] = k0;
-          if (j + 1 < a.nb) a.K[(j + 1) * a.ldk + i] = k1;
-        }
-      }
+    for (int nt = 0; nt < 4; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
+  const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
+  mbar_wait(fullA, 0);
+
+  for (int step = 0; step < nsteps; step++) {
+    // producer duty: refill the slot every warp left in the previous iteration
+    if (tid == 0 && step >= 1 && step - 1 + NST < nsteps) {
+      mbar_wait(&empty[(step - 1) % NST], ((step - 1) / NST) & 1);
+      issue_B(step - 1 + NST);
     }
+    const int s = step % NST;
+    mbar_wait(&full[s], (step / NST) & 1);
+    const double *Bt = Bs + s * B_DBL;
+#pragma unroll
+    for (int ks = 0; ks < KC; ks++) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) af[mt] = As[(wi * 32 + mt * 8 + g) * XSP + ks * 4 + q];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) bf[nt] = Bt[(wj * 32 + nt * 8 + g) * XSP + ks * 4 + q];
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) dmma884(S[mt][nt], af[mt], bf[nt]);
+    }
+    values_tile_epilogue(a, S, i0, (tj_lo + step) * kTileJ, bA, bBs + s * kTileJ, tab, wi, wj, g, q, lower_only);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the slot (tile and biases)
   }
 }
 
@@ -220,7 +330,13 @@ static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   a.njt = tiles > 200000 ? 16 : tiles > 50000 ? 8 : tiles > 1000 ? 4 : 2;  // measured: 10k rows 4 (0.25 vs 0.27 ms), 50k flat
 #endif
   dim3 grid((unsigned)((ntj + a.njt - 1) / a.njt), (unsigned)(ti1 - ti0 + 1));
-  if (multi) {
+  if (!multi && a.XS == XSP) {
+    constexpr int NST = KC <= 9 ? 3 : 2;
+    const size_t rsmem = (size_t)(kTileI * XSP + NST * kTileJ * XSP + NST * kTileJ + kTileI + 64 + 2 * NST + 2) * sizeof(double);
+    auto kern = values_ring_kernel<KC>;
+    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    kern<<<grid, 256, rsmem, st>>>(a);
+  } else if (multi) {
     auto kern = values_tile_kernel<KC, true>;
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(a);
@@ -780,6 +896,7 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
   const TcShape sh(nat);
   chunking(sh.KS, &w.KC, &w.nchunks);
   w.XS = w.KC * w.nchunks * 4;
+  if (w.XS % 8 == 0) w.XS += 4;  // row stride = 4 mod 8 doubles: rows can be bulk-copied into conflict-free shared tiles
   size_t off = 0;
   auto take = [&](size_t doubles) {
     size_t o = off;
