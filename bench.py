@@ -42,7 +42,7 @@ WORKLOAD = "cfg2: KREG energies+forces prediction, 9 atoms, Ntrain=10000, Ntest=
 # algorithmic work: E + dE/dxyz, values-trained
 FLOP_PER_STEP = float(NTEST) * NTRAIN * (5 * D + 4) + float(NTEST) * 30 * D
 SCALING = "weak"
-KERNEL = "kreg::predict_kernel<9,2,false,false,3,3,true>"
+KERNEL = "kreg::predict_kernel<9,2,false,false,3,3,true,8,false>"
 TRAFFIC = 429.13e6  # dram bytes of one launch, ncu --set full (profiles/r01_predict_ncu.txt)
 
 
@@ -59,7 +59,7 @@ def set_workload(name, world):
                 f"SURVEY.md 8d), {NTEST} per GPU")
     FLOP_PER_STEP = float(NTEST) * NTRAIN * (5 * D + 4) + float(NTEST) * 30 * D
     SCALING = "strong"
-    KERNEL = "kreg::predict_kernel<21,1,false,true,1,3,true>"
+    KERNEL = "kreg::predict_kernel<21,1,false,true,1,3,true,8,false>"
     TRAFFIC = None
 
 
