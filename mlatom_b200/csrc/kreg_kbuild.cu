@@ -349,9 +349,15 @@ static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   return KREG_OK;
 }
 
-// k-steps per staged chunk for a descriptor of KS k-steps: at most 12, as even as possible
+// k-steps per staged chunk: one chunk up to 12; longer descriptors in chunks of at most 9, the largest whose
+// double-buffered A and B tiles (3072 * XSP bytes, XSP <= 36) leave room for two CTAs per SM (aspirin, D = 210:
+// 3.93 -> 3.25 ms for a 20k x 20k block against chunks of 11)
+#ifndef KREG_MULTI_KC
+#define KREG_MULTI_KC 9
+#endif
 static void chunking(int KS, int *KC, int *nchunks) {
-  *nchunks = (KS + 11) / 12;
+  const int cap = KS <= 12 ? 12 : KREG_MULTI_KC;
+  *nchunks = (KS + cap - 1) / cap;
   *KC = (KS + *nchunks - 1) / *nchunks;
 }
 
