@@ -19,6 +19,7 @@ JSON keys beyond the base contract:
   cpu_baseline the oracle's port of MLatomF's prediction path on the host cores (bounded sample)
   e2e          same metric through PackedModel.predict_host: pinned host xyz in, host E/G out, copies
                inside the timed region
+  step_latency one geometry / 64 geometries per call (the MD step): device and CUDA-graph host-to-host microseconds
 """
 import argparse
 import json
@@ -138,6 +139,39 @@ def cpu_baseline(eq, xyz_tr, alpha, prior, seconds=12.0, threads=None):
     t = run(n)
     return {"value": n / t, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} of {NTEST} test geometries, full Ntrain={NTRAIN}, {t:.1f} s wall"}, n, t
+
+
+def step_latency(engine, model, dev):
+    """What an MD / geometry-optimisation driver pays per step (md.py:169,198 predicts ONE geometry per step;
+    md_parallel.py one batch per step): device time of kreg_predict in latency mode and host-to-host time of the
+    CUDA-graphed predictor, E + dE/dxyz, against this run's Ntrain = 10k model."""
+    import torch
+
+    from mlatom_b200 import synthetic as S
+
+    out = {}
+    eq = S.equilibrium(NAT)
+    for n in (1, 64):
+        x = torch.from_numpy(S.geometries(eq, n, seed=3)).to(dev)
+        for _ in range(20):
+            model.predict(x)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(200):
+            model.predict(x)
+        ev[1].record()
+        torch.cuda.synchronize()
+        gp = engine.GraphPredictor(model, n)
+        xh = x.cpu().numpy()
+        for _ in range(20):
+            gp(xh)
+        t0 = time.perf_counter()
+        for _ in range(500):
+            gp(xh)
+        out[f"batch_{n}"] = {"device_us": ev[0].elapsed_time(ev[1]) / 200 * 1e3,
+                             "graph_host_to_host_us": (time.perf_counter() - t0) / 500 * 1e6}
+    return out
 
 
 def kbuild_configs(engine, dev, hbm_peak, fp64_peak):
@@ -463,6 +497,7 @@ def run_ours(args):
                           "potrf_potrs_ms_timed_separately": extra.get("solve_ms")}
     if world == 1 and args.workload == "cfg2":
         line["kbuild_configs"] = kbuild_configs(engine, dev, line["kbuild"]["hbm_peak_gbs"], peak_dmma)
+        line["step_latency"] = step_latency(engine, model, dev)
     if world == 1 and not args.no_cpu:
         base, _, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
         line["cpu_baseline"] = base
