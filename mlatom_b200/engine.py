@@ -326,7 +326,8 @@ class GraphPredictor:
     optimisation -- replaying the graph removes the per-call launch and Python overhead of the four operations.
     """
 
-    ZERO_COPY_MAX = 1  # the single-geometry step reads / writes the pinned host buffers directly (measured: 43 vs 53 us; slower from 8 geometries on)
+    ZERO_COPY_MAX = 0  # kernels reading / writing the pinned host buffers directly (two graph nodes instead of five) measured
+    #                    41-60 us against 42-46 us with copy nodes for one geometry, and slower from 8 geometries on: off by default
 
     def __init__(self, model: PackedModel, n: int, energy: bool = True, gradient: bool = True, zero_copy=None):
         self.model, self.n, self.energy, self.gradient = model, int(n), energy, gradient
