@@ -334,12 +334,13 @@ class GraphPredictor:
         self.zero_copy = (n <= self.ZERO_COPY_MAX) if zero_copy is None else bool(zero_copy)
         dev, nat = model.device, model.natoms
         self.x_host = torch.zeros((n, nat, 3), dtype=F64).pin_memory()
-        self.e_host = torch.zeros(n, dtype=F64).pin_memory()
-        self.g_host = torch.zeros((n, nat, 3), dtype=F64).pin_memory()
+        # E and dE/dxyz share one buffer on each side: one device->host copy node instead of two
+        self.out_host = torch.zeros(n * (1 + 3 * nat), dtype=F64).pin_memory()
+        self.e_host, self.g_host = self.out_host[:n], self.out_host[n:].view(n, nat, 3)
         self._x_np, self._e_np, self._g_np = self.x_host.numpy(), self.e_host.numpy(), self.g_host.numpy()
         self.x = torch.zeros((n, nat, 3), dtype=F64, device=dev)
-        self.e = torch.zeros(n, dtype=F64, device=dev)
-        self.g = torch.zeros((n, nat, 3), dtype=F64, device=dev)
+        self.out = torch.zeros(n * (1 + 3 * nat), dtype=F64, device=dev)
+        self.e, self.g = self.out[:n], self.out[n:].view(n, nat, 3)
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -365,9 +366,11 @@ class GraphPredictor:
             return
         self.x.copy_(self.x_host, non_blocking=True)
         self.model.predict(self.x, self.energy, self.gradient, out_e=self.e, out_g=self.g)
-        if self.energy:
+        if self.energy and self.gradient:
+            self.out_host.copy_(self.out, non_blocking=True)
+        elif self.energy:
             self.e_host.copy_(self.e, non_blocking=True)
-        if self.gradient:
+        elif self.gradient:
             self.g_host.copy_(self.g, non_blocking=True)
 
     def __call__(self, xyz: np.ndarray):
