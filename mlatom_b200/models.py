@@ -12,7 +12,7 @@ from __future__ import annotations
 import json
 import os
 import uuid
-from typing import Any, Dict, Optional, Sequence, Union
+from typing import Any, Dict, Optional, Union
 
 import numpy as np
 import torch

@@ -28,7 +28,7 @@ xte_h = torch.from_numpy(S.geometries(eq, a.ntest, 2))
 xte = xte_h.pin_memory() if a.host else xte_h.to(dev)
 out_e = torch.empty(a.ntest, dtype=torch.float64).pin_memory() if a.host else None
 out_g = torch.empty((a.ntest, nat, 3), dtype=torch.float64).pin_memory() if a.host and not a.energy_only else None
-hp = engine.HostPredictor(None, 1) if False else None
+hp = None
 nv, ng = a.ntrain, (3 * nat * a.ntrain if a.grads else 0)
 alpha = torch.from_numpy(np.random.default_rng(0).standard_normal(nv + ng) * 1e-3).to(dev)
 model = engine.PackedModel.from_training_set(xtr, engine.xeq(torch.from_numpy(eq).to(dev)), alpha, sigma, 0.0, nv, ng)
