@@ -316,14 +316,18 @@ def run_reference(args):
     total = sum(times)
     value = n * len(times) / total
     sample = f"{n} of {NTEST} test geometries per step, full Ntrain={NTRAIN}"
+    shipped = kreg_so_baseline(eq, xyz_tr, alpha)  # the reference's own binary beside the port (slower: literal loops)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "natoms": NAT, "ntrain": NTRAIN, "ntest_per_gpu": NTEST, "sigma": SIGMA,
                    "note": "CPU only: MLatomF's optimised prediction loop restated in C/OpenMP (oracle/kreg_oracle.c), "
-                           "all host threads; geometries/s is independent of the sample size"},
+                           "all host threads; geometries/s is independent of the sample size.  The port is the arm "
+                           "because it is the FASTER of the two reference programs (BASELINE metric: 'vs MLatomF CPU'); "
+                           "the reference's shipped KREG.so, run through oracle/_ref, is reported beside it"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_reference_as_shipped": shipped,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
