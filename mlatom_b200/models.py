@@ -90,6 +90,48 @@ class kreg:
         if nthreads:
             self.nthreads = nthreads
 
+    def config_multiprocessing(self):
+        """Nothing to prepare before the model is used from parallel drivers (model_cls.py:29-33)."""
+
+    def parse_args(self, args):
+        """Command-line parsing belongs to MLatom's CLI layer, which is outside this package (model_cls.py:35-37)."""
+
+    def _predict_geomopt(self, return_string=False, dump_trajectory_interval=None, filename=None, format="json",
+                         print_properties=None, molecule=None, **kwargs):
+        """The hook MLatom's geometry optimisers call for every step (model_cls.py:39-76, simulations.py:382):
+        predict, warn about missing gradients, and -- when a dump interval is given -- append the step to the
+        optimisation trajectory file using the trajectory classes of the data module the molecule comes from."""
+        self.predict(molecule=molecule, **kwargs)
+        if np.any(np.isnan(molecule.energy_gradients)):
+            print(" * Warning* No gradients were calculated, check the logs for any reasons of this critical failure.")
+            if "error_message" in molecule.__dict__:
+                print(" Error message retrieved from the calculations:\n" + "-" * 10)
+                print(molecule.error_message)
+                print("-" * 10)
+        if dump_trajectory_interval is None:
+            return None
+        import sys
+
+        dmod = sys.modules[type(molecule).__module__]
+        if not hasattr(dmod, "molecular_trajectory"):
+            raise NotImplementedError("trajectory dumps need MLatom's data module (mlatom.data molecules)")
+        traj = dmod.molecular_trajectory()
+        traj.load(filename=filename, format=format)
+        nsteps = len(traj.steps)
+        text = None
+        if print_properties == "all" or isinstance(print_properties, list):
+            rule = " %s " % ("-" * 78)
+            text = "\n".join([rule, f" Iteration {nsteps + 1}", rule + "\n",
+                              molecule.info(properties=print_properties, return_string=True)]) + "\n"
+            if not return_string:
+                print(text)
+        traj.steps.append(dmod.molecular_trajectory_step(step=nsteps, molecule=molecule))
+        traj.dump(filename=filename, format=format)
+        moldb = dmod.molecular_database()
+        moldb.molecules = [step.molecule for step in traj.steps]
+        moldb.write_file_with_xyz_coordinates(os.path.splitext(os.path.basename(filename))[0] + ".xyz")
+        return text if return_string else None
+
     def reset(self):
         if self.model_file and os.path.exists(self.model_file):
             os.remove(self.model_file)

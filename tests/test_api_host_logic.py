@@ -68,6 +68,14 @@ def fake_engine(monkeypatch, oracle):
             e, g = self.model.predict_host(xyz, self.energy, self.gradient)
             return (None if e is None else e.numpy()), (None if g is None else g.numpy())
 
+    def hessian(x_train, alpha_val, xeq, sigma, xyz):
+        xte = xyz.numpy()
+        nv = 0 if alpha_val is None else alpha_val.numel()
+        a = np.zeros(0) if alpha_val is None else alpha_val.numpy()
+        return torch.from_numpy(oracle.hessian_kregf90(x_train.numpy(), a, sigma, nv, xte,
+                                                       oracle.descriptors(xte, xeq.numpy())))
+
+    monkeypatch.setattr(eng, "hessian", hessian)
     monkeypatch.setattr(eng, "GraphPredictor", FakeGraph)
     monkeypatch.setattr(eng, "build_kernel_matrix", build)
     monkeypatch.setattr(eng, "solve", solve)
@@ -331,3 +339,41 @@ def test_al_threshold_metric_matches_reference_formula():
         from mlatom import stats as ref_stats
 
         assert abs(al.median_absolute_deviation(v) - ref_stats.calc_median_absolute_deviation(v)) <= 1e-16
+
+
+def test_reference_drivers_run_on_this_model(fake_engine, tmp_path):
+    """Drop-in at the driver level: the REFERENCE's own geometry optimiser and MD driver (mlatom/simulations.py,
+    md.py:158-205) are handed this package's kreg model and reference data objects; they call model.predict(molecule=...)
+    per step and read mol.energy / atom.energy_gradients back (build container only: needs /root/reference)."""
+    ref_data = reference_mlatom()
+    if ref_data is None:
+        pytest.skip("reference checkout not available")
+    import mlatom as ml
+
+    nat = 5
+    db, xyz, e, g = make_db(ref_data, nat, 60, 1)
+    model = M.kreg(model_file=str(tmp_path / "drv"), hyperparameters={"sigma": 1.0, "lambda": 1e-8})
+    model.train(molecular_database=db, property_to_learn="energy", xyz_derivative_property_to_learn="energy_gradients")
+
+    start = db.molecules[3].copy()
+    opt = ml.optimize_geometry(model=model, initial_molecule=start, program="scipy")
+    final = opt.optimized_molecule
+    assert final.energy <= start.energy + 1e-12 if hasattr(start, "energy") else True
+    gmax = np.abs(final.get_energy_gradients()).max()
+    assert gmax < 5e-3, gmax                                    # converged on the model surface
+
+    init = db.molecules[5].copy()
+    for atom in init.atoms:
+        atom.xyz_velocities = np.zeros(3)
+    dyn = ml.md(model=model, molecule_with_initial_conditions=init, ensemble="NVE", time_step=0.2,
+                maximum_propagation_time=4.0)
+    steps = dyn.molecular_trajectory.steps
+    assert len(steps) >= 20
+    etot = np.array([s.molecule.total_energy for s in steps])
+    assert np.abs(etot - etot[0]).max() < 1e-4 * max(1.0, abs(etot[0]))   # velocity Verlet conserves E on a smooth surface
+
+    # Hessian consumer: predict(calculate_hessian=True) writes mol.hessian (3Nat x 3Nat) like kreg_api.py:130-131
+    hmol = final.copy()
+    model.predict(molecule=hmol, calculate_energy=True, calculate_energy_gradients=True, calculate_hessian=True)
+    assert np.asarray(hmol.hessian).shape == (3 * nat, 3 * nat)
+    assert np.abs(hmol.hessian - hmol.hessian.T).max() < 1e-10 * max(1.0, np.abs(hmol.hessian).max())
