@@ -377,3 +377,46 @@ def test_reference_drivers_run_on_this_model(fake_engine, tmp_path):
     model.predict(molecule=hmol, calculate_energy=True, calculate_energy_gradients=True, calculate_hessian=True)
     assert np.asarray(hmol.hessian).shape == (3 * nat, 3 * nat)
     assert np.abs(hmol.hessian - hmol.hessian.T).max() < 1e-10 * max(1.0, np.abs(hmol.hessian).max())
+
+
+def test_active_learning_trainer_call_sequence(fake_engine, tmp_path):
+    """The exact calls of al_utils.py:1086-1126 (main and auxiliary KREG trainers): widen sigma's range, grid-optimise
+    lambda and sigma (default 9 x 9 grid, prior='mean', the auxiliary one with its odd 'estimated'+name property), then
+    save through model.kreg_api; a second construction on the same file finds the model and skips training."""
+    mod = reference_mlatom() or D
+    sub, _, _, _ = make_db(mod, 5, 14, 1)
+    val, _, _, _ = make_db(mod, 5, 8, 3)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        main = M.kreg(model_file="main.npz", ml_program="KREG_API")
+        main.hyperparameters["sigma"].minval = 2 ** -5
+        main.optimize_hyperparameters(subtraining_molecular_database=sub, validation_molecular_database=val,
+                                      optimization_algorithm="grid", hyperparameters=["lambda", "sigma"],
+                                      training_kwargs={"property_to_learn": "energy",
+                                                       "xyz_derivative_property_to_learn": "energy_gradients", "prior": "mean"},
+                                      prediction_kwargs={"property_to_predict": "estimated_energy",
+                                                         "xyz_derivative_property_to_predict": "estimated_energy_gradients"},
+                                      validation_loss_function=None)
+        assert 2 ** -35 <= main.hyperparameters["lambda"].value <= 1.0 and 2 ** -5 <= main.hyperparameters["sigma"].value <= 2 ** 9
+        main.kreg_api.save_model("main.npz")
+        aux = M.kreg(model_file="aux.npz", ml_program="KREG_API")
+        aux.hyperparameters["sigma"].minval = 2 ** -5
+        aux.optimize_hyperparameters(subtraining_molecular_database=sub, validation_molecular_database=val,
+                                     optimization_algorithm="grid", hyperparameters=["lambda", "sigma"],
+                                     training_kwargs={"property_to_learn": "energy", "prior": "mean"},
+                                     prediction_kwargs={"property_to_predict": "estimated" + "energy"})
+        aux.kreg_api.save_model("aux.npz")
+        assert os.path.exists("main.npz") and os.path.exists("aux.npz")
+        # al_utils.py:1088-1090: the file exists -> the model is loaded, not retrained
+        again = M.kreg(model_file="main.npz", ml_program="KREG_API")
+        assert again.kreg_api.NtrGrXYZ == 3 * 5 * 14 and float(again.kreg_api.sigma) == main.hyperparameters["sigma"].value
+        # al_utils.py:1409-1424: uncertainty = |E_main - E_aux| written into the molecules
+        pool, _, _, _ = make_db(mod, 5, 6, 4, with_labels=False)
+        again.predict(molecular_database=pool, property_to_predict="energy", xyz_derivative_property_to_predict="energy_gradients")
+        M.kreg(model_file="aux.npz").predict(molecular_database=pool, property_to_predict="aux_energy",
+                                             xyz_derivative_property_to_predict="aux_energy_gradients")
+        uq = [abs(m.energy - m.aux_energy) for m in pool.molecules]
+        assert len(uq) == 6 and all(np.isfinite(uq))
+    finally:
+        os.chdir(cwd)
