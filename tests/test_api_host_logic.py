@@ -372,6 +372,16 @@ def test_reference_drivers_run_on_this_model(fake_engine, tmp_path):
     etot = np.array([s.molecule.total_energy for s in steps])
     assert np.abs(etot - etot[0]).max() < 1e-4 * max(1.0, abs(etot[0]))   # velocity Verlet conserves E on a smooth surface
 
+    # batch driver (md_parallel.py:155-200): one predict(molecular_database=...) per step for all trajectories
+    batch = ref_data.molecular_database()
+    for k in (1, 2, 7, 9):
+        mol = db.molecules[k].copy()
+        for atom in mol.atoms:
+            atom.xyz_velocities = np.zeros(3)
+        batch.molecules.append(mol)
+    par = ml.md_parallel(model=model, molecular_database=batch, ensemble="NVE", time_step=0.2, maximum_propagation_time=1.0)
+    assert len(par.molecular_trajectory.steps) >= 5 and len(par.molecular_trajectory.steps[0]) == 4
+
     # Hessian consumer: predict(calculate_hessian=True) writes mol.hessian (3Nat x 3Nat) like kreg_api.py:130-131
     hmol = final.copy()
     model.predict(molecule=hmol, calculate_energy=True, calculate_energy_gradients=True, calculate_hessian=True)
