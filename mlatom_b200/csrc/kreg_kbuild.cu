@@ -17,7 +17,6 @@ namespace kreg {
 
 // =================================================================================================
 // Values block / rectangular value-value block:  S = XA . XB^T on DMMA.8x8x4, then exp.
-// CTA tile 128 x 128, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 64 = 4 x 8 DMMA tiles.
 // =================================================================================================
 constexpr int kTileI = 128;  // rows per CTA tile
 constexpr int kTileJ = 64;   // columns per CTA tile
@@ -25,6 +24,9 @@ constexpr int kTileJ = 64;   // columns per CTA tile
 struct ValuesArgs {
   const double *XA;  // [na][XS] centred descriptors, zero padded
   const double *XB;  // [nb][XS]
+  const double *XAch;  // multi-chunk descriptors only: [nchunks][na][XSC] chunk-major copy (contiguous chunk tiles)
+  const double *XBch;  // [nchunks][nb][XSC]
+  int XSC;             // row stride of the chunk-major copies = the kernel's conflict-free chunk stride
   const double *biasA;  // -c1 n_i / 2
   const double *biasB;
   int64_t na, nb;
@@ -41,13 +43,6 @@ struct ValuesArgs {
   int njt;  // column tiles walked by one CTA (set by the launcher)
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
-  const unsigned sz = valid ? 16u : 0u;  // src-size 0: nothing is read, the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Epilogue of one 128 x 64 tile, shared by both values kernels: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly
 // 1 + lambda, 16-byte stores (64 B runs per row); the accumulators are cleared for the next tile.
@@ -117,113 +112,29 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
   }
 }
 
-// CTA tile 128 x 64, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 32 = 4 x 4 DMMA tiles, <= 128 registers so
-// two CTAs share an SM.  A CTA keeps its 128-row A tile and walks `njt` consecutive column tiles; the next
-// step's tile (B, and A too when the descriptor needs several K-chunks) is fetched with cp.async into the
-// other shared-memory buffer while the current one feeds the tensor pipe.
-template <int KC, bool MULTI>
-__global__ void __launch_bounds__(256, 2) values_tile_kernel(const ValuesArgs a) {
-  constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);  // stride = 4 mod 8 doubles: conflict-free LDS.64 fragments
-  constexpr int A_DBL = kTileI * XSP, B_DBL = kTileJ * XSP;
-  extern __shared__ __align__(16) double sm[];
-  double *Abuf = sm;                                  // [MULTI ? 2 : 1][A_DBL]
-  double *Bbuf = Abuf + (MULTI ? 2 : 1) * A_DBL;      // [2][B_DBL]
-  double *bA = Bbuf + 2 * B_DBL;                      // [128]   row bias
-  double *bBt = bA + kTileI;                          // [2][64] column bias, slot = column-tile parity
-  double *tab = bBt + 2 * kTileJ;                     // [64]
-
-  const int64_t ti = (int64_t)blockIdx.y + a.row_begin / kTileI;
-  const int64_t i0 = ti * kTileI;
-  if (i0 >= a.na) return;
-  int64_t tj_lo = (int64_t)blockIdx.x * a.njt;
-  int64_t tj_hi = tj_lo + a.njt;
-  const int64_t ntj = (a.nb + kTileJ - 1) / kTileJ;
-  if (tj_hi > ntj) tj_hi = ntj;
-  if (a.symmetric && !a.all_cols) {
-    const int64_t last = (i0 + kTileI - 1) / kTileJ + 1;  // tiles entirely above the diagonal are not needed
-    if (tj_hi > last) tj_hi = last;
-  }
-  if (tj_lo >= tj_hi) return;
-  const int nsteps = (int)(tj_hi - tj_lo) * a.nchunks;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  const int wi = warp >> 1, wj = warp & 1;
-
-  auto issue = [&](int step) {
-    const int64_t j0 = (tj_lo + step / a.nchunks) * kTileJ;
-    const int ch = step % a.nchunks, buf = step & 1;
-    if (MULTI || step == 0) {
-      double *dst = Abuf + (MULTI ? buf : 0) * A_DBL;
-      for (int e = tid; e < kTileI * KC * 2; e += 256) {
-        const int r = e / (KC * 2), c2 = e % (KC * 2);
-        const bool ok = i0 + r < a.na;
-        cp_async16(dst + r * XSP + c2 * 2, a.XA + (ok ? i0 + r : 0) * a.XS + ch * KC * 4 + c2 * 2, ok);
-      }
-    }
-    double *dst = Bbuf + buf * B_DBL;
-    for (int e = tid; e < kTileJ * KC * 2; e += 256) {
-      const int r = e / (KC * 2), c2 = e % (KC * 2);
-      const bool ok = j0 + r < a.nb;
-      cp_async16(dst + r * XSP + c2 * 2, a.XB + (ok ? j0 + r : 0) * a.XS + ch * KC * 4 + c2 * 2, ok);
-    }
-    if (ch == 0 && tid < kTileJ)
-      bBt[((step / a.nchunks) & 1) * kTileJ + tid] = (j0 + tid < a.nb) ? a.biasB[j0 + tid] : 0.0;
-    cp_async_commit();
-  };
-
-  issue(0);
-  fill_exp_table(tab, tid, 256);
-  if (tid < kTileI) bA[tid] = (i0 + tid < a.na) ? a.biasA[i0 + tid] : 0.0;
-
-  double S[4][4][2];
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
-  const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
-
-  for (int step = 0; step < nsteps; step++) {
-    cp_async_wait_all();
-    __syncthreads();  // this step's tiles are visible; every warp is done with the other buffer
-    if (step + 1 < nsteps) issue(step + 1);
-    const int ch = step % a.nchunks, buf = step & 1;
-    const double *As = Abuf + (MULTI ? buf : 0) * A_DBL;
-    const double *Bs = Bbuf + buf * B_DBL;
-#pragma unroll
-    for (int ks = 0; ks < KC; ks++) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int mt = 0; mt < 4; mt++) af[mt] = As[(wi * 32 + mt * 8 + g) * XSP + ks * 4 + q];
-#pragma unroll
-      for (int nt = 0; nt < 4; nt++) bf[nt] = Bs[(wj * 32 + nt * 8 + g) * XSP + ks * 4 + q];
-#pragma unroll
-      for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) dmma884(S[mt][nt], af[mt], bf[nt]);
-    }
-    if (ch != a.nchunks - 1) continue;
-
-    values_tile_epilogue(a, S, i0, (tj_lo + step / a.nchunks) * kTileJ, bA, bBt + ((step / a.nchunks) & 1) * kTileJ, tab, wi,
-                         wj, g, q, lower_only);
-  }
-}
-
-// Single-chunk descriptors (KS <= 12, i.e. D <= 48): the same tile shape, but the column tiles (descriptor rows + column
-// biases: two contiguous ranges of the workspace, whose row stride already is the conflict-free one) arrive through a
-// ring of TMA bulk copies with full/empty mbarriers, like the prediction kernel's model stream.  No CTA-wide barrier in
+// The values block: CTA tile 128 x 64, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 32 = 4 x 4 DMMA tiles, <= 128
+// registers so two CTAs share an SM.  A CTA walks `njt` consecutive column tiles; operands arrive through a ring of TMA
+// bulk copies with full/empty mbarriers, like the prediction kernel's model stream, so there is no CTA-wide barrier in
 // the steady state: a warp that has finished a tile's exponentials moves on to the next tile's tensor-core work while
 // the other warps are still in their epilogues.
-template <int KC>
+//   MULTI = false (KS <= 12, D <= 48): the A tile is loaded once; a stage = one column tile + its biases (the workspace
+//           row stride is the conflict-free one, so a tile of rows is one contiguous block).
+//   MULTI = true: the descriptor is walked in chunks of KC k-steps; a stage = the A chunk and the B chunk of one
+//           (tile, chunk) step, both contiguous in the chunk-major copy of the workspace; column biases travel with chunk 0
+//           into a slot selected by tile parity.
+template <int KC, bool MULTI>
 __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
-  constexpr int A_DBL = kTileI * XSP, B_DBL = kTileJ * XSP, NST = KC <= 9 ? 3 : 2;
+  constexpr int A_DBL = kTileI * XSP, B_DBL = kTileJ * XSP;
+  constexpr int NST = MULTI ? 2 : (KC <= 9 ? 3 : 2);
+  constexpr int STAGE = MULTI ? A_DBL + B_DBL : B_DBL;
+  constexpr int NBIAS = MULTI ? 2 : NST;
   extern __shared__ __align__(128) double sm[];
-  double *As = sm;                         // [128][XSP]
-  double *Bs = As + A_DBL;                 // [NST][64][XSP]
-  double *bBs = Bs + NST * B_DBL;          // [NST][64]
-  double *bA = bBs + NST * kTileJ;         // [128]
-  double *tab = bA + kTileI;               // [64]
+  double *As = sm;                                  // !MULTI: [128][XSP]
+  double *ring = As + (MULTI ? 0 : A_DBL);          // [NST][STAGE]  (MULTI: A chunk, then B chunk)
+  double *bBs = ring + NST * STAGE;                 // [NBIAS][64]
+  double *bA = bBs + NBIAS * kTileJ;                // [128]
+  double *tab = bA + kTileI;                        // [64]
   uint64_t *full = reinterpret_cast<uint64_t *>(tab + 64);  // [NST], then empty[NST], then fullA
   uint64_t *empty = full + NST;
   uint64_t *fullA = empty + NST;
@@ -240,7 +151,8 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
     if (tj_hi > last) tj_hi = last;
   }
   if (tj_lo >= tj_hi) return;
-  const int nsteps = (int)(tj_hi - tj_lo);
+  const int nch = MULTI ? a.nchunks : 1;
+  const int nsteps = (int)(tj_hi - tj_lo) * nch;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
@@ -260,22 +172,30 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
   // rows past the end of the matrix are not copied: their shared-memory rows hold whatever was there, their results
   // are never stored.  Byte counts stay multiples of 16 (bias ranges are rounded up to an even count; the workspace
   // arrays are padded to 256 bytes).
-  auto issue_B = [&](int step) {  // thread 0 only
-    const int s = step % NST;
-    const int64_t j0 = (tj_lo + step) * kTileJ;
+  const unsigned rowsA = (unsigned)(a.na - i0 < kTileI ? a.na - i0 : kTileI);
+  auto issue = [&](int step) {  // thread 0 only
+    const int s = step % NST, tile = step / nch, ch = step - tile * nch;
+    const int64_t j0 = (tj_lo + tile) * kTileJ;
     const unsigned rows = (unsigned)(a.nb - j0 < kTileJ ? a.nb - j0 : kTileJ);
-    const unsigned bx = rows * XSP * 8, bb = ((rows + 1) & ~1u) * 8;
-    mbar_arrive_expect_tx(&full[s], bx + bb);
-    bulk_g2s(Bs + s * B_DBL, a.XB + j0 * a.XS, bx, &full[s]);
-    bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
+    const unsigned bx = rows * XSP * 8, bb = ((rows + 1) & ~1u) * 8, ba = rowsA * XSP * 8;
+    double *st = ring + s * STAGE;
+    if (MULTI) {
+      mbar_arrive_expect_tx(&full[s], ba + bx + (ch == 0 ? bb : 0u));
+      bulk_g2s(st, a.XAch + ((int64_t)ch * a.na + i0) * XSP, ba, &full[s]);
+      bulk_g2s(st + A_DBL, a.XBch + ((int64_t)ch * a.nb + j0) * XSP, bx, &full[s]);
+      if (ch == 0) bulk_g2s(bBs + (tile & 1) * kTileJ, a.biasB + j0, bb, &full[s]);
+    } else {
+      mbar_arrive_expect_tx(&full[s], bx + bb);
+      bulk_g2s(st, a.XB + j0 * a.XS, bx, &full[s]);
+      bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
+    }
   };
   if (tid == 0) {
-    const unsigned rows = (unsigned)(a.na - i0 < kTileI ? a.na - i0 : kTileI);
-    const unsigned bx = rows * XSP * 8, bb = ((rows + 1) & ~1u) * 8;
+    const unsigned bb = ((rowsA + 1) & ~1u) * 8, bx = MULTI ? 0u : rowsA * XSP * 8;
     mbar_arrive_expect_tx(fullA, bx + bb);
-    bulk_g2s(As, a.XA + i0 * a.XS, bx, fullA);
+    if (!MULTI) bulk_g2s(As, a.XA + i0 * a.XS, bx, fullA);
     bulk_g2s(bA, a.biasA + i0, bb, fullA);
-    for (int s = 0; s < NST && s < nsteps; s++) issue_B(s);
+    for (int s = 0; s < NST && s < nsteps; s++) issue(s);
   }
 
   double S[4][4][2];
@@ -290,16 +210,17 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
     // producer duty: refill the slot every warp left in the previous iteration
     if (tid == 0 && step >= 1 && step - 1 + NST < nsteps) {
       mbar_wait(&empty[(step - 1) % NST], ((step - 1) / NST) & 1);
-      issue_B(step - 1 + NST);
+      issue(step - 1 + NST);
     }
     const int s = step % NST;
     mbar_wait(&full[s], (step / NST) & 1);
-    const double *Bt = Bs + s * B_DBL;
+    const double *At = MULTI ? ring + s * STAGE : As;
+    const double *Bt = ring + s * STAGE + (MULTI ? A_DBL : 0);
 #pragma unroll
     for (int ks = 0; ks < KC; ks++) {
       double af[4], bf[4];
 #pragma unroll
-      for (int mt = 0; mt < 4; mt++) af[mt] = As[(wi * 32 + mt * 8 + g) * XSP + ks * 4 + q];
+      for (int mt = 0; mt < 4; mt++) af[mt] = At[(wi * 32 + mt * 8 + g) * XSP + ks * 4 + q];
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) bf[nt] = Bt[(wj * 32 + nt * 8 + g) * XSP + ks * 4 + q];
 #pragma unroll
@@ -307,9 +228,33 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) dmma884(S[mt][nt], af[mt], bf[nt]);
     }
-    values_tile_epilogue(a, S, i0, (tj_lo + step) * kTileJ, bA, bBs + s * kTileJ, tab, wi, wj, g, q, lower_only);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the slot (tile and biases)
+    if (MULTI) {
+      // the stage only holds operands: hand it back before the epilogue (the biases live in their own slot, which is
+      // rewritten two tiles later, when every warp has long left this tile)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      const int tile = step / nch;
+      if (step - tile * nch == nch - 1)
+        values_tile_epilogue(a, S, i0, (tj_lo + tile) * kTileJ, bA, bBs + (tile & 1) * kTileJ, tab, wi, wj, g, q, lower_only);
+    } else {
+      values_tile_epilogue(a, S, i0, (tj_lo + step) * kTileJ, bA, bBs + s * kTileJ, tab, wi, wj, g, q, lower_only);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the slot (tile and biases)
+    }
+  }
+}
+
+// chunk-major copy of the descriptor rows for multi-chunk descriptors: Xch[ch][p][XSC] = Xc[p][ch*4*KC + (0..4*KC)), zero padded
+__global__ void __launch_bounds__(256) chunk_rows_kernel(int64_t n, int XS, int KC, int nchunks, int XSC,
+                                                         const double *__restrict__ Xc, double *__restrict__ Xch) {
+  const int64_t total = (int64_t)nchunks * n * XSC;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int dd = (int)(e % XSC);
+    const int64_t r = e / XSC;
+    const int64_t p = r % n;
+    const int ch = (int)(r / n);
+    const int d = ch * 4 * KC + dd;
+    Xch[e] = (dd < 4 * KC && d < XS) ? Xc[p * XS + d] : 0.0;
   }
 }
 
@@ -317,8 +262,7 @@ template <int KC>
 static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
   const bool multi = a.nchunks > 1;
-  const size_t smem =
-      (size_t)((multi ? 2 : 1) * kTileI * XSP + 2 * kTileJ * XSP + kTileI + 2 * kTileJ + 64) * sizeof(double);
+  if (multi ? (a.XSC != XSP || !a.XAch || !a.XBch) : (a.XS != XSP)) return KREG_E_BADARG;  // workspace layout contract
   const int64_t r1 = a.row_end < a.na ? a.row_end : a.na;
   if (r1 <= a.row_begin) return KREG_OK;
   const int64_t ti0 = a.row_begin / kTileI, ti1 = (r1 - 1) / kTileI;
@@ -330,18 +274,15 @@ static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   a.njt = tiles > 200000 ? 16 : tiles > 50000 ? 8 : tiles > 1000 ? 4 : 2;  // measured: 10k rows 4 (0.25 vs 0.27 ms), 50k flat
 #endif
   dim3 grid((unsigned)((ntj + a.njt - 1) / a.njt), (unsigned)(ti1 - ti0 + 1));
-  if (!multi && a.XS == XSP) {
-    constexpr int NST = KC <= 9 ? 3 : 2;
-    const size_t rsmem = (size_t)(kTileI * XSP + NST * kTileJ * XSP + NST * kTileJ + kTileI + 64 + 2 * NST + 2) * sizeof(double);
-    auto kern = values_ring_kernel<KC>;
-    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    kern<<<grid, 256, rsmem, st>>>(a);
-  } else if (multi) {
-    auto kern = values_tile_kernel<KC, true>;
+  if (multi) {
+    const size_t smem = (size_t)(2 * (kTileI + kTileJ) * XSP + 2 * kTileJ + kTileI + 64 + 2 * 2 + 2) * sizeof(double);
+    auto kern = values_ring_kernel<KC, true>;
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(a);
   } else {
-    auto kern = values_tile_kernel<KC, false>;
+    constexpr int NST = KC <= 9 ? 3 : 2;
+    const size_t smem = (size_t)(kTileI * XSP + NST * kTileJ * XSP + NST * kTileJ + kTileI + 64 + 2 * NST + 2) * sizeof(double);
+    auto kern = values_ring_kernel<KC, false>;
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(a);
   }
@@ -893,8 +834,8 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
 
 // workspace carve-up helpers ---------------------------------------------------------------
 struct BuildWs {
-  size_t off_center, off_X, off_bias, off_E, off_P, total;
-  int XS, KC, nchunks;
+  size_t off_center, off_X, off_Xch, off_bias, off_E, off_P, total;
+  int XS, KC, nchunks, XSC;
 };
 
 static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
@@ -911,6 +852,8 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
   };
   w.off_center = take(sh.D);
   w.off_X = take((size_t)n * w.XS);
+  w.XSC = w.KC * 4 + ((w.KC * 4) % 8 == 4 ? 0 : 4);
+  w.off_Xch = w.nchunks > 1 ? take((size_t)w.nchunks * n * w.XSC) : off;  // chunk-major copy for the values kernel
   w.off_bias = take((size_t)n);
   w.off_E = with_grad ? take((size_t)n * ((nat * nat * 3 + 1) & ~1)) : off;
   w.off_P = with_grad ? take((size_t)n * n * ((3 * nat + 3) & ~1)) : off;
@@ -959,9 +902,16 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     prep_rows_kernel<<<blocks, 256, 0, st>>>(natoms, ntrain, xyz_train, xeq, center, w.XS, c1, Xc, bias);
     KREG_LAUNCH_CHECK();
   }
+  double *Xch = reinterpret_cast<double *>(ws + w.off_Xch);
+  if (w.nchunks > 1 && ntrval > 0 && row_begin < ntrval) {
+    chunk_rows_kernel<<<1184, 256, 0, st>>>(ntrain, w.XS, w.KC, w.nchunks, w.XSC, Xc, Xch);
+    KREG_LAUNCH_CHECK();
+  }
   if (ntrval > 0 && row_begin < ntrval) {
     ValuesArgs a;
     a.XA = a.XB = Xc;
+    a.XAch = a.XBch = w.nchunks > 1 ? Xch : nullptr;
+    a.XSC = w.XSC;
     a.biasA = a.biasB = bias;
     a.na = a.nb = ntrain;
     a.XS = w.XS;
@@ -1034,9 +984,20 @@ extern "C" int kreg_kernel_block(int natoms, int64_t na, const double *xyz_a, in
   KREG_LAUNCH_CHECK();
   prep_rows_kernel<<<(int)((nb + 255) / 256), 256, 0, st>>>(natoms, nb, xyz_b, xeq, center, wb.XS, c1, XB, bB);
   KREG_LAUNCH_CHECK();
+  double *XAch = reinterpret_cast<double *>(ws + wa.off_Xch);
+  double *XBch = reinterpret_cast<double *>(ws + wa.total + wb.off_Xch);
+  if (wa.nchunks > 1) {
+    chunk_rows_kernel<<<1184, 256, 0, st>>>(na, wa.XS, wa.KC, wa.nchunks, wa.XSC, XA, XAch);
+    KREG_LAUNCH_CHECK();
+    chunk_rows_kernel<<<1184, 256, 0, st>>>(nb, wb.XS, wb.KC, wb.nchunks, wb.XSC, XB, XBch);
+    KREG_LAUNCH_CHECK();
+  }
   ValuesArgs a;
   a.XA = XA;
   a.XB = XB;
+  a.XAch = wa.nchunks > 1 ? XAch : nullptr;
+  a.XBch = wa.nchunks > 1 ? XBch : nullptr;
+  a.XSC = wa.XSC;
   a.biasA = bA;
   a.biasB = bB;
   a.na = na;
