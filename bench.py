@@ -125,11 +125,13 @@ def cpu_baseline(eq, xyz_tr, alpha, prior, seconds=12.0, threads=None):
     xeq = O.xeq(eq)
     x_tr = O.descriptors(xyz_tr, xeq)
 
+    last = {}
+
     def run(n):
-        xte = S.geometries(eq, n, seed=2)
+        xte = S.geometries(eq, n, seed=2)  # the first n geometries of rank 0's test batch (same generator stream)
         t0 = time.perf_counter()
         x_te = O.descriptors(xte, xeq)  # descriptor build is part of the path
-        O.predict_mlatomf(xyz_tr, x_tr, alpha, SIGMA, prior, NTRAIN, 0, xte, x_te, True, True)
+        last["e"], last["g"] = O.predict_mlatomf(xyz_tr, x_tr, alpha, SIGMA, prior, NTRAIN, 0, xte, x_te, True, True)
         return time.perf_counter() - t0
 
     n0 = 4 * threads
@@ -138,7 +140,8 @@ def cpu_baseline(eq, xyz_tr, alpha, prior, seconds=12.0, threads=None):
     n = max(threads, n // threads * threads)
     t = run(n)
     return {"value": n / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} of {NTEST} test geometries, full Ntrain={NTRAIN}, {t:.1f} s wall"}, n, t
+            "sample": f"{n} of {NTEST} test geometries, full Ntrain={NTRAIN}, {t:.1f} s wall",
+            "results": (last["e"], last["g"])}, n, t
 
 
 def step_latency(engine, model, dev):
@@ -503,8 +506,21 @@ def run_ours(args):
         line["kbuild_configs"] = kbuild_configs(engine, dev, line["kbuild"]["hbm_peak_gbs"], peak_dmma)
         line["step_latency"] = step_latency(engine, model, dev)
     if world == 1 and not args.no_cpu:
-        base, _, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
+        base, n_cpu, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
+        e_cpu, g_cpu = base.pop("results")
         line["cpu_baseline"] = base
+        # parity of the timed run itself: the CPU port predicted the first n_cpu geometries of this rank's test batch
+        # with the same alpha -- diff them against what the timed kernel left in d_e / d_g
+        e_gpu, g_gpu = d_e[:n_cpu].cpu().numpy(), d_g[:n_cpu].cpu().numpy()
+        line["parity"] = {
+            "against": "cpu_baseline (oracle port of MLatomF's loop, A_KRR_kernel.f90:327-412), same alpha, same geometries",
+            "geometries": int(n_cpu), "ntrain": NTRAIN,
+            "max_rel_energy": float(np.abs(e_gpu - e_cpu).max() / np.abs(e_cpu).max()),
+            "max_abs_gradient": float(np.abs(g_gpu - g_cpu).max()),
+            "max_abs_gradient_reference": float(np.abs(g_cpu).max()),
+            "tolerance": {"energy_rel": 1e-10, "gradient_abs": 1e-8},
+        }
+        line["parity"]["ok"] = bool(line["parity"]["max_rel_energy"] <= 1e-10 and line["parity"]["max_abs_gradient"] <= 1e-8)
         shipped = kreg_so_baseline(eq, xyz_tr, alpha.cpu().numpy())
         if shipped:
             line["cpu_baseline_reference_as_shipped"] = shipped

@@ -88,6 +88,9 @@ int kreg_descriptors(int natoms, int64_t npoints, const double *xyz, const doubl
  * and for gradient models the descriptor Jacobians plus 3*natoms+1 doubles per geometry pair).
  * kreg_kernel_block needs kreg_build_workspace_bytes(natoms, na, 0) + kreg_build_workspace_bytes(natoms, nb, 0). */
 size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr);
+/* The same for a call that assembles only rows [row_begin, row_end) (a rank's slab in the sharded assembly): the
+ * per-pair block then covers only the geometries whose gradient rows fall in the range, not all ntrain^2 pairs. */
+size_t kreg_build_workspace_bytes_rows(int natoms, int64_t ntrain, int64_t ntrgr, int64_t row_begin, int64_t row_end);
 
 /* Replaces KREG.kreg.calc_kernel_matrix + the diagonal shift of calcAlpha
  * (KREG.f90:293-346 and :616-622; A_KRR_kernel.f90:130-188, A_KRR.f90:905-918).
@@ -120,10 +123,22 @@ int kreg_solve_workspace_bytes(int64_t m, size_t *device_bytes, size_t *host_byt
  * dpotrs): in-place Cholesky of the matrix produced by kreg_build_kernel_matrix
  * (KREG_FILL_LOWER or _FULL) and solve for one right-hand side.  y is overwritten with alpha.
  * The only library call on the path (cuSOLVER potrf/potrs); timed separately by bench.py.
- * Synchronises the stream to read `info`.  Returns info (>0: leading minor not positive
- * definite; K is destroyed) or a negative error. */
+ * Synchronises the stream ONCE (to read potrf's `info`); the triangular solves are left running on `stream`.
+ * Returns info (>0: leading minor not positive definite; K is destroyed) or a negative error. */
 int kreg_solve(int64_t m, double *K, int64_t ldk, double *y_inout, void *device_workspace,
                size_t device_bytes, void *host_workspace, size_t host_bytes, void *stream);
+
+/* Symmetric-indefinite fallback, replaces mathUtils.solveSysLinEqsBK (mlatom/fortran/mathUtils.f90:106-186: dsytrf +
+ * dsytrs, entered from :24-26 when dpotrf fails).  K is a FRESHLY assembled matrix (kreg_build_kernel_matrix,
+ * KREG_FILL_LOWER is enough) -- not the one kreg_solve destroyed: the reference hands Bunch-Kaufman the array potrf
+ * already overwrote, which is not imitated.  y is overwritten with alpha, K is destroyed.
+ *   method 1: Bunch-Kaufman, cuSOLVER sytrf + sytrs on the stored triangle (m <= 46000: sytrf has a 32-bit interface);
+ *   method 2: pivoted LU, cuSOLVER getrf + getrs after mirroring the stored triangle in place;
+ *   method 0: 1 when m allows it, else 2.
+ * Returns 0, a negative error, or info > 0 (an exactly singular pivot). Synchronises the stream once to read info. */
+int kreg_solve_indefinite_workspace_bytes(int64_t m, int method, size_t *device_bytes, size_t *host_bytes);
+int kreg_solve_indefinite(int64_t m, double *K, int64_t ldk, double *y_inout, int method, void *device_workspace,
+                          size_t device_bytes, void *host_workspace, size_t host_bytes, void *stream);
 
 /* Prediction -------------------------------------------------------------------------------- */
 

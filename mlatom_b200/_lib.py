@@ -21,6 +21,7 @@ FILL_LOWER = 0
 FILL_FULL = 1
 PREDICT_ENERGY = 1
 PREDICT_GRADIENT = 2
+FUSED_MAX_NATOMS = 24  # KREG_FUSED_MAX_NATOMS: largest molecule of the register-resident prediction kernels
 
 _ERRORS = {
     KREG_E_BADARG: "bad argument",
@@ -39,6 +40,7 @@ PROTOTYPES = {
     "kreg_xeq": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "kreg_descriptors": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kreg_build_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64]),
+    "kreg_build_workspace_bytes_rows": (c_size_t, [c_int, c_int64, c_int64, c_int64, c_int64]),
     "kreg_build_kernel_matrix": (
         c_int,
         [c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_double, c_double, c_double, c_int64, c_int64,
@@ -51,6 +53,9 @@ PROTOTYPES = {
     ),
     "kreg_solve_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t), POINTER(c_size_t)]),
     "kreg_solve": (c_int, [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "kreg_solve_indefinite_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
+    "kreg_solve_indefinite": (
+        c_int, [c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "kreg_precompute_v": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kreg_packed_model_bytes": (c_size_t, [c_int, c_int64, c_int]),
     "kreg_pack_model": (

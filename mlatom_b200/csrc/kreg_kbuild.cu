@@ -384,7 +384,8 @@ struct GradArgs {
   int64_t row_begin, row_end;  // absolute row range of K to produce
   double *K;
   int64_t ldk;
-  double *P;             // [ntr][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
+  double *P;             // [i1 - i0][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
+  int64_t p_i0;          // first geometry i whose gradient rows intersect [row_begin, row_end): row 0 of P
   int ES;                // doubles per E block: Nat*Nat*3 rounded up to even (16-byte aligned blocks for bulk copies)
 };
 
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   }
   __syncthreads();
   // pair terms -> workspace (coalesced)
-  double *P = a.P + (i * a.ntr + j0) * PW;
+  double *P = a.P + ((i - a.p_i0) * a.ntr + j0) * PW;
   {
     // only pairs whose gradient-gradient block is emitted (j <= i unless mirrored) are read back by grad_emit_kernel
     const int64_t jgg = full ? a.ntr : i + 1;
@@ -682,7 +683,7 @@ __global__ void __launch_bounds__(128, 5) pair_terms_small_kernel(const GradArgs
   }
   __syncthreads();
   // pair terms -> workspace (coalesced); only pairs whose gradient-gradient block is emitted are read back
-  double *P = a.P + (i * a.ntr + j0) * PW;
+  double *P = a.P + ((i - a.p_i0) * a.ntr + j0) * PW;
   const int64_t jgg = full ? a.ntr : i + 1;
   const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
   for (int e = tid; e < np * PW; e += JT) P[e] = Us[(e / PW) * PWS + e % PW];
@@ -746,7 +747,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
     const int buf = n & 1;
     const unsigned bp = npair * PW * 8, bx = npair * (unsigned)XS * 8, be = npair * EJ * 8;
     mbar_arrive_expect_tx(&bar[buf], bp + bx + be);
-    bulk_g2s(Pb + buf * TJ * PW, a.P + (i * a.ntr + jb) * PW, bp, &bar[buf]);
+    bulk_g2s(Pb + buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
     bulk_g2s(Xj + buf * TJ * SM::XSMAX, a.Xc + jb * XS, bx, &bar[buf]);
     bulk_g2s(Ejs + buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
   };
@@ -867,8 +868,20 @@ struct BuildWs {
   int XS, KC, nchunks, XSC;
 };
 
-static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
+// geometries whose gradient rows intersect the row range [row_begin, row_end) of a matrix with nv value rows
+static void grad_geom_range(int nat, int64_t n, int64_t nv, int64_t row_begin, int64_t row_end, int64_t *i0, int64_t *i1) {
+  const int64_t G3 = 3 * (int64_t)nat;
+  int64_t a = row_begin > nv ? (row_begin - nv) / G3 : 0;
+  int64_t b = row_end > nv ? (row_end - nv + G3 - 1) / G3 : 0;
+  if (b > n) b = n;
+  if (a > b) a = b;
+  *i0 = a;
+  *i1 = b;
+}
+
+static BuildWs build_ws(int nat, int64_t n, bool with_grad, int64_t pair_rows = -1) {
   BuildWs w;
+  if (pair_rows < 0) pair_rows = n;
   const TcShape sh(nat);
   chunking(sh.KS, &w.KC, &w.nchunks);
   w.XS = w.KC * w.nchunks * 4;
@@ -885,7 +898,7 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad) {
   w.off_Xch = w.nchunks > 1 ? take((size_t)w.nchunks * n * w.XSC) : off;  // chunk-major copy for the values kernel
   w.off_bias = take((size_t)n);
   w.off_E = with_grad ? take((size_t)n * ((nat * nat * 3 + 1) & ~1)) : off;
-  w.off_P = with_grad ? take((size_t)n * n * ((3 * nat + 3) & ~1)) : off;
+  w.off_P = with_grad ? take((size_t)pair_rows * n * ((3 * nat + 3) & ~1)) : off;
   w.total = off;
   return w;
 }
@@ -897,6 +910,19 @@ using namespace kreg;
 extern "C" size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain < 0) return 0;
   return build_ws(natoms, ntrain, ntrgr > 0).total;
+}
+
+extern "C" size_t kreg_build_workspace_bytes_rows(int natoms, int64_t ntrain, int64_t ntrgr, int64_t row_begin,
+                                                  int64_t row_end) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain < 0 || row_begin < 0 || row_end < row_begin) return 0;
+  if (ntrgr <= 0) return build_ws(natoms, ntrain, false).total;
+  // the value block, when present, always has ntrain rows (kreg_build_kernel_matrix: ntrval in {0, ntrain}); a row range
+  // is interpreted for both layouts and the larger requirement returned, so the caller need not pass ntrval
+  int64_t i0, i1, j0, j1;
+  grad_geom_range(natoms, ntrain, ntrain, row_begin, row_end, &i0, &i1);
+  grad_geom_range(natoms, ntrain, 0, row_begin, row_end, &j0, &j1);
+  const int64_t rows = (i1 - i0) > (j1 - j0) ? (i1 - i0) : (j1 - j0);
+  return build_ws(natoms, ntrain, true, rows).total;
 }
 
 extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrval, int64_t ntrgr,
@@ -913,7 +939,9 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
   if (fill != KREG_FILL_LOWER && fill != KREG_FILL_FULL) return KREG_E_BADARG;
   // gradient models: the mirrored (FULL) layout is only produced for the whole matrix
   if (fill == KREG_FILL_FULL && ntrgr > 0 && !(row_begin == 0 && row_end == M)) return KREG_E_BADARG;
-  const BuildWs w = build_ws(natoms, ntrain, ntrgr > 0);
+  int64_t gi0 = 0, gi1 = 0;
+  grad_geom_range(natoms, ntrain, ntrval, row_begin, row_end, &gi0, &gi1);
+  const BuildWs w = build_ws(natoms, ntrain, ntrgr > 0, gi1 - gi0);
   if (workspace_bytes < w.total) return KREG_E_WORKSPACE;
   if (row_begin == row_end) return KREG_OK;
   cudaStream_t st = as_stream(stream);
@@ -980,6 +1008,7 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     g.K = K;
     g.ldk = ldk;
     g.P = reinterpret_cast<double *>(ws + w.off_P);
+    g.p_i0 = gi0;
     g.ES = (natoms * natoms * 3 + 1) & ~1;
     rc = launch_grad(natoms, g, st);
     if (rc) return rc;

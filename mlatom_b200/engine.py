@@ -25,10 +25,33 @@ except AttributeError:  # pragma: no cover - older / newer torch without the pri
     _raw_stream = None
 
 
-def _stream() -> int:
+def _stream(device=None) -> int:
+    """Raw handle of the current stream of ``device`` (default: the current device)."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
     if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
-    return torch.cuda.current_stream().cuda_stream
+        return _raw_stream(idx)
+    return torch.cuda.current_stream(idx).cuda_stream
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(t: torch.Tensor):
+    """Device guard for an ABI call: every kernel launch, cuSOLVER handle and SM-count query in the library binds to
+    the CURRENT device, so a call on tensors of another GPU (``kreg(device='cuda:1')`` while device 0 is current) must
+    switch to the tensors' device first.  No-op (no context-manager cost on the MD step) when it already is current;
+    pinned host tensors (zero-copy graph path) run on the current device."""
+    if not t.is_cuda or t.device.index is None or t.device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(t.device)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -64,7 +87,8 @@ def xeq(req) -> torch.Tensor:
     req = _dev(req)
     nat = req.shape[0]
     out = torch.empty(nat * (nat - 1) // 2, dtype=F64, device=req.device)
-    call("kreg_xeq", nat, _ptr(req), _ptr(out), _stream())
+    with _on(req):
+        call("kreg_xeq", nat, _ptr(req), _ptr(out), _stream(req.device))
     return out
 
 
@@ -73,8 +97,17 @@ def descriptors(xyz, xeq_: torch.Tensor) -> torch.Tensor:
     xyz = _dev(xyz, xeq_.device)
     n, nat, _ = xyz.shape
     out = torch.empty((n, nat * (nat - 1) // 2), dtype=F64, device=xyz.device)
-    call("kreg_descriptors", nat, n, _ptr(xyz), _ptr(xeq_), _ptr(out), _stream())
+    with _on(xyz):
+        call("kreg_descriptors", nat, n, _ptr(xyz), _ptr(xeq_), _ptr(out), _stream(xyz.device))
     return out
+
+
+def build_workspace_bytes(nat: int, ntr: int, ntrgr: int, rows: Optional[Tuple[int, int]] = None) -> int:
+    """Scratch bytes of one assembly call; with ``rows`` only the pair-term block of the geometries those rows touch."""
+    lib = _lib.load()
+    if rows is None:
+        return int(lib.kreg_build_workspace_bytes(nat, ntr, ntrgr))
+    return int(lib.kreg_build_workspace_bytes_rows(nat, ntr, ntrgr, int(rows[0]), int(rows[1])))
 
 
 def build_kernel_matrix(
@@ -89,12 +122,15 @@ def build_kernel_matrix(
     rows: Optional[Tuple[int, int]] = None,
     out: Optional[torch.Tensor] = None,
     row_offset: int = 0,
+    workspace: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """K + diag(lambda) assembled on the device (KREG.f90:293-346 + :616-622).
 
     Returns the (M, M) row-major matrix; with ``fill=FILL_LOWER`` only j <= i is defined.
     ``rows=(r0, r1)`` restricts the assembly to a row slab (multi-GPU sharding); ``out`` is then either the
     whole matrix or, with ``row_offset=r0``, a slab buffer whose first row is matrix row r0.
+    ``workspace`` (uint8, >= build_workspace_bytes) lets a caller that assembles repeatedly (grid search) reuse one
+    scratch allocation.
     """
     xyz = _dev(xyz, xeq_.device)
     ntr, nat, _ = xyz.shape
@@ -106,13 +142,17 @@ def build_kernel_matrix(
     r0, r1 = (0, m) if rows is None else rows
     assert out.is_cuda and out.dtype == F64 and out.stride(1) == 1 and out.shape[1] >= m
     assert out.shape[0] >= r1 - row_offset and row_offset <= r0
-    ws_bytes = _lib.load().kreg_build_workspace_bytes(nat, ntr, ntrgr)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
-    call(
-        "kreg_build_kernel_matrix", nat, ntr, ntrval, ntrgr, _ptr(xyz), _ptr(xeq_), float(sigma), float(lambdav),
-        float(lambdagradxyz), r0, r1, fill, _ptr(out) - row_offset * out.stride(0) * 8, out.stride(0), _ptr(ws), ws_bytes,
-        _stream(),
-    )
+    ws_bytes = build_workspace_bytes(nat, ntr, ntrgr, None if rows is None else (r0, r1))
+    if workspace is not None and workspace.numel() >= ws_bytes and workspace.device == xyz.device:
+        ws = workspace
+    else:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+    with _on(xyz):
+        call(
+            "kreg_build_kernel_matrix", nat, ntr, ntrval, ntrgr, _ptr(xyz), _ptr(xeq_), float(sigma), float(lambdav),
+            float(lambdagradxyz), r0, r1, fill, _ptr(out) - row_offset * out.stride(0) * 8, out.stride(0), _ptr(ws),
+            ws.numel(), _stream(xyz.device),
+        )
     return out
 
 
@@ -125,8 +165,9 @@ def kernel_block(xyz_a: torch.Tensor, xyz_b: torch.Tensor, xeq_: torch.Tensor, s
     lib = _lib.load()
     ws_bytes = lib.kreg_build_workspace_bytes(nat, na, 0) + lib.kreg_build_workspace_bytes(nat, nb, 0)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz_a.device)
-    call("kreg_kernel_block", nat, na, _ptr(xyz_a), nb, _ptr(xyz_b), _ptr(xeq_), float(sigma), _ptr(out),
-         out.stride(0), _ptr(ws), ws_bytes, _stream())
+    with _on(xyz_a):
+        call("kreg_kernel_block", nat, na, _ptr(xyz_a), nb, _ptr(xyz_b), _ptr(xeq_), float(sigma), _ptr(out),
+             out.stride(0), _ptr(ws), ws_bytes, _stream(xyz_a.device))
     return out
 
 
@@ -137,13 +178,46 @@ def solve(k: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     returns alpha.  Raises KregError(code > 0) if K is not positive definite."""
     m = k.shape[0]
     alpha = y.detach().clone().to(F64).contiguous()
-    dbytes, hbytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
-    call("kreg_solve_workspace_bytes", m, ctypes.byref(dbytes), ctypes.byref(hbytes))
-    dws = torch.empty(max(dbytes.value, 16), dtype=torch.uint8, device=k.device)
-    hws = torch.empty(max(hbytes.value, 16), dtype=torch.uint8).pin_memory()
-    call("kreg_solve", m, _ptr(k), k.stride(0), _ptr(alpha), _ptr(dws), dbytes.value, hws.data_ptr(), hbytes.value,
-         _stream())
+    with _on(k):
+        dbytes, hbytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        call("kreg_solve_workspace_bytes", m, ctypes.byref(dbytes), ctypes.byref(hbytes))
+        dws = torch.empty(max(dbytes.value, 16), dtype=torch.uint8, device=k.device)
+        hws = _pinned_scratch(max(hbytes.value, 16))
+        call("kreg_solve", m, _ptr(k), k.stride(0), _ptr(alpha), _ptr(dws), dbytes.value, hws.data_ptr(), hbytes.value,
+             _stream(k.device))
     return alpha
+
+
+SOLVE_AUTO, SOLVE_BUNCH_KAUFMAN, SOLVE_LU = 0, 1, 2
+
+
+def solve_indefinite(k: torch.Tensor, y: torch.Tensor, method: int = SOLVE_AUTO) -> torch.Tensor:
+    """alpha = K^-1 y for a symmetric matrix that is NOT positive definite: Bunch-Kaufman (cuSOLVER sytrf/sytrs) or
+    pivoted LU, behind the C ABI (kreg_solve_indefinite; the reference: solveSysLinEqsBK, mathUtils.f90:106-186).
+    ``k`` must be freshly assembled (lower triangle valid) -- not the matrix a failed ``solve`` left behind -- and is
+    destroyed.  Raises KregError(code > 0) for an exactly singular pivot."""
+    m = k.shape[0]
+    alpha = y.detach().clone().to(F64).contiguous()
+    with _on(k):
+        dbytes, hbytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        call("kreg_solve_indefinite_workspace_bytes", m, int(method), ctypes.byref(dbytes), ctypes.byref(hbytes))
+        dws = torch.empty(max(dbytes.value, 16), dtype=torch.uint8, device=k.device)
+        hws = _pinned_scratch(max(hbytes.value, 16))
+        call("kreg_solve_indefinite", m, _ptr(k), k.stride(0), _ptr(alpha), int(method), _ptr(dws), dbytes.value,
+             hws.data_ptr(), hbytes.value, _stream(k.device))
+    return alpha
+
+
+_PINNED: dict = {}
+
+
+def _pinned_scratch(nbytes: int) -> torch.Tensor:
+    """One small pinned host buffer per size class, reused across solves (pinning costs ~100 us per allocation)."""
+    size = 1 << max(8, (int(nbytes) - 1).bit_length())
+    buf = _PINNED.get(size)
+    if buf is None:
+        buf = _PINNED[size] = torch.empty(size, dtype=torch.uint8).pin_memory()
+    return buf
 
 
 def hessian(x_train: torch.Tensor, alpha_val: Optional[torch.Tensor], xeq_: torch.Tensor, sigma: float,
@@ -153,8 +227,9 @@ def hessian(x_train: torch.Tensor, alpha_val: Optional[torch.Tensor], xeq_: torc
     n, nat, _ = xyz.shape
     out = torch.zeros((n, 3 * nat, 3 * nat), dtype=F64, device=xyz.device)
     ntr = 0 if alpha_val is None else int(alpha_val.numel())
-    call("kreg_hessian", nat, ntr, _ptr(x_train), _ptr(alpha_val), _ptr(xeq_), float(sigma), n, _ptr(xyz), _ptr(out),
-         _stream())
+    with _on(xyz):
+        call("kreg_hessian", nat, ntr, _ptr(x_train), _ptr(alpha_val), _ptr(xeq_), float(sigma), n, _ptr(xyz), _ptr(out),
+             _stream(xyz.device))
     return out
 
 
@@ -162,7 +237,9 @@ def precompute_v(xyz_tr: torch.Tensor, xeq_: torch.Tensor, alpha_grad: torch.Ten
     """v_j = J_j alpha_grad,j. alpha_grad (Ntr, Nat, 3) -> (Ntr, D)."""
     ntr, nat, _ = xyz_tr.shape
     out = torch.empty((ntr, nat * (nat - 1) // 2), dtype=F64, device=xyz_tr.device)
-    call("kreg_precompute_v", nat, ntr, _ptr(xyz_tr), _ptr(xeq_), _ptr(alpha_grad.contiguous()), _ptr(out), _stream())
+    with _on(xyz_tr):
+        call("kreg_precompute_v", nat, ntr, _ptr(xyz_tr), _ptr(xeq_), _ptr(alpha_grad.contiguous()), _ptr(out),
+             _stream(xyz_tr.device))
     return out
 
 
@@ -198,8 +275,9 @@ class PackedModel:
         nbytes = _lib.load().kreg_packed_model_bytes(nat, ntr, 1 if v is not None else 0)
         packed = torch.empty(nbytes, dtype=torch.uint8, device=xeq_.device)
         center = torch.empty_like(xeq_)
-        call("kreg_pack_model", nat, ntr, _ptr(xyz_tr), _ptr(xeq_), _ptr(alpha_v), _ptr(v), float(sigma),
-             _ptr(center), _ptr(packed), nbytes, _stream())
+        with _on(xeq_):
+            call("kreg_pack_model", nat, ntr, _ptr(xyz_tr), _ptr(xeq_), _ptr(alpha_v), _ptr(v), float(sigma),
+                 _ptr(center), _ptr(packed), nbytes, _stream(xeq_.device))
         return cls(nat, ntr, float(sigma), float(prior), v is not None, xeq_, center, packed)
 
     @classmethod
@@ -214,14 +292,18 @@ class PackedModel:
         nbytes = _lib.load().kreg_packed_model_bytes(natoms, ntr, 0)
         packed = torch.empty(nbytes, dtype=torch.uint8, device=xeq_.device)
         center = torch.empty_like(xeq_)
-        call("kreg_pack_model_x", natoms, ntr, _ptr(x_tr), _ptr(alpha_v), None, float(sigma), _ptr(center), _ptr(packed),
-             nbytes, _stream())
+        with _on(xeq_):
+            call("kreg_pack_model_x", natoms, ntr, _ptr(x_tr), _ptr(alpha_v), None, float(sigma), _ptr(center),
+                 _ptr(packed), nbytes, _stream(xeq_.device))
         return cls(natoms, ntr, float(sigma), float(prior), False, xeq_, center, packed)
 
-    def predict(self, xyz: torch.Tensor, energy: bool = True, gradient: bool = True, out_e=None, out_g=None):
+    def predict(self, xyz: torch.Tensor, energy: bool = True, gradient: bool = True, out_e=None, out_g=None, ws=None):
         """xyz (N, Nat, 3) cuda fp64 -> (E (N,) or None, dE/dxyz (N, Nat, 3) or None).  Pinned host tensors are accepted
         too (unified addressing: the kernels then read / write host memory directly -- only sensible for a few
-        geometries, where it saves the copy operations; see GraphPredictor)."""
+        geometries, where it saves the copy operations; see GraphPredictor).
+
+        ``ws``: scratch tensor owned by the CALLER (``workspace(n)``).  Anything that records this call in a CUDA graph
+        must pass its own: the graph keeps the raw pointer, so the scratch has to live as long as the graph does."""
         assert (xyz.is_cuda or xyz.is_pinned()) and xyz.dtype == F64 and xyz.is_contiguous()
         n = xyz.shape[0]
         assert xyz.shape[1] == self.natoms
@@ -230,19 +312,52 @@ class PackedModel:
         g = (out_g if out_g is not None else torch.empty((n, self.natoms, 3), dtype=F64, device=odev)) if gradient else None
         flags = (PREDICT_ENERGY if energy else 0) | (PREDICT_GRADIENT if gradient else 0)
         hv = 1 if self.has_gradient_terms else 0
-        ws, ws_bytes = None, 0
-        if 0 < n <= self._small_batch_limit():  # latency mode: split the training set over the chip
-            ws_bytes = _lib.load().kreg_predict_workspace_bytes(self.natoms, self.ntrain, hv, n)
-            if ws_bytes:
-                if self._ws is None or self._ws.numel() < ws_bytes:
-                    self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=odev)
-                ws = self._ws
-        call("kreg_predict", self.natoms, self.ntrain, _ptr(self.packed), _ptr(self.center), _ptr(self.xeq),
-             self.sigma, self.prior, hv, n, _ptr(xyz), flags, _ptr(e), _ptr(g), _ptr(ws), ws_bytes, _stream())
+        ws_bytes = 0
+        if ws is not None:
+            ws_bytes = ws.numel()
+        elif n > 0 and (self._always_ws or n <= self._small_batch_limit()):
+            need = self.workspace_bytes(n)
+            if need:
+                ws = self._shared_ws(need, odev)
+                ws_bytes = ws.numel()
+        with _on(self.packed):
+            call("kreg_predict", self.natoms, self.ntrain, _ptr(self.packed), _ptr(self.center), _ptr(self.xeq),
+                 self.sigma, self.prior, hv, n, _ptr(xyz), flags, _ptr(e), _ptr(g), _ptr(ws), ws_bytes,
+                 _stream(self.packed.device))
         return e, g
 
-    _ws: Optional[torch.Tensor] = None       # small-batch scratch, grown on demand
+    _ws: Optional[torch.Tensor] = None       # scratch shared by eager calls, grown on demand
+    _ws_retired: Optional[list] = None       # outgrown scratch buffers: kept alive (see _shared_ws)
     _wave_rows: Optional[int] = None
+
+    @property
+    def _always_ws(self) -> bool:
+        """Molecules above the register-resident kernels' range (> 24 atoms) run the tiled three-kernel path, which
+        needs scratch for every batch size."""
+        return self.natoms > _lib.FUSED_MAX_NATOMS
+
+    def workspace_bytes(self, n: int) -> int:
+        """Scratch bytes kreg_predict can use for a batch of n geometries (0: none needed)."""
+        with _on(self.packed):
+            return int(_lib.load().kreg_predict_workspace_bytes(self.natoms, self.ntrain,
+                                                                1 if self.has_gradient_terms else 0, int(n)))
+
+    def workspace(self, n: int) -> Optional[torch.Tensor]:
+        """A scratch tensor the caller owns (CUDA-graph owners: one per captured batch shape)."""
+        need = self.workspace_bytes(n)
+        return torch.empty(need, dtype=torch.uint8, device=self.device) if need else None
+
+    def _shared_ws(self, need: int, device) -> torch.Tensor:
+        # A larger batch replaces the shared scratch, but the outgrown buffer is never handed back to the allocator
+        # while the model lives: a CUDA graph captured around an eager predict() (torch.cuda.graph over user code)
+        # holds its raw pointer.  The total is bounded (the small-batch scratch tops out at ~2 x SMs x tile bytes).
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            if self._ws is not None:
+                if self._ws_retired is None:
+                    self._ws_retired = []
+                self._ws_retired.append(self._ws)
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
 
     def _small_batch_limit(self) -> int:
         return self.wave_rows() // 2
@@ -255,10 +370,15 @@ class PackedModel:
             self._wave_rows = int(rows) * int(sms)
         return self._wave_rows
 
+    _host_predictor = None
+
     def predict_host(self, xyz_host: np.ndarray, energy: bool = True, gradient: bool = True, chunk: Optional[int] = None):
         """Host-buffer entry point: numpy (N, Nat, 3) in, numpy out.  Streams chunks through pinned
         staging buffers with H2D copy / kernel / D2H copy overlapped on three streams."""
-        return HostPredictor(self, chunk).run(xyz_host, energy, gradient)
+        hp = self._host_predictor
+        if hp is None or (chunk is not None and hp.chunk != int(chunk)):
+            hp = self._host_predictor = HostPredictor(self, chunk)  # streams, events, staging buffers: built once
+        return hp.run(xyz_host, energy, gradient)
 
 
 class HostPredictor:
@@ -341,6 +461,7 @@ class GraphPredictor:
         self.x = torch.zeros((n, nat, 3), dtype=F64, device=dev)
         self.out = torch.zeros(n * (1 + 3 * nat), dtype=F64, device=dev)
         self.e, self.g = self.out[:n], self.out[n:].view(n, nat, 3)
+        self.ws = model.workspace(n)  # owned by this graph: the captured kernels keep its raw pointer
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -362,10 +483,10 @@ class GraphPredictor:
 
     def _body(self):
         if self.zero_copy:  # two graph nodes instead of five: no copy operations around the kernels
-            self.model.predict(self.x_host, self.energy, self.gradient, out_e=self.e_host, out_g=self.g_host)
+            self.model.predict(self.x_host, self.energy, self.gradient, out_e=self.e_host, out_g=self.g_host, ws=self.ws)
             return
         self.x.copy_(self.x_host, non_blocking=True)
-        self.model.predict(self.x, self.energy, self.gradient, out_e=self.e, out_g=self.g)
+        self.model.predict(self.x, self.energy, self.gradient, out_e=self.e, out_g=self.g, ws=self.ws)
         if self.energy and self.gradient:
             self.out_host.copy_(self.out, non_blocking=True)
         elif self.energy:

@@ -24,7 +24,7 @@ import torch
 
 from . import data as _data
 from . import engine
-from ._lib import FILL_FULL, FILL_LOWER, KregError
+from ._lib import FILL_LOWER, KregError
 
 
 def _as_database(molecular_database=None, molecule=None):
@@ -103,6 +103,7 @@ class KREG_API:
         """Array entry point: xyz (N,Nat,3), req (Nat,3), y (N,), ygrad (N,Nat,3); numpy or cuda tensors."""
         if y is None and ygrad is None:
             raise ValueError("nothing to learn: give property_to_learn and/or xyz_derivative_property_to_learn")
+        self._model, self._graphs = None, {}  # a retrain through this entry point must not keep the old model's graphs alive
         self.sigma, self.lambdav, self.lambdagradxyz = float(sigma), float(lambdav), float(lambdagradxyz)
         d_xyz = xyz if torch.is_tensor(xyz) else self._t(xyz)
         d_xyz = d_xyz.to(self._dev(), torch.float64).contiguous()
@@ -147,16 +148,17 @@ class KREG_API:
         except KregError as err:
             if err.code <= 0:
                 raise
-            # The reference falls back to Bunch-Kaufman (mathUtils.f90:24-26) when dpotrf fails; here the
-            # matrix is re-assembled (potrf destroyed it) and solved by pivoted LU (cuSOLVER getrf/getrs).
+            # The reference falls back to Bunch-Kaufman (mathUtils.f90:24-26 -> solveSysLinEqsBK :106-186) when dpotrf
+            # fails.  Same here, behind the C ABI (kreg_solve_indefinite: cuSOLVER sytrf/sytrs), on a RE-ASSEMBLED
+            # matrix written into the same buffer: potrf has overwritten part of the first one (the reference hands BK
+            # that clobbered array; not imitated).
             if not shutup:
-                print(" Cholesky decomposition failed. Attempting a pivoted factorisation")
+                print(" Cholesky decomposition failed. Attempting Bunch-Kaufman decomposition")
             warnings.warn(f"K + lambda is not positive definite (leading minor {err.code}); "
-                          "falling back to a pivoted LU solve -- consider a larger lambda")
-            del k
-            k = engine.build_kernel_matrix(d_xyz, d_xeq, self.sigma, self.lambdav, self.lambdagradxyz, use_values=use_v,
-                                           use_gradients=use_g, fill=FILL_FULL)
-            d_alpha = torch.linalg.solve(k, d_y)
+                          "falling back to a Bunch-Kaufman solve -- consider a larger lambda")
+            engine.build_kernel_matrix(d_xyz, d_xeq, self.sigma, self.lambdav, self.lambdagradxyz, use_values=use_v,
+                                       use_gradients=use_g, fill=FILL_LOWER, out=k)
+            d_alpha = engine.solve_indefinite(k, d_y)
         del k
         self._model = engine.PackedModel.from_training_set(d_xyz, d_xeq, d_alpha, self.sigma, self.prior, self.NtrVal,
                                                            self.NtrGrXYZ)

@@ -46,7 +46,10 @@ class BatchedNVE:
         self.epot = torch.empty(b, dtype=F64, device=xyz.device)
         self.grad = torch.empty((b, nat, 3), dtype=F64, device=xyz.device)
         self.ekin = torch.empty(b, dtype=F64, device=xyz.device)
-        model.predict(self.xyz, True, True, out_e=self.epot, out_g=self.grad)  # forces at t = 0
+        # scratch owned by this integrator: the captured graph keeps the raw pointers (never the model's shared scratch)
+        self.ws = model.workspace(b)
+        self.ws_aux = aux_model.workspace(b) if aux_model is not None else None
+        model.predict(self.xyz, True, True, out_e=self.epot, out_g=self.grad, ws=self.ws)  # forces at t = 0
         self._kinetic()
         if self.aux is not None:
             self._check_uncertain()  # an initial condition can already be uncertain (stop_step = 0)
@@ -76,7 +79,7 @@ class BatchedNVE:
 
     def _check_uncertain(self):
         """uq = |E - E_aux| (al_utils.py:1418-1424); running trajectories above the threshold stop here."""
-        self.aux.predict(self.xyz, True, False, out_e=self.eaux)
+        self.aux.predict(self.xyz, True, False, out_e=self.eaux, ws=self.ws_aux)
         torch.sub(self.epot, self.eaux, out=self.uq).abs_()
         hit = (self.uq > self.uq_threshold) & (self.active.reshape(-1) > 0)
         self.stop_step.copy_(torch.where(hit, self.step_no.expand_as(self.stop_step), self.stop_step))
@@ -87,7 +90,7 @@ class BatchedNVE:
         if self.aux is None:
             self.vel.add_(self.grad * self.inv_m, alpha=-0.5 * dt)   # v(t + dt/2) = v - dt/2 * grad/m
             self.xyz.add_(self.vel, alpha=dt)                        # x(t + dt)
-            self.model.predict(self.xyz, True, True, out_e=self.epot, out_g=self.grad)
+            self.model.predict(self.xyz, True, True, out_e=self.epot, out_g=self.grad, ws=self.ws)
             self.vel.add_(self.grad * self.inv_m, alpha=-0.5 * dt)   # v(t + dt)
             self._kinetic()
             return
@@ -95,7 +98,7 @@ class BatchedNVE:
         self.step_no.add_(1)
         self.vel.add_(self.grad * self.inv_m * self.active, alpha=-0.5 * dt)
         self.xyz.add_(self.vel * self.active, alpha=dt)
-        self.model.predict(self.xyz, True, True, out_e=self.epot, out_g=self.grad)
+        self.model.predict(self.xyz, True, True, out_e=self.epot, out_g=self.grad, ws=self.ws)
         self.vel.add_(self.grad * self.inv_m * self.active, alpha=-0.5 * dt)
         self._kinetic()
         self._check_uncertain()

@@ -462,7 +462,8 @@ class _FusedHoldout:
     """Hold-out validation loss as a function of lambda at a fixed sigma, everything resident in HBM: K(sigma) is
     assembled once by ``set_sigma``; ``loss(lambda)`` shifts the diagonal of a copy, factorises it, predicts the
     validation set and returns the reference's loss (RMSE, geometric mean of scalar and vectorial parts,
-    model_cls.py:577-585).  A matrix that is not positive definite at some lambda scores +inf."""
+    model_cls.py:577-585).  A matrix that is not positive definite at some lambda is solved by the Bunch-Kaufman
+    fallback, as the reference does (mathUtils.f90:24-26)."""
 
     def __init__(self, t, eq_xyz, sub_db, val_db, p_learn, g_learn, prior, fixed_lam_g):
         self.p_learn, self.g_learn, self.fixed_lam_g = p_learn, g_learn, fixed_lam_g
@@ -486,11 +487,14 @@ class _FusedHoldout:
         self.work = torch.empty_like(self.k0)
         self.diag = torch.arange(m, device=dev)
         self.sigma = None
+        self.fallbacks = 0  # grid points solved by the symmetric-indefinite route
+        ws_bytes = engine.build_workspace_bytes(nat, ntr, self.ng) if self.xyz.is_cuda else 0
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None  # one scratch for every sigma
 
     def set_sigma(self, sigma):
         self.sigma = float(sigma)
         engine.build_kernel_matrix(self.xyz, self.xeq, self.sigma, 0.0, 0.0, use_values=self.nv > 0,
-                                   use_gradients=self.ng > 0, fill=FILL_LOWER, out=self.k0)
+                                   use_gradients=self.ng > 0, fill=FILL_LOWER, out=self.k0, workspace=self.ws)
 
     def loss(self, lam):
         nv, diag, work = self.nv, self.diag, self.work
@@ -503,7 +507,18 @@ class _FusedHoldout:
         except KregError as err:
             if err.code <= 0:
                 raise
-            return float("inf")  # not positive definite at this (lambda, sigma)
+            # not positive definite at this (lambda, sigma) -- the regime the default lambda = 2^-35 visits: the same
+            # Bunch-Kaufman fallback as KREG_API.train_arrays (mathUtils.f90:24-26), on a fresh copy of K(sigma)
+            work.copy_(self.k0)
+            work[diag[:nv], diag[:nv]] += lam
+            work[diag[nv:], diag[nv:]] += lam_g
+            try:
+                alpha = engine.solve_indefinite(work, self.ytrain)
+            except KregError as err2:
+                if err2.code <= 0:
+                    raise
+                return float("inf")  # exactly singular pivot: no solution to score
+            self.fallbacks += 1
         model = engine.PackedModel.from_training_set(self.xyz, self.xeq, alpha, self.sigma, self.prior_value, nv, self.ng)
         e, g = model.predict(self.xyz_val, self.p_learn is not None, self.g_learn is not None)
         total = 1.0

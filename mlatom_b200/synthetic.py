@@ -69,12 +69,25 @@ def equilibrium(natoms: int) -> np.ndarray:
         return ASPIRIN_EQ[:natoms].copy()
     if 21 < natoms <= 24:
         return np.vstack([ASPIRIN_EQ, EXTRA_EQ[: natoms - 21]])
+    if natoms > 24:
+        return lattice_equilibrium(natoms)
     raise ValueError("no synthetic equilibrium geometry for %d atoms" % natoms)
+
+
+def lattice_equilibrium(natoms: int, spacing: float = 1.5, jitter: float = 0.15) -> np.ndarray:
+    """Molecules above 24 atoms: the first `natoms` sites of a cubic lattice (1.5 Angstrom), each displaced by a fixed
+    pseudo-random vector of at most `jitter` per component -- every pair distance stays above 1.0 Angstrom."""
+    side = int(np.ceil(natoms ** (1.0 / 3.0)))
+    grid = np.array([(i, j, k) for i in range(side) for j in range(side) for k in range(side)], dtype=np.float64)
+    rng = np.random.default_rng(1000 + natoms)
+    return spacing * grid[:natoms] + jitter * (2.0 * rng.random((natoms, 3)) - 1.0)
 
 
 def atomic_numbers(natoms: int) -> np.ndarray:
     if natoms == 9:
         return ETHANOL_Z.copy()
+    if natoms > 24:
+        return np.where(np.arange(natoms) % 3 == 0, 6, 1).astype(ASPIRIN_Z.dtype)
     if natoms > 21:
         return np.concatenate([ASPIRIN_Z, np.ones(natoms - 21, dtype=ASPIRIN_Z.dtype)])
     return ASPIRIN_Z[:natoms].copy()

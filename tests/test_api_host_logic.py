@@ -14,75 +14,12 @@ from mlatom_b200 import data as D, synthetic as S  # noqa: E402
 from mlatom_b200 import kreg_api as KA, models as M  # noqa: E402
 
 
-class FakePacked:
-    def __init__(self, oracle, xyz_tr, xeq, alpha, sigma, prior, nv, ng):
-        self.o, self.sigma, self.prior, self.device = oracle, sigma, prior, torch.device("cpu")
-        self.xeq = xeq.numpy()
-        self.xyz_tr = xyz_tr.numpy()
-        self.X = oracle.descriptors(self.xyz_tr, self.xeq)
-        a = alpha.numpy().reshape(-1)
-        self.av = a[:nv] if nv else None
-        self.v = oracle.precompute_v(self.xyz_tr, self.X, a[nv:]) if ng else None
-
-    def predict(self, xyz, energy=True, gradient=True, **_):
-        x = xyz.numpy()
-        e, g = self.o.predict_factored(self.X, self.av, self.v, self.sigma, self.prior, x, self.o.descriptors(x, self.xeq))
-        return (torch.from_numpy(e) if energy else None), (torch.from_numpy(g) if gradient else None)
-
-    def predict_host(self, xyz, energy=True, gradient=True, **_):
-        return self.predict(torch.from_numpy(np.ascontiguousarray(xyz)), energy, gradient)
+from oracle_engine import FakePacked, install_oracle_engine  # noqa: E402,F401
 
 
 @pytest.fixture
 def fake_engine(monkeypatch, oracle):
-    eng = KA.engine
-    monkeypatch.setattr(KA.KREG_API, "_dev", lambda self: torch.device("cpu"))
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(eng, "xeq", lambda req: torch.from_numpy(oracle.xeq(req.numpy())))
-    monkeypatch.setattr(eng, "descriptors", lambda xyz, xeq: torch.from_numpy(oracle.descriptors(xyz.numpy(), xeq.numpy())))
-
-    def build(xyz, xeq, sigma, lv, lg, use_values=True, use_gradients=False, fill=0, rows=None, out=None):
-        x = xyz.numpy()
-        n, nat, _ = x.shape
-        nv, ng = (n if use_values else 0), (3 * nat * n if use_gradients else 0)
-        k = oracle.kernel_matrix(x, oracle.descriptors(x, xeq.numpy()), sigma, nv, ng, factored=True)
-        k[np.diag_indices_from(k)] += np.r_[np.full(nv, lv), np.full(ng, lg)]
-        k = torch.from_numpy(k)
-        if out is not None:
-            out.copy_(k)
-            return out
-        return k
-
-    def solve(k, y):
-        from scipy.linalg import cho_factor, cho_solve
-
-        a = np.tril(k.numpy())
-        a = a + np.tril(a, -1).T
-        return torch.from_numpy(cho_solve(cho_factor(a), y.numpy()))
-
-    class FakeGraph:
-        def __init__(self, model, n, energy=True, gradient=True):
-            self.model, self.energy, self.gradient = model, energy, gradient
-
-        def __call__(self, xyz):
-            e, g = self.model.predict_host(xyz, self.energy, self.gradient)
-            return (None if e is None else e.numpy()), (None if g is None else g.numpy())
-
-    def hessian(x_train, alpha_val, xeq, sigma, xyz):
-        xte = xyz.numpy()
-        nv = 0 if alpha_val is None else alpha_val.numel()
-        a = np.zeros(0) if alpha_val is None else alpha_val.numpy()
-        return torch.from_numpy(oracle.hessian_kregf90(x_train.numpy(), a, sigma, nv, xte,
-                                                       oracle.descriptors(xte, xeq.numpy())))
-
-    monkeypatch.setattr(eng, "hessian", hessian)
-    monkeypatch.setattr(eng, "GraphPredictor", FakeGraph)
-    monkeypatch.setattr(eng, "build_kernel_matrix", build)
-    monkeypatch.setattr(eng, "solve", solve)
-    monkeypatch.setattr(eng.PackedModel, "from_training_set",
-                        classmethod(lambda cls, xyz, xeq, alpha, sigma, prior, nv, ng, device=None:
-                                    FakePacked(oracle, xyz, xeq, alpha, sigma, prior, nv, ng)))
-    return eng
+    return install_oracle_engine(monkeypatch.setattr, oracle)
 
 
 def make_db(mod, nat, n, seed, with_labels=True):
