@@ -43,7 +43,11 @@ extern "C" {
 #define KREG_E_CUDA (-4)        /* a CUDA runtime / cuSOLVER call failed (see kreg_last_error) */
 
 #define KREG_MIN_NATOMS 2
-#define KREG_MAX_NATOMS 24 /* largest molecule whose accumulators + test tile fit one SM (D = 276) */
+#define KREG_MAX_NATOMS 64 /* D = 2016.  The reference has no limit (Natoms is a run-time argument everywhere); this
+                              one is where the shared-memory plans of the gradient blocks end, not an algorithmic one */
+#define KREG_FUSED_MAX_NATOMS 24 /* up to here prediction keeps a test row's D + 1 accumulators in one warp's registers
+                                    (one fused kernel); larger molecules take the tiled three-kernel path, which needs
+                                    the scratch kreg_predict_workspace_bytes reports for EVERY batch size */
 
 /* kreg_build_kernel_matrix `fill` argument: which part of the symmetric K is written */
 #define KREG_FILL_LOWER 0 /* K[i][j], j <= i (row-major lower == column-major upper, potrf 'U') */

@@ -30,6 +30,18 @@ __host__ __device__ constexpr int pair_index(int nat, int a, int b) {  // requir
   return (2 * nat - a - 1) * a / 2 + (b - a) - 1;
 }
 
+// inverse of pair_index: descriptor element d -> atoms a < b (closed form + integer fix-up; no table, any Natoms)
+__host__ __device__ inline void pair_from_index(int nat, int d, int &a, int &b) {
+  const double t = 2.0 * nat - 1.0;
+  int aa = (int)((t - sqrt(t * t - 8.0 * d)) * 0.5);
+  if (aa < 0) aa = 0;
+  if (aa > nat - 2) aa = nat - 2;
+  while (aa > 0 && (2 * nat - aa - 1) * aa / 2 > d) aa--;
+  while (aa < nat - 2 && (2 * nat - aa - 2) * (aa + 1) / 2 <= d) aa++;
+  a = aa;
+  b = d - (2 * nat - aa - 1) * aa / 2 + aa + 1;
+}
+
 // Squared distance exactly as the reference's Rij (KREG.f90:84): (dx^2 + dy^2) + dz^2 with every
 // operation individually rounded (no FMA contraction), so descriptors are bit-identical.
 __device__ __forceinline__ double rij2_exact(const double *pa, const double *pb) {

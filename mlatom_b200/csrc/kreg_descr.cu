@@ -5,12 +5,6 @@
 
 namespace kreg {
 
-// d -> (a, b) lookup built in shared memory (inverse of KREG.f90:48)
-__device__ __forceinline__ void build_pair_table(int nat, unsigned short *tab) {
-  for (int a = threadIdx.x; a < nat; a += blockDim.x)
-    for (int b = a + 1; b < nat; b++) tab[pair_index(nat, a, b)] = (unsigned short)(a | (b << 8));
-}
-
 __global__ void xeq_kernel(int nat, const double *__restrict__ req, double *__restrict__ xeq) {
   for (int a = threadIdx.x; a < nat; a += blockDim.x)
     for (int b = a + 1; b < nat; b++) xeq[pair_index(nat, a, b)] = sqrt(rij2_exact(req + 3 * a, req + 3 * b));
@@ -24,15 +18,13 @@ __global__ void __launch_bounds__(256) descriptors_kernel(int nat, int64_t npoin
                                                           const double *__restrict__ xeq,
                                                           const double *__restrict__ center,
                                                           double *__restrict__ X) {
-  __shared__ unsigned short tab[descr_size(KREG_MAX_NATOMS)];
-  build_pair_table(nat, tab);
-  __syncthreads();
   const int D = descr_size(nat);
   const int64_t total = npoints * D;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = e / D;
     int d = (int)(e - p * D);
-    int a = tab[d] & 0xff, b = tab[d] >> 8;
+    int a, b;
+    pair_from_index(nat, d, a, b);  // inverse of KREG.f90:48
     const double *m = xyz + p * nat * 3;
     double x = xeq[d] / sqrt(rij2_exact(m + 3 * a, m + 3 * b));
     if (MODE == 1) x -= center[d];
@@ -49,10 +41,8 @@ __global__ void __launch_bounds__(256) descriptor_mean_kernel(int nat, int64_t n
                                                               double *__restrict__ center) {
   __shared__ double red[256];
   const int d = blockIdx.x;
-  int a = 0, b = 0;
-  for (int aa = 0; aa < nat; aa++)
-    for (int bb = aa + 1; bb < nat; bb++)
-      if (pair_index(nat, aa, bb) == d) { a = aa; b = bb; }
+  int a, b;
+  pair_from_index(nat, d, a, b);
   if (npoints > 2048) npoints = 2048;
   double s = 0.0;
   for (int64_t p = threadIdx.x; p < npoints; p += 256) {

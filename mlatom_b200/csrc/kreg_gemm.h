@@ -1,0 +1,60 @@
+// kreg_gemm.h -- argument block and entry points of the DMMA tile kernel (values_ring_kernel, kreg_kbuild.cu) shared by
+// the kernel-matrix assembly and the large-molecule prediction path (kreg_predict_big.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kreg {
+
+struct ValuesArgs {
+  const double *XA;  // [na][XS] centred descriptors, zero padded
+  const double *XB;  // [nb][XS]
+  const double *XAch;  // multi-chunk descriptors only: [nchunks][na][XSC] chunk-major copy (contiguous chunk tiles)
+  const double *XBch;  // [nchunks][nb][XSC]
+  int XSC;             // row stride of the chunk-major copies = the kernel's conflict-free chunk stride
+  const double *biasA;  // row term, already scaled: -c1 n_i / 2 (EPI_LIN: unused)
+  const double *biasB;  // column term in units of S: -n_j / 2 (EPI_LIN: any additive column term); it is the initial value
+                        // of the GEMM accumulators, so the epilogue needs no per-element add
+  int64_t na, nb;
+  int64_t strideA, strideB;  // rows per chunk of the chunk-major copies (na / nb unless an operand is a row sub-range)
+  int XS;       // row stride (doubles), >= 4*KC*nchunks, = 4 mod 8
+  int nchunks;  // K-chunks of 4*KC descriptor elements
+  double c1;
+  double lambda;  // added where i == j when `symmetric`
+  int symmetric;  // 1: XA == XB (K build): exact 1+lambda on the diagonal, tiles above the diagonal skipped unless `all_cols`
+  int all_cols;   // 1: compute every column tile directly (row-slab FULL mode / rectangular block)
+  int mirror;     // 1: also write K[j][i] for tiles strictly below the diagonal blocks (whole-matrix FULL mode)
+  int64_t row_begin, row_end;  // rows of A to produce
+  double *K;
+  int64_t ldk;
+  int njt;  // column tiles walked by one CTA (set by the launcher)
+  // EPI_W (prediction of large molecules, kreg_predict_big.cu): w_ij = k_ij * colscale[j] (value models) or
+  // k_ij * Cin[i][j] (gradient models, which also keep k_ij), written chunk-major as the A operand of the second GEMM
+  const double *colscale;
+  const double *Cin;
+  int64_t ldc;
+  double *Wch, *Kfch;  // [nchunks_w][na][wkc]
+  int wkc;             // columns per output chunk (the second GEMM's K chunk)
+};
+
+constexpr int kGemmKC = 9;  // k-steps per chunk of the GEMM modes (chunk width 36 doubles, conflict-free stride 36)
+
+// epilogue modes of values_ring_kernel
+constexpr int EPI_K = 0;    // K-matrix / validation block: exp, diagonal, mirror
+constexpr int EPI_W = 1;    // prediction GEMM1: exp * column scale -> chunk-major W
+constexpr int EPI_WV = 2;   // prediction GEMM1, gradient models: exp * Cin -> chunk-major W and K
+constexpr int EPI_LIN = 3;  // plain GEMM: C = A B^T + column term (row-major)
+
+// kreg_kbuild.cu
+int launch_gemm_epi(const ValuesArgs &a, int epi, cudaStream_t st);
+// centred, zero-padded descriptor rows Xc[n][XS] of the geometries xyz[n][nat][3]; bias[p] = -c1 |Xc_p|^2 / 2 and
+// (optionally) bias_col[p] = -|Xc_p|^2 / 2
+int launch_prep_rows(int nat, int64_t n, const double *xyz, const double *xeq, const double *center, int XS, double c1,
+                     double *Xc, double *bias, double *bias_col, cudaStream_t st);
+// the two bias arrays alone, for rows Xc that are already in place
+int launch_prep_bias(int nat, int64_t n, int XS, double c1, const double *Xc, double *bias, double *bias_col,
+                     cudaStream_t st);
+// chunk-major copy Xch[ch][p][XSC] = Xc[p][ch * 4 KC + (0 .. 4 KC)), zero padded
+int launch_chunk_rows(int64_t n, int XS, int KC, int nchunks, int XSC, const double *Xc, double *Xch, cudaStream_t st);
+
+}  // namespace kreg

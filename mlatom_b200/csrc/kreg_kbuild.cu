@@ -12,6 +12,7 @@
 // bracket is the O(D) expansion of the reference's (Nat-1)^2-term double loop.
 #include "kreg_common.cuh"
 #include "kreg_internal.h"
+#include "kreg_gemm.h"
 
 namespace kreg {
 
@@ -21,33 +22,25 @@ namespace kreg {
 constexpr int kTileI = 128;  // rows per CTA tile
 constexpr int kTileJ = 64;   // columns per CTA tile
 
-struct ValuesArgs {
-  const double *XA;  // [na][XS] centred descriptors, zero padded
-  const double *XB;  // [nb][XS]
-  const double *XAch;  // multi-chunk descriptors only: [nchunks][na][XSC] chunk-major copy (contiguous chunk tiles)
-  const double *XBch;  // [nchunks][nb][XSC]
-  int XSC;             // row stride of the chunk-major copies = the kernel's conflict-free chunk stride
-  const double *biasA;  // -c1 n_i / 2
-  const double *biasB;
-  int64_t na, nb;
-  int XS;       // row stride (doubles), >= 4*KC*nchunks, = 4 mod 8
-  int nchunks;  // K-chunks of 4*KC descriptor elements
-  double c1;
-  double lambda;  // added where i == j when `symmetric`
-  int symmetric;  // 1: XA == XB (K build): exact 1+lambda on the diagonal, tiles above the diagonal skipped unless `all_cols`
-  int all_cols;   // 1: compute every column tile directly (row-slab FULL mode / rectangular block)
-  int mirror;     // 1: also write K[j][i] for tiles strictly below the diagonal blocks (whole-matrix FULL mode)
-  int64_t row_begin, row_end;  // rows of A to produce
-  double *K;
-  int64_t ldk;
-  int njt;  // column tiles walked by one CTA (set by the launcher)
-};
 
 
-// Epilogue of one 128 x 64 tile, shared by both values kernels: k = exp(c1 (s - n_i/2 - n_j/2)), diagonal exactly
-// 1 + lambda, 16-byte stores (64 B runs per row); the accumulators are cleared for the next tile.
+// The exponent c1 (X'_i.X'_j - n_i/2 - n_j/2) = -c1 |X_i - X_j|^2 / 2 is <= 0 up to rounding (a few ulp of c1 n);
+// a positive rounding residue only makes k = 1 + O(1e-16), far inside the 1e-13 parity tolerance, so no clamp is
+// needed (one FP64-pipe instruction per element saved; -DKREG_VALUES_CLAMP=1 restores it).
+#ifndef KREG_VALUES_CLAMP
+#define KREG_VALUES_CLAMP 0
+#endif
+#if KREG_VALUES_CLAMP
+#define KREG_EXP_ARG(x) fmin((x), 0.0)
+#else
+#define KREG_EXP_ARG(x) (x)
+#endif
+
+// Epilogue of one 128 x 64 tile, shared by both values kernels: k = exp(c1 s + b_i) where the accumulator s already
+// holds X'_i.X'_j - n_j/2 (it was initialised with the column term), diagonal exactly 1 + lambda, 16-byte stores (64 B
+// runs per row).
 __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
-                                                     const double *bA, const double *bB, const double *tab, int wi,
+                                                     const double *bA, const double *tab, int wi,
                                                      int wj, int g, int q, bool lower_only) {
   const bool diag_tile = a.symmetric && j0 + kTileJ - 1 >= i0;  // touches the diagonal block: computed directly
   // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
@@ -61,10 +54,8 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
         const int cj = wj * 32 + nt * 8 + 2 * q;
-        const double2 bj = *reinterpret_cast<const double2 *>(bB + cj);
-        const double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bj.x), 0.0), tab);
-        const double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bj.y), 0.0), tab);
-        S[mt][nt][0] = S[mt][nt][1] = 0.0;
+        const double k0 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][0], a.c1, bi)), tab);
+        const double k1 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][1], a.c1, bi)), tab);
         *reinterpret_cast<double2 *>(row + nt * 8) = make_double2(k0, k1);
         if (a.mirror) {
           double *t = a.K + (j0 + cj) * a.ldk + i0 + wi * 32 + mt * 8 + g;
@@ -86,9 +77,8 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
     for (int nt = 0; nt < 4; nt++) {
       const int cj = wj * 32 + nt * 8 + 2 * q;
       const int64_t j = j0 + cj;
-      double k0 = exp_from_scaled(fmin(fma(S[mt][nt][0], a.c1, bi + bB[cj]), 0.0), tab);
-      double k1 = exp_from_scaled(fmin(fma(S[mt][nt][1], a.c1, bi + bB[cj + 1]), 0.0), tab);
-      S[mt][nt][0] = S[mt][nt][1] = 0.0;
+      double k0 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][0], a.c1, bi)), tab);
+      double k1 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][1], a.c1, bi)), tab);
       if (a.symmetric) {
         if (i == j) k0 = 1.0 + a.lambda;
         if (i == j + 1) k1 = 1.0 + a.lambda;
@@ -112,6 +102,65 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
   }
 }
 
+// Prediction GEMM1 epilogue (large molecules): w_ij = k_ij * colscale[j] (EPI_W) or k_ij * Cin[i][j] (EPI_WV, which
+// also keeps k_ij), stored chunk-major -- [j / wkc][i][j % wkc] -- which is the layout the second GEMM streams its A
+// operand in.  j is even and wkc is even, so a (j, j+1) pair never straddles a chunk and every store is 16 bytes.
+template <int EPI>
+__device__ __forceinline__ void w_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
+                                                const double *bA, const double *tab, int wi, int wj, int g, int q) {
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int ri = wi * 32 + mt * 8 + g;
+    const int64_t i = i0 + ri;
+    const bool row_ok = i < a.na;
+    const double bi = bA[ri];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
+      if (!row_ok || j >= a.nb) continue;
+      double k0 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][0], a.c1, bi)), tab);
+      double k1 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][1], a.c1, bi)), tab);
+      const bool has1 = j + 1 < a.nb;
+      if (!has1) k1 = 0.0;  // padding column of the last chunk: must be an exact zero for the second GEMM
+      double w0, w1;
+      if (EPI == EPI_WV) {
+        const double *c = a.Cin + i * a.ldc + j;
+        w0 = k0 * c[0];
+        w1 = has1 ? k1 * c[1] : 0.0;
+      } else {
+        w0 = k0 * __ldg(a.colscale + j);
+        w1 = has1 ? k1 * __ldg(a.colscale + j + 1) : 0.0;
+      }
+      const int64_t ch = j / a.wkc;
+      const int64_t off = (ch * a.na + i) * a.wkc + (j - ch * a.wkc);
+      *reinterpret_cast<double2 *>(a.Wch + off) = make_double2(w0, w1);
+      if (EPI == EPI_WV) *reinterpret_cast<double2 *>(a.Kfch + off) = make_double2(k0, k1);
+    }
+  }
+}
+
+// Plain GEMM epilogue: C[i][j] = accumulator (A_i . B_j + column term), row-major.
+__device__ __forceinline__ void lin_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
+                                                  int wi, int wj, int g, int q) {
+  const bool vec = (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int64_t i = i0 + wi * 32 + mt * 8 + g;
+    if (i >= a.na) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
+      double *dst = a.K + i * a.ldk + j;
+      if (vec && j + 1 < a.nb) {
+        *reinterpret_cast<double2 *>(dst) = make_double2(S[mt][nt][0], S[mt][nt][1]);
+      } else {
+        if (j < a.nb) dst[0] = S[mt][nt][0];
+        if (j + 1 < a.nb) dst[1] = S[mt][nt][1];
+      }
+    }
+  }
+}
+
 // The values block: CTA tile 128 x 64, 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 32 = 4 x 4 DMMA tiles, <= 128
 // registers so two CTAs share an SM.  A CTA walks `njt` consecutive column tiles; operands arrive through a ring of TMA
 // bulk copies with full/empty mbarriers, like the prediction kernel's model stream, so there is no CTA-wide barrier in
@@ -122,7 +171,7 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
 //   MULTI = true: the descriptor is walked in chunks of KC k-steps; a stage = the A chunk and the B chunk of one
 //           (tile, chunk) step, both contiguous in the chunk-major copy of the workspace; column biases travel with chunk 0
 //           into a slot selected by tile parity.
-template <int KC, bool MULTI>
+template <int KC, bool MULTI, int EPI = EPI_K>
 __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
   constexpr int A_DBL = kTileI * XSP, B_DBL = kTileJ * XSP;
@@ -181,8 +230,8 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
     double *st = ring + s * STAGE;
     if (MULTI) {
       mbar_arrive_expect_tx(&full[s], ba + bx + (ch == 0 ? bb : 0u));
-      bulk_g2s(st, a.XAch + ((int64_t)ch * a.na + i0) * XSP, ba, &full[s]);
-      bulk_g2s(st + A_DBL, a.XBch + ((int64_t)ch * a.nb + j0) * XSP, bx, &full[s]);
+      bulk_g2s(st, a.XAch + ((int64_t)ch * a.strideA + i0) * XSP, ba, &full[s]);
+      bulk_g2s(st + A_DBL, a.XBch + ((int64_t)ch * a.strideB + j0) * XSP, bx, &full[s]);
       if (ch == 0) bulk_g2s(bBs + (tile & 1) * kTileJ, a.biasB + j0, bb, &full[s]);
     } else {
       mbar_arrive_expect_tx(&full[s], bx + bb);
@@ -199,12 +248,30 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
   }
 
   double S[4][4][2];
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
   const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
   mbar_wait(fullA, 0);
+
+  // accumulators start from the column term of their tile (-n_j/2; an arbitrary additive term for EPI_LIN), which
+  // arrived with the tile's first stage: the epilogue then has no per-element bias add
+  auto init_acc = [&](const double *bcol) {
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const double2 b = *reinterpret_cast<const double2 *>(bcol + wj * 32 + nt * 8 + 2 * q);
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) {
+        S[mt][nt][0] = b.x;
+        S[mt][nt][1] = b.y;
+      }
+    }
+  };
+  auto epilogue = [&](int64_t j0) {
+    if (EPI == EPI_K)
+      values_tile_epilogue(a, S, i0, j0, bA, tab, wi, wj, g, q, lower_only);
+    else if (EPI == EPI_LIN)
+      lin_tile_epilogue(a, S, i0, j0, wi, wj, g, q);
+    else
+      w_tile_epilogue<EPI>(a, S, i0, j0, bA, tab, wi, wj, g, q);
+  };
 
   for (int step = 0; step < nsteps; step++) {
     // producer duty: refill the slot every warp left in the previous iteration
@@ -216,6 +283,12 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
     mbar_wait(&full[s], (step / NST) & 1);
     const double *At = MULTI ? ring + s * STAGE : As;
     const double *Bt = ring + s * STAGE + (MULTI ? A_DBL : 0);
+    if (MULTI) {
+      const int tile = step / nch;
+      if (step - tile * nch == 0) init_acc(bBs + (tile & 1) * kTileJ);
+    } else {
+      init_acc(bBs + s * kTileJ);
+    }
 #pragma unroll
     for (int ks = 0; ks < KC; ks++) {
       double af[4], bf[4];
@@ -234,10 +307,9 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
       const int tile = step / nch;
-      if (step - tile * nch == nch - 1)
-        values_tile_epilogue(a, S, i0, (tj_lo + tile) * kTileJ, bA, bBs + (tile & 1) * kTileJ, tab, wi, wj, g, q, lower_only);
+      if (step - tile * nch == nch - 1) epilogue((tj_lo + tile) * kTileJ);
     } else {
-      values_tile_epilogue(a, S, i0, (tj_lo + step) * kTileJ, bA, bBs + s * kTileJ, tab, wi, wj, g, q, lower_only);
+      epilogue((tj_lo + step) * kTileJ);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the slot (tile and biases)
     }
@@ -258,10 +330,17 @@ __global__ void __launch_bounds__(256) chunk_rows_kernel(int64_t n, int XS, int 
   }
 }
 
-template <int KC>
+int launch_chunk_rows(int64_t n, int XS, int KC, int nchunks, int XSC, const double *Xc, double *Xch, cudaStream_t st) {
+  if (n <= 0) return KREG_OK;
+  chunk_rows_kernel<<<1184, 256, 0, st>>>(n, XS, KC, nchunks, XSC, Xc, Xch);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
+template <int KC, int EPI = EPI_K>
 static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
-  const bool multi = a.nchunks > 1;
+  const bool multi = a.nchunks > 1 || EPI != EPI_K;  // the GEMM modes always stream chunk-major operands
   if (multi ? (a.XSC != XSP || !a.XAch || !a.XBch) : (a.XS != XSP)) return KREG_E_BADARG;  // workspace layout contract
   const int64_t r1 = a.row_end < a.na ? a.row_end : a.na;
   if (r1 <= a.row_begin) return KREG_OK;
@@ -271,23 +350,40 @@ static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
 #ifdef KREG_NJT_OVERRIDE
   a.njt = KREG_NJT_OVERRIDE;
 #else
-  a.njt = tiles > 200000 ? 16 : tiles > 50000 ? 8 : tiles > 1000 ? 4 : 2;  // measured: 10k rows 4 (0.25 vs 0.27 ms), 50k flat
+  if (a.njt <= 0)
+    a.njt = tiles > 200000 ? 16 : tiles > 50000 ? 8 : tiles > 1000 ? 4 : 2;  // measured: 10k rows 4 (0.25 vs 0.27 ms), 50k flat
 #endif
   dim3 grid((unsigned)((ntj + a.njt - 1) / a.njt), (unsigned)(ti1 - ti0 + 1));
   if (multi) {
     const size_t smem = (size_t)(2 * (kTileI + kTileJ) * XSP + 2 * kTileJ + kTileI + 64 + 2 * 2 + 2) * sizeof(double);
-    auto kern = values_ring_kernel<KC, true>;
+    auto kern = values_ring_kernel<KC, true, EPI>;
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(a);
-  } else {
+  } else if constexpr (EPI == EPI_K) {
     constexpr int NST = KC <= 9 ? 3 : 2;
     const size_t smem = (size_t)(kTileI * XSP + NST * kTileJ * XSP + NST * kTileJ + kTileI + 64 + 2 * NST + 2) * sizeof(double);
-    auto kern = values_ring_kernel<KC, false>;
+    auto kern = values_ring_kernel<KC, false, EPI_K>;
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, st>>>(a);
   }
   KREG_LAUNCH_CHECK();
   return KREG_OK;
+}
+
+// The GEMM modes used by the large-molecule prediction path (kreg_predict_big.cu): always chunks of kGemmKC k-steps.
+int launch_gemm_epi(const ValuesArgs &a, int epi, cudaStream_t st) {
+  switch (epi) {
+    case EPI_W:
+      return launch_values_kc<kGemmKC, EPI_W>(a, st);
+    case EPI_WV:
+      return launch_values_kc<kGemmKC, EPI_WV>(a, st);
+    case EPI_LIN:
+      return launch_values_kc<kGemmKC, EPI_LIN>(a, st);
+    case EPI_K:
+      return launch_values_kc<kGemmKC, EPI_K>(a, st);
+    default:
+      return KREG_E_BADARG;
+  }
 }
 
 // k-steps per staged chunk: one chunk up to 12; longer descriptors in chunks of at most 9, the largest whose
@@ -303,6 +399,9 @@ static void chunking(int KS, int *KC, int *nchunks) {
 }
 
 static int launch_values(ValuesArgs a, int KC, cudaStream_t st) {
+  a.njt = 0;
+  a.strideA = a.na;
+  a.strideB = a.nb;
   switch (KC) {
 #define KREG_KC(N) \
   case N:          \
@@ -329,12 +428,8 @@ __global__ void __launch_bounds__(256) prep_descr_kernel(int nat, int64_t n, con
     const int d = (int)(e - p * XS);
     double v = 0.0;  // padding columns
     if (d < D) {
-      int rem = d, a = 0;
-      while (rem >= nat - 1 - a) {
-        rem -= nat - 1 - a;
-        a++;
-      }
-      const int b = a + 1 + rem;
+      int a, b;
+      pair_from_index(nat, d, a, b);
       const double *m = xyz + p * nat * 3;
       v = xeq[d] / sqrt(rij2_exact(m + 3 * a, m + 3 * b)) - center[d];
     }
@@ -342,26 +437,37 @@ __global__ void __launch_bounds__(256) prep_descr_kernel(int nat, int64_t n, con
   }
 }
 
-// Row biases -c1 |x|^2 / 2, summed in descriptor order (one thread per geometry; the sum is a short FMA chain).
+// Row terms -c1 |x|^2 / 2 (scaled exponent units) and column terms -|x|^2 / 2 (units of S), summed in descriptor
+// order (one thread per geometry; the sum is a short FMA chain).
 __global__ void __launch_bounds__(256) prep_bias_kernel(int nat, int64_t n, int XS, double c1,
-                                                        const double *__restrict__ Xc, double *__restrict__ bias) {
+                                                        const double *__restrict__ Xc, double *__restrict__ bias,
+                                                        double *__restrict__ bias_col) {
   const int D = descr_size(nat);
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     const double *x = Xc + p * XS;
     double nn = 0.0;
     for (int d = 0; d < D; d++) nn = fma(x[d], x[d], nn);
     bias[p] = -0.5 * c1 * nn;
+    if (bias_col) bias_col[p] = -0.5 * nn;
   }
 }
 
-static int launch_prep_rows(int nat, int64_t n, const double *xyz, const double *xeq, const double *center, int XS,
-                            double c1, double *Xc, double *bias, cudaStream_t st) {
+int launch_prep_bias(int nat, int64_t n, int XS, double c1, const double *Xc, double *bias, double *bias_col,
+                     cudaStream_t st) {
+  if (n <= 0) return KREG_OK;
+  prep_bias_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(nat, n, XS, c1, Xc, bias, bias_col);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
+int launch_prep_rows(int nat, int64_t n, const double *xyz, const double *xeq, const double *center, int XS,
+                     double c1, double *Xc, double *bias, double *bias_col, cudaStream_t st) {
   if (n <= 0) return KREG_OK;
   const int64_t total = n * XS;
   const int blocks = (int)(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
   prep_descr_kernel<<<blocks, 256, 0, st>>>(nat, n, xyz, xeq, center, XS, Xc);
   KREG_LAUNCH_CHECK();
-  prep_bias_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(nat, n, XS, c1, Xc, bias);
+  prep_bias_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(nat, n, XS, c1, Xc, bias, bias_col);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
@@ -816,10 +922,346 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
   }
 }
 
+// =================================================================================================
+// Run-time-Natoms versions of the two gradient-block kernels: any molecule size (the reference takes Natoms as a
+// run-time argument, KREG.f90:293-346), and no per-thread register arrays -- every operand is read from shared memory,
+// so the kernels stay at a few dozen registers and several CTAs share an SM (the templated emit kernel keeps E_i(b, .)
+// in 6 Nat registers per thread: 255 registers and spills from 11 atoms up).
+// =================================================================================================
+
+// Pair terms, cooperative: CTA = (geometry i, JT geometries j), 256 threads.
+//   shared: E_i [Nat][Nat][3] | X_i [D] | D_j = X_j - X_i [JT][DP] (DP odd: conflict-free columns) | Us [JT][PWS] | exp table
+__global__ void __launch_bounds__(256) pair_terms_rt_kernel(const GradArgs a, int nat, int JT) {
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, PWS = PW | 1, DP = D | 1, XS = a.XS;
+  extern __shared__ __align__(16) double rsm[];
+  double *Ei = rsm;                  // [ES]
+  double *Xi = Ei + a.ES;            // [D (+1)]
+  double *Dl = Xi + ((D + 1) & ~1);  // [JT][DP]
+  double *Us = Dl + (((size_t)JT * DP + 1) & ~(size_t)1);  // [JT][PWS]
+  double *tab = Us + (((size_t)JT * PWS + 1) & ~(size_t)1);
+
+  const int64_t i = blockIdx.y;
+  const int64_t rbase = a.nv + i * G3;
+  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t jend = (a.nv || full) ? a.ntr : i + 1;  // value-gradient rows need every j
+  const int64_t j0 = (int64_t)blockIdx.x * JT;
+  if (j0 >= jend) return;
+  const int nj = (int)(jend - j0 < JT ? jend - j0 : JT);
+  const int tid = threadIdx.x;
+
+  fill_exp_table(tab, tid, 256);
+  for (int e = tid; e < a.ES; e += 256) Ei[e] = a.E[i * a.ES + e];
+  for (int e = tid; e < D; e += 256) Xi[e] = a.Xc[i * XS + e];
+  __syncthreads();
+  for (int e = tid; e < nj * D; e += 256) {  // consecutive threads -> consecutive d: coalesced rows
+    const int jj = e / D, d = e - jj * D;
+    Dl[jj * DP + d] = a.Xc[(j0 + jj) * XS + d] - Xi[d];
+  }
+  __syncthreads();
+  for (int base = 0; base < nj; base += 64) {  // k_ij / s^2: four lanes per pair, in the order the templated kernel sums
+    const int jj = base + (tid >> 2), sub = tid & 3;
+    const double *dd = Dl + (jj < nj ? jj : 0) * DP;
+    double d2 = 0.0;
+    for (int d = sub; d < D; d += 4) d2 = fma(dd[d], dd[d], d2);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
+    if (sub == 0 && jj < nj) {
+      const double k = (j0 + jj == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
+      Us[jj * PWS] = k * a.inv_s2;
+      Us[jj * PWS + 1] = 0.0;
+    }
+  }
+  // u_i^(j)[(a,t)] = sum_c E_i(a,c)[t] D_j[d_ac]: item = (atom a, geometry j), consecutive threads -> consecutive j
+  for (int e = tid; e < nat * JT; e += 256) {
+    const int aa = e / JT, jj = e - aa * JT;
+    if (jj >= nj) continue;
+    const double *dd = Dl + jj * DP;
+    const double *ea = Ei + aa * G3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < nat; c++) {
+      if (c == aa) continue;
+      const double dl = dd[pair_index(nat, aa < c ? aa : c, aa < c ? c : aa)];
+      s0 = fma(ea[c * 3 + 0], dl, s0);
+      s1 = fma(ea[c * 3 + 1], dl, s1);
+      s2 = fma(ea[c * 3 + 2], dl, s2);
+    }
+    double *out = Us + jj * PWS + 2 + aa * 3;
+    out[0] = s0;
+    out[1] = s1;
+    out[2] = s2;
+  }
+  __syncthreads();
+  if ((G3 + 2) < PW)  // the pad element of a pair's record
+    for (int jj = tid; jj < nj; jj += 256) Us[jj * PWS + PW - 1] = 0.0;
+  __syncthreads();
+  double *P = a.P + ((i - a.p_i0) * a.ntr + j0) * PW;
+  {
+    const int64_t jgg = full ? a.ntr : i + 1;
+    const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
+    for (int e = tid; e < np * PW; e += 256) P[e] = Us[(e / PW) * PWS + e % PW];
+  }
+  if (a.nv) {
+    for (int e = tid; e < G3 * JT; e += 256) {
+      const int q = e / JT, jj = e - q * JT;
+      const int64_t row = rbase + q;
+      if (jj < nj && row >= a.row_begin && row < a.row_end) {
+        const double v = Us[jj * PWS] * Us[jj * PWS + 2 + q];
+        a.K[row * a.ldk + j0 + jj] = v;
+        if (full) a.K[(j0 + jj) * a.ldk + row] = v;
+      }
+    }
+  }
+}
+
+// Emit: CTA = ONE geometry i x up to NJB steps of TJ geometries j; a thread owns NV (1 or 2) adjacent matrix columns
+// of the step and walks the 3 Nat rows of geometry i.  NV = 2 stores 16 bytes per lane (profiles/r01_store_pattern.txt:
+// 7.0-7.2 TB/s against 5.3-6.2 for 8-byte lanes); the pairing is taken relative to the ABSOLUTE column parity so that
+// every 16-byte store is aligned whatever NtrVal is.  Per step the pair terms, X_j rows and E_j blocks of the TJ
+// geometries arrive as three TMA bulk copies (NBUF = 2: into the other buffer while this step's stores are issued).
+// By antisymmetry E(b,c)[u] = -E(c,b)[u], the value a column (j,b,u) needs for row atom c is E_j[c][b][u]: for a fixed c
+// consecutive columns read consecutive doubles (conflict-free), and likewise E_i[c][b][t] on the row side.
+template <int NV>
+__global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int nat, int TJ, int NJB, int NBUF) {
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, EJ = a.ES, XS = a.XS;
+  extern __shared__ __align__(128) double esm[];
+  double *Pb = esm;                                 // [NBUF][TJ*PW]
+  double *Xj = Pb + (size_t)NBUF * TJ * PW;         // [NBUF][TJ*XS]
+  double *Ejs = Xj + (size_t)NBUF * TJ * XS;        // [NBUF][TJ*EJ]
+  double *Xi = Ejs + (size_t)NBUF * TJ * EJ;        // [XS]
+  double *Ei = Xi + XS;                             // [EJ]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(Ei + EJ);  // [2]
+
+  const int64_t i = blockIdx.y;
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t jend = full ? a.ntr : i + 1;
+  const int64_t jb0 = (int64_t)blockIdx.x * ((int64_t)NJB * TJ);
+  if (jb0 >= jend) return;
+  const int64_t rbase = a.nv + i * G3;
+  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
+  const int nsteps = (int)(((jend - jb0 < (int64_t)NJB * TJ ? jend - jb0 : (int64_t)NJB * TJ) + TJ - 1) / TJ);
+
+  const int tid = threadIdx.x;
+  const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
+  const int64_t ld = a.ldk;
+  const int cols = TJ * G3;
+  // NV = 2: columns are paired on the absolute column parity (jb * G3 is even because TJ is even)
+  const int par = NV == 2 ? (int)(a.nv & 1) : 0;
+  int rr[NV], jl[NV], cc[NV], bb[NV];
+  bool okc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    const int r = tid * NV + v - par;
+    okc[v] = r >= 0 && r < cols;
+    rr[v] = okc[v] ? r : 0;
+    jl[v] = rr[v] / G3;
+    cc[v] = rr[v] - jl[v] * G3;
+    bb[v] = cc[v] / 3;
+  }
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  for (int e = tid; e < D; e += blockDim.x) Xi[e] = a.Xc[i * XS + e];
+  for (int e = tid; e < EJ; e += blockDim.x) Ei[e] = a.E[i * a.ES + e];
+  __syncthreads();
+
+  auto prefetch = [&](int n) {  // thread 0 only
+    const int64_t jb = jb0 + (int64_t)n * TJ;
+    const unsigned npair = (unsigned)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
+    const int buf = NBUF == 2 ? (n & 1) : 0;
+    const unsigned bp = npair * PW * 8, bx = npair * (unsigned)XS * 8, be = npair * (unsigned)EJ * 8;
+    mbar_arrive_expect_tx(&bar[buf], bp + bx + be);
+    bulk_g2s(Pb + (size_t)buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
+    bulk_g2s(Xj + (size_t)buf * TJ * XS, a.Xc + jb * XS, bx, &bar[buf]);
+    bulk_g2s(Ejs + (size_t)buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
+  };
+  if (tid == 0) prefetch(0);
+
+  for (int n = 0; n < nsteps; n++) {
+    __syncthreads();  // NBUF = 2: everyone left buffer (n+1)&1 (read during step n-1); NBUF = 1: everyone left the buffer
+    if (NBUF == 2) {
+      if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    } else if (tid == 0 && n > 0) {
+      prefetch(n);
+    }
+    const int buf = NBUF == 2 ? (n & 1) : 0;
+    mbar_wait(&bar[buf], NBUF == 2 ? ((n >> 1) & 1) : (n & 1));
+    const int64_t jb = jb0 + (int64_t)n * TJ;
+    const double *pbuf = Pb + (size_t)buf * TJ * PW;
+    const double *xbuf = Xj + (size_t)buf * TJ * XS;
+    const double *ebuf = Ejs + (size_t)buf * TJ * EJ;
+
+    double kj[NV], c2[NV], kjd[NV][3];
+    bool work[NV];
+    const double *pb[NV], *ej[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int64_t j = jb + jl[v];
+      work[v] = okc[v] && j < jend;
+      pb[v] = pbuf + jl[v] * PW;
+      ej[v] = ebuf + (size_t)jl[v] * EJ + cc[v];  // E_j[c][b][u] at ej[c * G3]  (= -E_j(b,c)[u])
+      kj[v] = pb[v][0];
+      const double *xj = xbuf + jl[v] * XS;
+      const double *ei = Ei + 3 * bb[v];          // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
+      const int b = bb[v];
+      double sj = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      if (work[v]) {
+        for (int c = 0; c < nat; c++) {
+          const double nej = ej[v][c * G3];
+          if (c != b) {
+            const int d = pair_index(nat, b < c ? b : c, b < c ? c : b);
+            sj = fma(nej, xj[d] - Xi[d], sj);
+          }
+          a0 = fma(-ei[c * G3 + 0], nej, a0);
+          a1 = fma(-ei[c * G3 + 1], nej, a1);
+          a2 = fma(-ei[c * G3 + 2], nej, a2);
+        }
+      }
+      c2[v] = (sj * a.inv_s2) * kj[v];  // -(k/s^2) u_j[col] / s^2
+      kjd[v][0] = -a0 * kj[v];
+      kjd[v][1] = -a1 * kj[v];
+      kjd[v][2] = -a2 * kj[v];
+    }
+    // fast path: whole block wanted, not the diagonal block, and (NV = 2) both columns live and 16-byte aligned
+    const int64_t j_first = jb + jl[0], j_last = jb + jl[NV - 1];
+    bool fast = interior && work[0] && work[NV - 1] && j_first != i && j_last != i;
+    if (NV == 2) fast = fast && okc[0] && okc[1] && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
+    if (fast) {
+      double *dst = a.K + rbase * ld + a.nv + jb * G3 + rr[0];
+      for (int aa = 0; aa < nat; aa++) {
+        double nej[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) nej[v] = ej[v][aa * G3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const int q = aa * 3 + t;
+          double val[NV];
+#pragma unroll
+          for (int v = 0; v < NV; v++) {
+            const double e27 = -Ei[aa * G3 + 3 * bb[v] + t];
+            val[v] = fma(pb[v][2 + q], c2[v], kj[v] * (e27 * nej[v]));
+            if (aa == bb[v]) val[v] += kjd[v][t];
+          }
+          if (NV == 2)
+            *reinterpret_cast<double2 *>(dst) = make_double2(val[0], val[NV - 1]);
+          else
+            *dst = val[0];
+          dst += ld;
+        }
+      }
+    } else {
+      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal, columns one at a time
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        if (!work[v]) continue;
+        const int64_t j = jb + jl[v];
+        double *dst = a.K + rbase * ld + a.nv + j * G3 + cc[v];
+        for (int q = 0; q < G3; q++) {
+          const int aa = q / 3, t = q - aa * 3;
+          const double e27 = -Ei[aa * G3 + 3 * bb[v] + t];
+          double val = fma(pb[v][2 + q], c2[v], kj[v] * (e27 * ej[v][aa * G3]));
+          if (aa == bb[v]) val += (t == 0 ? kjd[v][0] : t == 1 ? kjd[v][1] : kjd[v][2]);
+          if (j == i && q == cc[v]) val += a.lambdag;
+          const int64_t r = rbase + q;
+          if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * ld] = val;
+        }
+      }
+    }
+  }
+}
+
+#ifndef KREG_EMIT_RT_FROM
+#define KREG_EMIT_RT_FROM 11  // first molecule size whose gradient-gradient blocks are emitted by the run-time kernel
+#endif
+
+// launch plan of the run-time kernels (KREG_RT_* environment variables override, for tuning runs)
+struct RtPlan {
+  int JT, TJ, NJB, NBUF, NV, threads;
+  size_t pair_smem, emit_smem;
+};
+
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static RtPlan rt_plan(int nat, const GradArgs &a) {
+  RtPlan p;
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, PWS = PW | 1, DP = D | 1, EJ = a.ES, XS = a.XS;
+  // pair terms: as many j per CTA as ~100 KB allow (two CTAs per SM), at most 64
+  const size_t fixed = (size_t)EJ + ((D + 1) & ~1) + 64 + 4;
+  const size_t per_j = (size_t)DP + PWS + 1;
+  long jt = ((long)(100 * 1024 / 8) - (long)fixed) / (long)per_j;
+  if (jt < 4) jt = ((long)(220 * 1024 / 8) - (long)fixed) / (long)per_j;  // large molecules: one CTA per SM
+  if (jt > 64) jt = 64;
+  if (jt < 1) jt = 1;
+  p.JT = env_int("KREG_RT_JT", (int)jt);
+  p.pair_smem = (fixed + (((size_t)p.JT * DP + 1) & ~(size_t)1) + (((size_t)p.JT * PWS + 1) & ~(size_t)1)) * sizeof(double);
+  // emit: NV = 2 columns per thread; TJ even; TJ * G3 <= 510 columns; double-buffered while three CTAs still fit an SM
+  p.NV = env_int("KREG_RT_NV", 2);
+  const size_t per_geom = (size_t)PW + XS + EJ;
+  int tj = (256 * p.NV - 2) / G3;
+  tj &= ~1;
+  if (tj < 2) tj = 2;
+  if (tj > 16) tj = 16;
+  const size_t budget = 72 * 1024 / 8;  // doubles: three CTAs per SM
+  const size_t own = (size_t)XS + EJ + 4;
+  auto fit = [&](int nb, size_t lim) {  // largest even TJ <= tj whose buffers fit `lim` doubles (0: none)
+    int t = tj;
+    while (t >= 2 && own + (size_t)nb * per_geom * t > lim) t -= 2;
+    return t < 2 ? 0 : t;
+  };
+  int nbuf = 2;
+  int t2 = fit(2, budget), t1 = fit(1, budget);
+  if (t2 >= tj / 2 && t2 >= 2) {
+    tj = t2;
+  } else if (t1 >= 2) {
+    nbuf = 1;
+    tj = t1;
+  } else {  // large molecules: one CTA per SM, single buffer, whatever fits
+    nbuf = 1;
+    t1 = fit(1, 220 * 1024 / 8);
+    tj = t1 >= 2 ? t1 : 2;
+  }
+  p.TJ = env_int("KREG_RT_TJ", tj) & ~1;
+  if (p.TJ < 2) p.TJ = 2;
+  p.NBUF = env_int("KREG_RT_NBUF", nbuf);
+  p.NJB = env_int("KREG_RT_NJB", 8);
+  const int need = (p.TJ * G3 + p.NV - 1) / p.NV + 1;
+  p.threads = ((need + 31) / 32) * 32;
+  p.emit_smem = (own + (size_t)p.NBUF * per_geom * p.TJ) * sizeof(double);
+  return p;
+}
+
+static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, cudaStream_t st) {
+  const RtPlan p = rt_plan(nat, a);
+  if (p.threads > 256 || p.pair_smem > 227 * 1024 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
+  if (pair_terms) {
+    KREG_CUDA_TRY(cudaFuncSetAttribute(pair_terms_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pair_smem));
+    dim3 grid((unsigned)((a.ntr + p.JT - 1) / p.JT), (unsigned)a.ntr);
+    pair_terms_rt_kernel<<<grid, 256, p.pair_smem, st>>>(a, nat, p.JT);
+    KREG_LAUNCH_CHECK();
+  }
+  dim3 grid((unsigned)((a.ntr + (int64_t)p.NJB * p.TJ - 1) / ((int64_t)p.NJB * p.TJ)), (unsigned)a.ntr);
+  if (p.NV == 2) {
+    KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
+    grad_emit_rt_kernel<2><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NJB, p.NBUF);
+  } else {
+    KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
+    grad_emit_rt_kernel<1><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NJB, p.NBUF);
+  }
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
 template <int NAT>
-static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
+static int launch_grad_nat(const GradArgs &a, cudaStream_t st, bool do_pair, bool do_emit) {
   using C = GradCfg<NAT>;
-  if constexpr (C::D <= 45) {
+  if (!do_pair) {
+  } else if constexpr (C::D <= 45) {
     using SM = PairSmall<NAT>;
     auto kern = pair_terms_small_kernel<NAT>;
     const size_t smem = (size_t)SM::DOUBLES * sizeof(double);
@@ -835,6 +1277,7 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
     kern<<<grid, 256, smem, st>>>(a);
     KREG_LAUNCH_CHECK();
   }
+  if (!do_emit) return KREG_OK;
   dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)a.ntr);
   auto emit = grad_emit_kernel<NAT>;
   const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
@@ -844,11 +1287,19 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
   return KREG_OK;
 }
 
+// Which kernels run (defaults from the measurements in DESIGN.md 4.3; KREG_PAIR_RT / KREG_EMIT_RT = 0 / 1 override for
+// A/B runs): molecules above 24 atoms have no templated instantiation and always take the run-time kernels.
 static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
+  if (nat > KREG_FUSED_MAX_NATOMS) return launch_grad_rt(nat, a, true, st);
+  const bool pair_rt = env_int("KREG_PAIR_RT", 0) != 0;
+  const bool emit_rt = env_int("KREG_EMIT_RT", nat >= KREG_EMIT_RT_FROM ? 1 : 0) != 0;
+  if (pair_rt && emit_rt) return launch_grad_rt(nat, a, true, st);
+  int rc = KREG_E_UNSUPPORTED;
   switch (nat) {
-#define KREG_CASE(N) \
-  case N:            \
-    return launch_grad_nat<N>(a, st);
+#define KREG_CASE(N)                                           \
+  case N:                                                      \
+    rc = launch_grad_nat<N>(a, st, !pair_rt, !emit_rt);        \
+    break;
 #ifdef KREG_ONLY_NAT9  /* experiment builds (tools/ab_kbuild.sh): one instantiation, seconds to compile */
     KREG_CASE(9)
 #else
@@ -860,11 +1311,18 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
     default:
       return KREG_E_UNSUPPORTED;
   }
+  if (rc) return rc;
+  if (pair_rt || emit_rt) {
+    // mixed: one stage from the templated kernels (above), the other from the run-time ones
+    if (pair_rt) return KREG_E_BADARG;  // run-time pair terms are only combined with the run-time emit kernel
+    return launch_grad_rt(nat, a, false, st);
+  }
+  return KREG_OK;
 }
 
 // workspace carve-up helpers ---------------------------------------------------------------
 struct BuildWs {
-  size_t off_center, off_X, off_Xch, off_bias, off_E, off_P, total;
+  size_t off_center, off_X, off_Xch, off_bias, off_biasc, off_E, off_P, total;
   int XS, KC, nchunks, XSC;
 };
 
@@ -897,6 +1355,7 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad, int64_t pair_rows = 
   w.XSC = w.KC * 4 + ((w.KC * 4) % 8 == 4 ? 0 : 4);
   w.off_Xch = w.nchunks > 1 ? take((size_t)w.nchunks * n * w.XSC) : off;  // chunk-major copy for the values kernel
   w.off_bias = take((size_t)n);
+  w.off_biasc = take((size_t)n);
   w.off_E = with_grad ? take((size_t)n * ((nat * nat * 3 + 1) & ~1)) : off;
   w.off_P = with_grad ? take((size_t)pair_rows * n * ((3 * nat + 3) & ~1)) : off;
   w.total = off;
@@ -949,12 +1408,13 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
   double *center = reinterpret_cast<double *>(ws + w.off_center);
   double *Xc = reinterpret_cast<double *>(ws + w.off_X);
   double *bias = reinterpret_cast<double *>(ws + w.off_bias);
+  double *biasc = reinterpret_cast<double *>(ws + w.off_biasc);
   const double inv_s2 = 1.0 / (sigma * sigma);
   const double c1 = kExpScale * inv_s2;
 
   int rc = launch_descriptor_mean(natoms, ntrain, xyz_train, xeq, center, st);
   if (rc) return rc;
-  rc = launch_prep_rows(natoms, ntrain, xyz_train, xeq, center, w.XS, c1, Xc, bias, st);
+  rc = launch_prep_rows(natoms, ntrain, xyz_train, xeq, center, w.XS, c1, Xc, bias, biasc, st);
   if (rc) return rc;
   double *Xch = reinterpret_cast<double *>(ws + w.off_Xch);
   if (w.nchunks > 1 && ntrval > 0 && row_begin < ntrval) {
@@ -966,7 +1426,8 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     a.XA = a.XB = Xc;
     a.XAch = a.XBch = w.nchunks > 1 ? Xch : nullptr;
     a.XSC = w.XSC;
-    a.biasA = a.biasB = bias;
+    a.biasA = bias;
+    a.biasB = biasc;
     a.na = a.nb = ntrain;
     a.XS = w.XS;
     a.nchunks = w.nchunks;
@@ -1031,13 +1492,14 @@ extern "C" int kreg_kernel_block(int natoms, int64_t na, const double *xyz_a, in
   double *center = reinterpret_cast<double *>(ws + wa.total + wb.off_center);
   double *XA = reinterpret_cast<double *>(ws + wa.off_X), *bA = reinterpret_cast<double *>(ws + wa.off_bias);
   double *XB = reinterpret_cast<double *>(ws + wa.total + wb.off_X);
-  double *bB = reinterpret_cast<double *>(ws + wa.total + wb.off_bias);
+  double *bB = reinterpret_cast<double *>(ws + wa.total + wb.off_biasc);
+  double *bBrow = reinterpret_cast<double *>(ws + wa.total + wb.off_bias);
   const double c1 = kExpScale / (sigma * sigma);
   int rc = launch_descriptor_mean(natoms, nb, xyz_b, xeq, center, st);
   if (rc) return rc;
-  rc = launch_prep_rows(natoms, na, xyz_a, xeq, center, wa.XS, c1, XA, bA, st);
+  rc = launch_prep_rows(natoms, na, xyz_a, xeq, center, wa.XS, c1, XA, bA, nullptr, st);
   if (rc) return rc;
-  rc = launch_prep_rows(natoms, nb, xyz_b, xeq, center, wb.XS, c1, XB, bB, st);
+  rc = launch_prep_rows(natoms, nb, xyz_b, xeq, center, wb.XS, c1, XB, bBrow, bB, st);
   if (rc) return rc;
   double *XAch = reinterpret_cast<double *>(ws + wa.off_Xch);
   double *XBch = reinterpret_cast<double *>(ws + wa.total + wb.off_Xch);

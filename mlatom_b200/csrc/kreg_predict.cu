@@ -27,16 +27,13 @@ __global__ void __launch_bounds__(256) precompute_v_kernel(int nat, int64_t ntra
                                                            const double *__restrict__ xeq,
                                                            const double *__restrict__ alpha_g,
                                                            double *__restrict__ V) {
-  __shared__ unsigned short tab[descr_size(KREG_MAX_NATOMS)];
-  for (int a = threadIdx.x; a < nat; a += blockDim.x)
-    for (int b = a + 1; b < nat; b++) tab[pair_index(nat, a, b)] = (unsigned short)(a | (b << 8));
-  __syncthreads();
   const int D = descr_size(nat);
   const int64_t total = ntrain * D;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t j = e / D;
     int d = (int)(e - j * D);
-    int a = tab[d] & 0xff, c = tab[d] >> 8;
+    int a, c;
+    pair_from_index(nat, d, a, c);
     const double *m = xyz + j * nat * 3;
     const double *ag = alpha_g + j * nat * 3;
     double r2 = rij2_exact(m + 3 * a, m + 3 * c);
@@ -222,6 +219,8 @@ extern "C" int kreg_pack_model_x(int natoms, int64_t ntrain, const double *X_tra
   const TcShape sh(natoms);
   descriptor_mean_x_kernel<<<sh.D, 256, 0, st>>>(sh.D, ntrain, X_train, center);
   KREG_LAUNCH_CHECK();
+  if (natoms > KREG_FUSED_MAX_NATOMS)
+    return big_pack_model(natoms, ntrain, nullptr, X_train, nullptr, alpha_val, V, sigma, center, packed, packed_bytes, st);
   const int TS = sh.NT * 8 > sh.KS * 4 ? sh.NT * 8 : sh.KS * 4;
   const size_t smem = (size_t)(16 * TS + 16) * sizeof(double);
   const double inv_s2 = 1.0 / (sigma * sigma);
@@ -239,11 +238,13 @@ extern "C" int kreg_pack_model_x(int natoms, int64_t ntrain, const double *X_tra
 
 extern "C" int kreg_predict_tile_rows(int natoms, int has_gradient_terms) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  if (natoms > KREG_FUSED_MAX_NATOMS) return 128;  // CTA tile rows of the tiled path
   return tile_rows(natoms, has_gradient_terms != 0);
 }
 
 extern "C" size_t kreg_packed_model_bytes(int natoms, int64_t ntrain, int has_gradient_terms) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain < 0) return 0;
+  if (natoms > KREG_FUSED_MAX_NATOMS) return big_packed_model_bytes(natoms, ntrain, has_gradient_terms != 0);
   const TcShape sh(natoms);
   const int64_t groups = (ntrain + 7) / 8;
   return (size_t)groups * sh.chunk_doubles(has_gradient_terms != 0) * sizeof(double);
@@ -260,6 +261,8 @@ extern "C" int kreg_pack_model(int natoms, int64_t ntrain, const double *xyz_tra
   cudaStream_t st = as_stream(stream);
   int rc = launch_descriptor_mean(natoms, ntrain, xyz_train, xeq, center, st);
   if (rc) return rc;
+  if (natoms > KREG_FUSED_MAX_NATOMS)
+    return big_pack_model(natoms, ntrain, xyz_train, nullptr, xeq, alpha_val, V, sigma, center, packed, packed_bytes, st);
   const TcShape sh(natoms);
   const int TS = sh.NT * 8 > sh.KS * 4 ? sh.NT * 8 : sh.KS * 4;
   const size_t smem = (size_t)(16 * TS + 16) * sizeof(double);
@@ -292,6 +295,8 @@ extern "C" size_t kreg_predict_workspace_bytes(int natoms, int64_t ntrain, int h
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0 || npoints <= 0) return 0;
   int sms = 0;
   if (device_sm_count(&sms) != KREG_OK) return 0;
+  if (natoms > KREG_FUSED_MAX_NATOMS)
+    return big_predict_workspace_bytes(natoms, ntrain, has_gradient_terms != 0, npoints, sms);
   PredictArgs a = {};
   a.npoints = npoints;
   a.ngroups = (int)((ntrain + 7) / 8);
@@ -313,6 +318,10 @@ extern "C" int kreg_predict(int natoms, int64_t ntrain, const void *packed, cons
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc) return rc;
+  if (natoms > KREG_FUSED_MAX_NATOMS)
+    return big_predict(natoms, ntrain, packed, center, xeq, sigma, prior, has_gradient_terms != 0, npoints, xyz,
+                       (flags & KREG_PREDICT_ENERGY) ? E : nullptr, (flags & KREG_PREDICT_GRADIENT) ? G : nullptr,
+                       workspace, workspace_bytes, sms, as_stream(stream));
   PredictArgs a = {};
   a.xyz = xyz;
   a.npoints = npoints;

@@ -107,7 +107,8 @@ def test_golden_hessian(golden, eng):
         assert not h.any()
 
 
-@pytest.mark.parametrize("nat,ntr,nte", [(2, 5, 3), (3, 33, 4), (12, 100, 7), (16, 64, 3), (21, 40, 2), (24, 37, 3)])
+@pytest.mark.parametrize("nat,ntr,nte", [(2, 5, 3), (3, 33, 4), (12, 100, 7), (16, 64, 3), (21, 40, 2), (24, 37, 3),
+                                         (25, 40, 2), (32, 37, 3), (48, 9, 2)])
 def test_hessian_vs_oracle(eng, oracle, nat, ntr, nte):
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 11), S.geometries(eq, nte, 12)
@@ -308,9 +309,10 @@ def test_small_batch_latency_mode_vs_oracle(eng, oracle, nat, ntr, use_grads):
         assert (e_only - e).abs().max().item() <= 1e-12 * max(1.0, np.abs(sc).max())
 
 
-@pytest.mark.parametrize("nat", list(range(2, 25)))
+@pytest.mark.parametrize("nat", list(range(2, 25)) + [25, 26, 27, 29, 32, 33, 40, 48, 57, 64])
 def test_every_supported_molecule_size(eng, oracle, nat):
-    """Natoms = 2..24 (KREG_MIN/MAX_NATOMS): K blocks and E/dE for a gradient-trained model against the oracle."""
+    """Natoms = 2..64 (KREG_MIN/MAX_NATOMS; above 24 the run-time-Natoms kernels and the tiled prediction path): K blocks
+    and E/dE for a gradient-trained model against the oracle."""
     ntr, nte = 11, 23
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
@@ -349,7 +351,7 @@ def test_edge_cases(eng):
     from mlatom_b200._lib import KregError
 
     with pytest.raises(KregError):
-        eng.xeq(dev(np.random.default_rng(0).standard_normal((40, 3))))
+        eng.xeq(dev(np.random.default_rng(0).standard_normal((65, 3))))
 
 
 def test_full_size_kernel_matrices(eng, oracle):
