@@ -44,13 +44,27 @@ WORKLOAD = "cfg2: KREG energies+forces prediction, 9 atoms, Ntrain=10000, Ntest=
 FLOP_PER_STEP = float(NTEST) * NTRAIN * (5 * D + 4) + float(NTEST) * 30 * D
 SCALING = "weak"
 KERNEL = "kreg::predict_kernel<9,2,false,false,3,3,true,8,false>"
-TRAFFIC = 429.13e6  # dram bytes of one launch, ncu --set full (profiles/r01_predict_ncu.txt)
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the ncu capture recorded in
+    profiles/traffic.json (written by tools/ncu_summary.py next to the summary it was read from); None if the kernel
+    has no entry -- never a constant kept in this file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f).get(kernel)
+        return (rec["dram_bytes"], rec["source"]) if rec else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+TRAFFIC, TRAFFIC_SOURCE = measured_traffic(KERNEL)
 
 
 def set_workload(name, world):
     """--workload cfg4: BASELINE.json configs[3], 10M 21-atom geometries in total, split over the ranks (strong scaling).
     The default (cfg2) is the configuration the metric is quoted on and is what the driver runs."""
-    global NAT, NTRAIN, NTEST, SIGMA, D, METRIC, WORKLOAD, FLOP_PER_STEP, SCALING, KERNEL, TRAFFIC
+    global NAT, NTRAIN, NTEST, SIGMA, D, METRIC, WORKLOAD, FLOP_PER_STEP, SCALING, KERNEL, TRAFFIC, TRAFFIC_SOURCE
     if name == "cfg2":
         return
     NAT, NTRAIN, NTEST, SIGMA = 21, 10000, 10_000_000 // world, 2.0
@@ -61,7 +75,7 @@ def set_workload(name, world):
     FLOP_PER_STEP = float(NTEST) * NTRAIN * (5 * D + 4) + float(NTEST) * 30 * D
     SCALING = "strong"
     KERNEL = "kreg::predict_kernel<21,1,false,true,1,3,true,8,false>"
-    TRAFFIC = None
+    TRAFFIC, TRAFFIC_SOURCE = measured_traffic(KERNEL)
 
 
 def training_set():
@@ -213,6 +227,156 @@ def kbuild_configs(engine, dev, hbm_peak, fp64_peak):
         del k
         torch.cuda.empty_cache()
     return out
+
+
+def kbuild_sharded(engine, dev, world, rank, barrier, max_over_ranks):
+    """BASELINE configs[2]: the 50k x 50k values K (10 GB lower triangle) assembled as row slabs over the ranks and gathered
+    onto the factorising GPU (rank 0) with the pipelined trapezoid gather of mlatom_b200.dist; potrf timed apart; the
+    gathered matrix is checked on sampled rows against the independent rectangular-block kernel."""
+    import torch
+    import torch.distributed as dist
+
+    from mlatom_b200 import dist as kd, synthetic as S
+
+    ntr = 50000
+    eq = S.equilibrium(NAT)
+    xyz_h = S.geometries(eq, ntr, seed=1)
+    e_h, _ = S.pair_potential(xyz_h, eq)
+    xyz = torch.from_numpy(xyz_h).to(dev)
+    xeq = engine.xeq(torch.from_numpy(eq).to(dev))
+    m = ntr
+
+    def build_rows(r0, r1, out, row_offset):
+        engine.build_kernel_matrix(xyz, xeq, SIGMA, LAMBDA, LAMBDA, rows=(r0, r1), out=out, row_offset=row_offset)
+
+    slabs = kd.triangle_row_slabs(m, world)
+    r0, r1 = slabs[rank]
+    # (1) assembly alone: this rank's slab into a trapezoid buffer, CUDA events, max over ranks
+    buf = torch.empty((r1 - r0, kd.piece_width(r1, m)), dtype=torch.float64, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ms = []
+    for it in range(4):
+        barrier()
+        ev[0].record()
+        build_rows(r0, r1, buf, r0)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it:
+            ms.append(ev[0].elapsed_time(ev[1]))
+    build_ms = max_over_ranks(float(np.mean(ms)))
+    del buf
+    if world > 1:  # open the NCCL point-to-point channels before timing (lazy connection setup is not the gather)
+        tiny = torch.zeros(8, dtype=torch.float64, device=dev)
+        if rank == 0:
+            for r in range(1, world):
+                dist.recv(tiny, r)
+        else:
+            dist.send(tiny, 0)
+    # (2) assembly + gather, pipelined; device time on every rank, max over ranks
+    total_ms, stats, k = [], {}, None
+    for it in range(2):
+        del k
+        k = None
+        torch.cuda.empty_cache()
+        barrier()
+        ev[0].record()
+        k = kd.build_kernel_matrix_sharded(build_rows, m, dev, root=0, pieces=4, stats=stats)
+        ev[1].record()
+        torch.cuda.synchronize()
+        total_ms.append(ev[0].elapsed_time(ev[1]))
+    total = max_over_ranks(total_ms[-1])
+    gbytes = stats.get("gather_bytes", 0)
+    if world > 1:
+        t = torch.tensor([float(gbytes if rank else 0)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        gbytes = t.item()
+    out = {"workload": f"cfg3: K 50k x 50k values (lower triangle, 4*M*(M+1) = {4.0 * m * (m + 1) / 1e9:.1f} GB), "
+                       f"row slabs over {world} GPU(s), gathered onto rank 0",
+           "assembly_ms_max_over_ranks": build_ms, "assembly_gb_per_s_aggregate": 4.0 * m * (m + 1) / build_ms * 1e-6,
+           "assembly_plus_gather_ms": total, "gather_bytes_into_root": gbytes,
+           "gather_ms_not_hidden": max(total - build_ms, 0.0),
+           "inbound_gb_per_s": (gbytes / (max(total - build_ms, 1e-3)) * 1e-6) if world > 1 else None,
+           "nvlink_reference_gb_per_s": 770.0,
+           "note": "slabs travel as trapezoids (columns j <= i only), in 4 equal-area pieces per rank, each sent while the "
+                   "next is assembled; the root scatters them into its M x M matrix"}
+    if rank == 0:
+        rng = np.random.default_rng(11)
+        rows = np.sort(rng.choice(ntr, size=32, replace=False))
+        idx = torch.as_tensor(rows).to(dev)
+        blk = engine.kernel_block(xyz[idx].contiguous(), xyz, xeq, SIGMA)
+        worst = 0.0
+        for n, i in enumerate(rows):
+            if i:
+                worst = max(worst, (k[i, :i] - blk[n, :i]).abs().max().item())
+        out["sampled_rows_max_abs_difference_vs_kernel_block"] = worst
+        y = torch.from_numpy(e_h - e_h.mean()).to(dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        alpha = engine.solve(k, y)
+        torch.cuda.synchronize()
+        out["potrf_potrs_ms_timed_separately"] = 1e3 * (time.perf_counter() - t0)
+        res = blk @ alpha + LAMBDA * alpha[idx] - y[idx]
+        out["residual_rel_sampled_rows"] = (res.norm() / y[idx].norm()).item()
+    del k
+    torch.cuda.empty_cache()
+    return out
+
+
+def cfg4_strong(engine, dev, world, rank, barrier, max_over_ranks):
+    """BASELINE configs[3]: 10 M aspirin-sized (21-atom) geometries IN TOTAL, split over the ranks (strong scaling),
+    streamed from pinned host memory through PackedModel.predict_host (H2D, kernel, D2H overlapped on three streams);
+    Ntrain = 10 000 (assumed), alpha from a real solve on rank 0."""
+    import torch
+    import torch.distributed as dist
+
+    from mlatom_b200 import synthetic as S
+
+    nat, ntr, total, sigma = 21, 10000, 10_000_000, 2.0
+    d = nat * (nat - 1) // 2
+    eq = S.equilibrium(nat)
+    xtr_h = S.geometries(eq, ntr, seed=1)
+    e_h, _ = S.pair_potential(xtr_h, eq)
+    xtr = torch.from_numpy(xtr_h).to(dev)
+    xeq = engine.xeq(torch.from_numpy(eq).to(dev))
+    alpha = torch.empty(ntr, dtype=torch.float64, device=dev)
+    if rank == 0:
+        k = engine.build_kernel_matrix(xtr, xeq, sigma, LAMBDA, LAMBDA)
+        alpha.copy_(engine.solve(k, torch.from_numpy(e_h - e_h.mean()).to(dev)))
+        del k
+    if world > 1:
+        dist.broadcast(alpha, src=0)
+    model = engine.PackedModel.from_training_set(xtr, xeq, alpha, sigma, float(e_h.mean()), ntr, 0)
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    n = hi - lo
+    # this rank's shard, generated on the device in slices and parked in pinned host memory (the workload's input)
+    x_host = torch.empty((n, nat, 3), dtype=torch.float64, pin_memory=True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    d_eq = torch.from_numpy(eq).to(dev)
+    for a in range(0, n, 1 << 20):
+        b = min(n, a + (1 << 20))
+        x_host[a:b].copy_(d_eq + 0.05 * torch.randn((b - a, nat, 3), dtype=torch.float64, device=dev, generator=gen))
+    out_e = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    out_g = torch.empty((n, nat, 3), dtype=torch.float64, pin_memory=True)
+    torch.cuda.synchronize()
+    host = engine.HostPredictor(model)
+    warm = min(n, 2 * host.chunk)
+    host.run(x_host[:warm], True, True, out_e[:warm], out_g[:warm])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    t0 = time.perf_counter()
+    ev[0].record()
+    host.run(x_host, True, True, out_e, out_g)
+    ev[1].record()
+    barrier()
+    ms = max_over_ranks(max(ev[0].elapsed_time(ev[1]), 1e3 * (time.perf_counter() - t0)))
+    flop = float(total) * ntr * (5 * d + 4) + float(total) * 30 * d
+    return {"workload": "cfg4: KREG E+F screening of 10M 21-atom geometries in total (strong scaling), Ntrain=10000, "
+                        "pinned host xyz -> pinned host E, dE/dxyz",
+            "geometries_total": total, "geometries_per_gpu": n, "ms": ms, "value": total / ms * 1e3, "unit": UNIT,
+            "scaling": "strong", "h2d_bytes_per_gpu": n * nat * 24, "d2h_bytes_per_gpu": n * (8 + nat * 24),
+            "algorithmic_tflops_aggregate": flop / ms * 1e-9, "checksum": float(out_e[:1000].sum()),
+            "finite": bool(torch.isfinite(out_e).all().item())}
 
 
 def cfg1_side_by_side(engine, dev):
@@ -452,6 +616,18 @@ def run_ours(args):
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
     e2e_value = world * NTEST * e2e_steps / (e2e_ms * 1e-3)
     checksum = float(out_e[:1000].sum())  # the device->host read of the step's result
+    d_e_keep = None
+    parity_n = 200000  # the CPU baseline's sample never exceeds this many geometries (12 s at ~9 k geometries/s)
+    e_keep_host, g_keep_host = d_e[:parity_n].cpu().numpy(), d_g[:parity_n].cpu().numpy()
+    del out_e, out_g, host
+
+    # ---- the two multi-GPU configurations north_star names beside the headline (every rank takes part) ----
+    sharded_blocks = {}
+    if args.workload == "cfg2" and not args.no_extra:
+        del d_xte, d_g, d_e_keep
+        torch.cuda.empty_cache()
+        sharded_blocks["kbuild_sharded"] = kbuild_sharded(engine, dev, world, rank, barrier, max_over_ranks)
+        sharded_blocks["cfg4_strong"] = cfg4_strong(engine, dev, world, rank, barrier, max_over_ranks)
 
     if world > 1:
         dist.barrier()
@@ -474,8 +650,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "pipe": "FP64 tensor core (DMMA.8x8x4); shares the FP64 pipe with DFMA",
                      "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
                      "traffic": TRAFFIC,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
-                                       "profiles/r01_predict_ncu.txt (algorithmic I/O: 440 MB per launch)" if TRAFFIC else None,
+                     "traffic_source": TRAFFIC_SOURCE,
+                     "algorithmic_io_bytes_per_launch": NTEST * (NAT * 3 * 8 * 2 + 8),
                      "peak_source": "measured live by kreg_measure_fp64_peak(DMMA) (MEASURED_PEAKS.json has no FP64 figure)",
                      "peak_dfma": peak_dfma, "algorithmic_flop_per_launch": FLOP_PER_STEP,
                      "kernel": KERNEL, "kernel_ms": kernel_ms,
@@ -511,7 +687,9 @@ def run_ours(args):
         line["cpu_baseline"] = base
         # parity of the timed run itself: the CPU port predicted the first n_cpu geometries of this rank's test batch
         # with the same alpha -- diff them against what the timed kernel left in d_e / d_g
-        e_gpu, g_gpu = d_e[:n_cpu].cpu().numpy(), d_g[:n_cpu].cpu().numpy()
+        n_cpu = min(n_cpu, parity_n)
+        e_cpu, g_cpu = e_cpu[:n_cpu], g_cpu[:n_cpu]
+        e_gpu, g_gpu = e_keep_host[:n_cpu], g_keep_host[:n_cpu]
         line["parity"] = {
             "against": "cpu_baseline (oracle port of MLatomF's loop, A_KRR_kernel.f90:327-412), same alpha, same geometries",
             "geometries": int(n_cpu), "ntrain": NTRAIN,
@@ -526,6 +704,7 @@ def run_ours(args):
             line["cpu_baseline_reference_as_shipped"] = shipped
         if args.workload == "cfg2":
             line["cfg1"] = cfg1_side_by_side(engine, dev)
+    line.update(sharded_blocks)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -538,6 +717,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the kbuild_sharded / cfg4_strong blocks (profiling runs)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
                     help="cfg2 (default, the configuration the metric is quoted on) or cfg4 (10M 21-atom geometries)")
     args = ap.parse_args()

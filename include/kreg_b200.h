@@ -62,6 +62,10 @@ extern "C" {
 int kreg_abi_version(void);
 /* Text of the last CUDA/cuSOLVER error seen by the calling thread ("" if none). */
 const char *kreg_last_error(void);
+/* Debug builds (make -C mlatom_b200/csrc debug -> libkreg_b200_dbg.so, -DKREG_DEBUG_BOUNDS) check every bulk-copy size /
+ * alignment and every guarded global store inside the kernels; this returns the number of failed checks so far (and the
+ * first failure's code and source line), synchronising the device.  Release builds return -1. */
+long long kreg_debug_bounds_failures(int *first_code, int *first_line);
 /* 0 if the current CUDA device can run the kernels (compute capability 10.x). */
 int kreg_device_check(void);
 /* Blocks the calling host thread until `stream` has drained (cudaStreamSynchronize): lets a ctypes caller finish a
@@ -101,8 +105,10 @@ size_t kreg_build_workspace_bytes_rows(int natoms, int64_t ntrain, int64_t ntrgr
  * Builds rows [row_begin,row_end) of  K + diag(lambdav*1_NtrVal, lambdagradxyz*1_NtrGrXYZ)
  * directly from Cartesian coordinates (descriptor build fused into the call).
  *   ntrval  in {0, ntrain}; ntrgr in {0, 3*natoms*ntrain}  (kreg_api.py:52-72); M = ntrval+ntrgr.
- *   K points at element (0,0) of an M x ldk row-major matrix (ldk >= M); only rows in the range
- *   are touched, so ranks can assemble disjoint row slabs of one matrix.
+ *   K points at element (0,0) of an M x ldk row-major matrix; only rows in the range are touched, so ranks can
+ *   assemble disjoint row slabs of one matrix.  ldk >= M, except that with KREG_FILL_LOWER a slab may use
+ *   a shorter row stride: at least row_end (rounded up to a whole 3*natoms block in the gradient part), the defined
+ *   length of its last row -- slabs then travel between GPUs as trapezoids, not as M-wide rows.
  *   fill = KREG_FILL_LOWER writes j <= i only; KREG_FILL_FULL mirrors as the reference does (for gradient models
  *   only together with the whole row range; a partial range returns KREG_E_BADARG). */
 int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrval, int64_t ntrgr,
@@ -193,6 +199,21 @@ int kreg_predict(int natoms, int64_t ntrain, const void *packed, const double *c
  * H[p][3Nat][3Nat], symmetric. */
 int kreg_hessian(int natoms, int64_t ntrain, const double *X_train, const double *alpha_val, const double *xeq,
                  double sigma, int64_t npoints, const double *xyz, double *H, void *stream);
+
+/* Batched molecular dynamics around kreg_predict (velocity Verlet exactly as mlatom/md.py:158-205; batch driver
+ * md_parallel.py:155-200), all arrays device resident: xyz, vel, grad [ntraj][natoms][3]; acc_scale[3*natoms] = c_acc / m_a
+ * and kin_scale[3*natoms] = c_kin * m_a / 2 per Cartesian component (the reference's unit factors, md.py:171 and
+ * data.py:862, folded in by the caller); `active` (may be NULL) holds 1.0 for running and 0.0 for frozen trajectories.
+ *   first half : a = -grad * acc_scale;  x += v dt + a dt^2/2;  v += a dt/2          (md.py:190-193)
+ *   second half: v += a_new dt/2;  ekin[p] = sum kin_scale v^2                        (md.py:204, data.py:862)
+ *   uncertainty: uq = |epot - eaux|; a running trajectory with uq > threshold is frozen and stop_step[p] = *step_no
+ *                (the sampler's stop function, al_utils.py:246-322, :1418-1424) */
+int kreg_md_first_half(int natoms, int64_t ntraj, double dt, const double *acc_scale, const double *grad, double *xyz,
+                       double *vel, const double *active, void *stream);
+int kreg_md_second_half(int natoms, int64_t ntraj, double dt, const double *acc_scale, const double *kin_scale,
+                        const double *grad, double *vel, double *ekin, const double *active, void *stream);
+int kreg_md_uncertainty(int64_t ntraj, const double *epot, const double *eaux, double threshold, const int64_t *step_no,
+                        double *uq, double *active, int64_t *stop_step, void *stream);
 
 /* Test geometries one CTA of kreg_predict handles for this molecule size / model kind (<0: unsupported size).
  * Callers that split a batch into chunks (host streaming, multi-stream pipelines) should use multiples of

@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkreg_b200.so")
+# KREG_LIB selects another build of the same ABI (the bounds-checking debug library, libkreg_b200_dbg.so)
+LIB_PATH = os.environ.get("KREG_LIB") or os.path.join(_HERE, "libkreg_b200.so")
 
 KREG_OK = 0
 KREG_E_BADARG = -1
@@ -35,6 +36,7 @@ PROTOTYPES = {
     "kreg_abi_version": (c_int, []),
     "kreg_last_error": (c_char_p, []),
     "kreg_device_check": (c_int, []),
+    "kreg_debug_bounds_failures": (ctypes.c_longlong, [POINTER(c_int), POINTER(c_int)]),
     "kreg_stream_synchronize": (c_int, [c_void_p]),
     "kreg_measure_fp64_peak": (c_int, [c_int, c_int, c_double, POINTER(c_double)]),
     "kreg_xeq": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
@@ -64,6 +66,11 @@ PROTOTYPES = {
     ),
     "kreg_pack_model_x": (
         c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kreg_md_first_half": (c_int, [c_int, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kreg_md_second_half": (
+        c_int, [c_int, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kreg_md_uncertainty": (
+        c_int, [c_int64, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kreg_hessian": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_int64, c_void_p, c_void_p, c_void_p]),
     "kreg_predict_tile_rows": (c_int, [c_int, c_int]),
     "kreg_predict_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int64]),

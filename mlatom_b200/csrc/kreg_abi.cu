@@ -5,6 +5,12 @@
 
 namespace kreg {
 
+#ifdef KREG_DEBUG_BOUNDS
+__device__ unsigned long long g_debug_failures = 0ull;
+__device__ int g_debug_first_code = 0;
+__device__ int g_debug_first_line = 0;
+#endif
+
 static thread_local char tls_error[512] = "";
 
 void set_last_error(const char *what, const char *detail) {
@@ -53,6 +59,26 @@ __global__ void __launch_bounds__(256) probe_dmma_kernel(double *out, int iters)
 using namespace kreg;
 
 extern "C" int kreg_abi_version(void) { return 1; }
+
+// Number of failed bounds / alignment checks since the library was loaded (synchronises the device); -1 in a build
+// without -DKREG_DEBUG_BOUNDS.  first_code / first_line (may be NULL) identify the first failure (kreg_common.cuh).
+extern "C" long long kreg_debug_bounds_failures(int *first_code, int *first_line) {
+#ifdef KREG_DEBUG_BOUNDS
+  unsigned long long n = 0;
+  int code = 0, line = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(&n, g_debug_failures, sizeof n) != cudaSuccess) return -2;
+  cudaMemcpyFromSymbol(&code, g_debug_first_code, sizeof code);
+  cudaMemcpyFromSymbol(&line, g_debug_first_line, sizeof line);
+  if (first_code) *first_code = code;
+  if (first_line) *first_line = line;
+  return (long long)n;
+#else
+  if (first_code) *first_code = 0;
+  if (first_line) *first_line = 0;
+  return -1;
+#endif
+}
 
 extern "C" const char *kreg_last_error(void) { return tls_error; }
 

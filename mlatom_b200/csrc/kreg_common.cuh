@@ -113,6 +113,33 @@ __device__ __forceinline__ void fill_exp_table(double *tab64, int tid, int nthre
   for (int j = tid; j < 64; j += nthreads) tab64[j] = exp2((double)j * (1.0 / 64.0));
 }
 
+// ---- debug build: every bulk-copy size / alignment and every guarded global store is checked --------------------
+// compute-sanitizer is closed on this GPU pool; `make debug` builds libkreg_b200_dbg.so with -DKREG_DEBUG_BOUNDS, the
+// parity tests are run against it once per round (KREG_LIB=...), and kreg_debug_bounds_failures() must stay 0.
+// Failure codes: 1 bulk copy size not a positive multiple of 16; 2 bulk copy address misaligned; 3 store outside the
+// extent the caller declared; 4 shared-memory destination outside the CTA's dynamic allocation.
+#ifdef KREG_DEBUG_BOUNDS
+extern __device__ unsigned long long g_debug_failures;
+extern __device__ int g_debug_first_code;
+extern __device__ int g_debug_first_line;
+__device__ __forceinline__ void debug_fail(int code, int line) {
+  if (atomicAdd(&g_debug_failures, 1ull) == 0ull) {
+    g_debug_first_code = code;
+    g_debug_first_line = line;
+  }
+}
+#define KREG_CHECK(cond, code)               \
+  do {                                       \
+    if (!(cond)) kreg::debug_fail(code, __LINE__); \
+  } while (0)
+// store through a pointer that must lie inside [base, base + count) doubles
+#define KREG_CHECK_STORE(ptr, base, count) \
+  KREG_CHECK((ptr) >= (base) && (ptr) < (base) + (count), 3)
+#else
+#define KREG_CHECK(cond, code) ((void)0)
+#define KREG_CHECK_STORE(ptr, base, count) ((void)0)
+#endif
+
 // ---- mbarrier + bulk async copy (TMA engine, SASS UBLKCP) ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -145,6 +172,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+#ifdef KREG_DEBUG_BOUNDS
+  {
+    unsigned tot_size;
+    asm("mov.u32 %0, %%total_smem_size;" : "=r"(tot_size));
+    KREG_CHECK(bytes > 0 && (bytes & 15u) == 0, 1);
+    KREG_CHECK((reinterpret_cast<uintptr_t>(src_gmem) & 15) == 0 && (smem_u32(dst_smem) & 15u) == 0, 2);
+    KREG_CHECK(smem_u32(dst_smem) + bytes <= tot_size, 4);
+  }
+#endif
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))

@@ -43,8 +43,12 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
                                                      const double *bA, const double *tab, int wi,
                                                      int wj, int g, int q, bool lower_only) {
   const bool diag_tile = a.symmetric && j0 + kTileJ - 1 >= i0;  // touches the diagonal block: computed directly
+  // Row-slab FULL assembly of the values block computes K[i][j] and K[j][i] in different tiles (possibly on different
+  // GPUs): there the exponent is formed symmetrically, c1 s + (b_i + b_j) with s = X'_i.X'_j alone (the accumulators were
+  // started from zero), so that the two are bit-identical like the reference's mirrored copy (KREG.f90:317-318).
+  const bool symx = a.symmetric && a.all_cols;
   // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
-  const bool interior = !diag_tile && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
+  const bool interior = !diag_tile && !symx && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
                         j0 + kTileJ <= a.nb && (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
   if (interior) {
     double *row = a.K + (i0 + wi * 32 + g) * a.ldk + j0 + wj * 32 + 2 * q;
@@ -56,9 +60,11 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
         const int cj = wj * 32 + nt * 8 + 2 * q;
         const double k0 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][0], a.c1, bi)), tab);
         const double k1 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][1], a.c1, bi)), tab);
+        KREG_CHECK_STORE(row + nt * 8 + 1, a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
         *reinterpret_cast<double2 *>(row + nt * 8) = make_double2(k0, k1);
         if (a.mirror) {
           double *t = a.K + (j0 + cj) * a.ldk + i0 + wi * 32 + mt * 8 + g;
+          KREG_CHECK_STORE(t + a.ldk, a.K, a.na * a.ldk);
           t[0] = k0;
           t[a.ldk] = k1;
         }
@@ -67,6 +73,9 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
     }
     return;
   }
+  // whole-matrix modes compute the tiles on and below the diagonal only: inside a diagonal tile the entries above the
+  // diagonal are taken from their mirror images (written below), never computed a second time
+  const bool tri = a.symmetric && !a.all_cols;
 #pragma unroll
   for (int mt = 0; mt < 4; mt++) {
     const int ri = wi * 32 + mt * 8 + g;
@@ -77,16 +86,22 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
     for (int nt = 0; nt < 4; nt++) {
       const int cj = wj * 32 + nt * 8 + 2 * q;
       const int64_t j = j0 + cj;
-      double k0 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][0], a.c1, bi)), tab);
-      double k1 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][1], a.c1, bi)), tab);
+      double e0 = bi, e1 = bi;
+      if (symx) {
+        e0 = bi + (j < a.nb ? __ldg(a.biasA + j) : 0.0);
+        e1 = bi + (j + 1 < a.nb ? __ldg(a.biasA + j + 1) : 0.0);
+      }
+      double k0 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][0], a.c1, e0)), tab);
+      double k1 = exp_from_scaled(KREG_EXP_ARG(fma(S[mt][nt][1], a.c1, e1)), tab);
       if (a.symmetric) {
         if (i == j) k0 = 1.0 + a.lambda;
         if (i == j + 1) k1 = 1.0 + a.lambda;
       }
       if (row_ok) {
         double *dst = a.K + i * a.ldk + j;
-        const bool w0 = j < a.nb && (!lower_only || j <= i);
-        const bool w1 = j + 1 < a.nb && (!lower_only || j + 1 <= i);
+        const bool w0 = j < a.nb && (!tri || j <= i);
+        const bool w1 = j + 1 < a.nb && (!tri || j + 1 <= i);
+        if (w0 || w1) KREG_CHECK_STORE(dst + (w1 ? 1 : 0), a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
         if (w0 && w1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
           *reinterpret_cast<double2 *>(dst) = make_double2(k0, k1);
         } else {
@@ -94,9 +109,9 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
           if (w1) dst[1] = k1;
         }
       }
-      if (a.mirror && !diag_tile && i < a.na) {
-        if (j < a.nb) a.K[j * a.ldk + i] = k0;
-        if (j + 1 < a.nb) a.K[(j + 1) * a.ldk + i] = k1;
+      if (a.mirror && i < a.na) {
+        if (j < a.nb && j < i) a.K[j * a.ldk + i] = k0;
+        if (j + 1 < a.nb && j + 1 < i) a.K[(j + 1) * a.ldk + i] = k1;
       }
     }
   }
@@ -133,6 +148,7 @@ __device__ __forceinline__ void w_tile_epilogue(const ValuesArgs &a, double (&S)
       }
       const int64_t ch = j / a.wkc;
       const int64_t off = (ch * a.na + i) * a.wkc + (j - ch * a.wkc);
+      KREG_CHECK(off >= 0 && off + 1 < (int64_t)((a.nb + a.wkc - 1) / a.wkc) * a.na * a.wkc && (off & 1) == 0, 3);
       *reinterpret_cast<double2 *>(a.Wch + off) = make_double2(w0, w1);
       if (EPI == EPI_WV) *reinterpret_cast<double2 *>(a.Kfch + off) = make_double2(k0, k1);
     }
@@ -151,6 +167,7 @@ __device__ __forceinline__ void lin_tile_epilogue(const ValuesArgs &a, double (&
     for (int nt = 0; nt < 4; nt++) {
       const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
       double *dst = a.K + i * a.ldk + j;
+      if (j < a.nb) KREG_CHECK_STORE(dst + (j + 1 < a.nb ? 1 : 0), a.K, a.na * a.ldk);
       if (vec && j + 1 < a.nb) {
         *reinterpret_cast<double2 *>(dst) = make_double2(S[mt][nt][0], S[mt][nt][1]);
       } else {
@@ -253,10 +270,12 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
 
   // accumulators start from the column term of their tile (-n_j/2; an arbitrary additive term for EPI_LIN), which
   // arrived with the tile's first stage: the epilogue then has no per-element bias add
+  const bool zero_init = EPI == EPI_K && a.symmetric && a.all_cols;  // see values_tile_epilogue: symmetric exponent
   auto init_acc = [&](const double *bcol) {
 #pragma unroll
     for (int nt = 0; nt < 4; nt++) {
-      const double2 b = *reinterpret_cast<const double2 *>(bcol + wj * 32 + nt * 8 + 2 * q);
+      double2 b = *reinterpret_cast<const double2 *>(bcol + wj * 32 + nt * 8 + 2 * q);
+      if (zero_init) b = make_double2(0.0, 0.0);
 #pragma unroll
       for (int mt = 0; mt < 4; mt++) {
         S[mt][nt][0] = b.x;
@@ -492,6 +511,7 @@ struct GradArgs {
   int64_t ldk;
   double *P;             // [i1 - i0][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
   int64_t p_i0;          // first geometry i whose gradient rows intersect [row_begin, row_end): row 0 of P
+  int64_t p_i1;          // one past the last such geometry
   int ES;                // doubles per E block: Nat*Nat*3 rounded up to even (16-byte aligned blocks for bulk copies)
 };
 
@@ -675,6 +695,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
       const int64_t row = rbase + q;
       if (jj < nj && row >= a.row_begin && row < a.row_end) {
         const double v = Us[jj * PWS] * Us[jj * PWS + 2 + q];
+        KREG_CHECK_STORE(a.K + row * a.ldk + j0 + jj, a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
         a.K[row * a.ldk + j0 + jj] = v;
         if (full) a.K[(j0 + jj) * a.ldk + row] = v;
       }
@@ -780,6 +801,7 @@ __global__ void __launch_bounds__(128, 5) pair_terms_small_kernel(const GradArgs
           const int64_t row = rbase + q;
           if (interior || (row >= a.row_begin && row < a.row_end)) {
             const double v = ks * s[t];
+            KREG_CHECK_STORE(kcol + (int64_t)q * a.ldk, a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
             kcol[(int64_t)q * a.ldk] = v;
             if (full) a.K[(j0 + tid) * a.ldk + row] = v;
           }
@@ -902,6 +924,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
           const int aa = q / 3, t = q % 3;
           double v = fma(pb[2 + q], c2, kj * (e27[q] * nej[aa]));
           if (aa == b) v += kjd[t];
+          KREG_CHECK_STORE(dst, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
           *dst = v;
           dst += ld;
         }
@@ -915,7 +938,10 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
           if (aa == b) v += (t == 0 ? kjd[0] : t == 1 ? kjd[1] : kjd[2]);
           if (j == i && q == col) v += a.lambdag;
           const int64_t r = rbase + q;
-          if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * ld] = v;
+          if (r >= a.row_begin && r < a.row_end) {
+            KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+            dst[(int64_t)q * ld] = v;
+          }
         }
       }
     }
@@ -1007,6 +1033,7 @@ __global__ void __launch_bounds__(256) pair_terms_rt_kernel(const GradArgs a, in
       const int64_t row = rbase + q;
       if (jj < nj && row >= a.row_begin && row < a.row_end) {
         const double v = Us[jj * PWS] * Us[jj * PWS + 2 + q];
+        KREG_CHECK_STORE(a.K + row * a.ldk + j0 + jj, a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
         a.K[row * a.ldk + j0 + jj] = v;
         if (full) a.K[(j0 + jj) * a.ldk + row] = v;
       }
@@ -1014,159 +1041,151 @@ __global__ void __launch_bounds__(256) pair_terms_rt_kernel(const GradArgs a, in
   }
 }
 
-// Emit: CTA = ONE geometry i x up to NJB steps of TJ geometries j; a thread owns NV (1 or 2) adjacent matrix columns
-// of the step and walks the 3 Nat rows of geometry i.  NV = 2 stores 16 bytes per lane (profiles/r01_store_pattern.txt:
-// 7.0-7.2 TB/s against 5.3-6.2 for 8-byte lanes); the pairing is taken relative to the ABSOLUTE column parity so that
-// every 16-byte store is aligned whatever NtrVal is.  Per step the pair terms, X_j rows and E_j blocks of the TJ
-// geometries arrive as three TMA bulk copies (NBUF = 2: into the other buffer while this step's stores are issued).
-// By antisymmetry E(b,c)[u] = -E(c,b)[u], the value a column (j,b,u) needs for row atom c is E_j[c][b][u]: for a fixed c
-// consecutive columns read consecutive doubles (conflict-free), and likewise E_i[c][b][t] on the row side.
-template <int NV>
-__global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int nat, int TJ, int NJB, int NBUF) {
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, EJ = a.ES, XS = a.XS;
+// Emit: CTA = a block of TJ geometries j (their E_j blocks and X_j rows stay RESIDENT in shared memory) x a run of NIB
+// geometries i, one per step; thread = one matrix column (j, b, u) of the block, which walks the 3 Nat rows (a, t) of the
+// step's geometry i: every row segment a warp writes is 256 contiguous bytes.  What streams per step is only E_i, X_i and
+// the TJ pair-term records of (i, j-block) -- (Nat^2 3 + D + TJ (3 Nat + 2)) doubles for TJ (3 Nat)^2 outputs -- as three
+// TMA bulk copies into the other buffer while this step's stores are issued.  (The first run-time version fixed i and
+// streamed the E_j blocks: 0.4 bytes in per byte out, and a third of all issue slots spent polling the mbarrier,
+// profiles/r02_gradk21_rt_v2_ncu.txt.)  Shared-memory reads are arranged to be conflict-free and few:
+//  * by antisymmetry E(b,c)[u] = -E(c,b)[u], the value column (j,b,u) needs for row atom c is E_j[c][b][u]: for a fixed c
+//    consecutive columns read consecutive doubles; likewise E_i[c][b][t] on the row side;
+//  * X_j - X_i is scattered once per step into an atom-pair matrix Dsq[j][c][b], so that -u_j[col] = sum_c E_j[c][b][u]
+//    Dsq[j][c][b] reads consecutive addresses instead of gathering descriptor elements;
+//  * the 3x3 diagonal blocks (a == b) need sum_c E_i(b,c)[t] E_j(b,c)[u], which is exactly minus the sum over the rows
+//    (c, t) of the products the thread forms anyway while walking the rows: it is accumulated on the way and the three
+//    a == b rows are stored last, instead of a separate prologue loop.
+__global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int nat, int TJ, int NIB) {
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, EJ = a.ES, XS = a.XS, NS = nat | 1;
   extern __shared__ __align__(128) double esm[];
-  double *Pb = esm;                                 // [NBUF][TJ*PW]
-  double *Xj = Pb + (size_t)NBUF * TJ * PW;         // [NBUF][TJ*XS]
-  double *Ejs = Xj + (size_t)NBUF * TJ * XS;        // [NBUF][TJ*EJ]
-  double *Xi = Ejs + (size_t)NBUF * TJ * EJ;        // [XS]
-  double *Ei = Xi + XS;                             // [EJ]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(Ei + EJ);  // [2]
+  double *Ejs = esm;                                // [TJ*EJ]     resident
+  double *Xj = Ejs + (size_t)TJ * EJ;               // [TJ*XS]     resident
+  double *Eib = Xj + (size_t)TJ * XS;               // [2][EJ]     streamed
+  double *Xib = Eib + 2 * (size_t)EJ;               // [2][XS]
+  double *Pb = Xib + 2 * (size_t)XS;                // [2][TJ*PW]
+  double *Dsq = Pb + 2 * (size_t)TJ * PW;           // [TJ][nat*NS]   Dsq[j][c*NS + b] = (X_j - X_i)[d_bc], 0 for b == c
+  uint64_t *bar = reinterpret_cast<uint64_t *>(Dsq + (((size_t)TJ * nat * NS + 1) & ~(size_t)1));  // [3]
+  unsigned short *ptab = reinterpret_cast<unsigned short *>(bar + 4);                               // [D] d -> (lo | hi << 8)
 
-  const int64_t i = blockIdx.y;
   const bool full = a.fill == KREG_FILL_FULL;
-  const int64_t jend = full ? a.ntr : i + 1;
-  const int64_t jb0 = (int64_t)blockIdx.x * ((int64_t)NJB * TJ);
-  if (jb0 >= jend) return;
-  const int64_t rbase = a.nv + i * G3;
-  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
-  const int nsteps = (int)(((jend - jb0 < (int64_t)NJB * TJ ? jend - jb0 : (int64_t)NJB * TJ) + TJ - 1) / TJ);
+  const int64_t jb = (int64_t)blockIdx.x * TJ;
+  // geometries i of this CTA: its chunk, clipped to the row range, and (lower fill) to i >= the block's first j
+  int64_t i_lo = (int64_t)blockIdx.y * NIB + a.p_i0, i_hi = i_lo + NIB;
+  if (i_hi > a.p_i1) i_hi = a.p_i1;
+  if (!full && i_lo < jb) i_lo = jb;
+  if (i_lo >= i_hi) return;
+  const int nsteps = (int)(i_hi - i_lo);
+  const int npair = (int)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
 
   const int tid = threadIdx.x;
-  const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
   const int64_t ld = a.ldk;
-  const int cols = TJ * G3;
-  // NV = 2: columns are paired on the absolute column parity (jb * G3 is even because TJ is even)
-  const int par = NV == 2 ? (int)(a.nv & 1) : 0;
-  int rr[NV], jl[NV], cc[NV], bb[NV];
-  bool okc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; v++) {
-    const int r = tid * NV + v - par;
-    okc[v] = r >= 0 && r < cols;
-    rr[v] = okc[v] ? r : 0;
-    jl[v] = rr[v] / G3;
-    cc[v] = rr[v] - jl[v] * G3;
-    bb[v] = cc[v] / 3;
-  }
+  const int cols = npair * G3;
+  const bool okc = tid < cols;
+  const int r = okc ? tid : 0;
+  const int jl = r / G3, cc = r - jl * G3, b = cc / 3;
+  const int64_t j = jb + jl;
 
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
     mbar_fence_init();
   }
-  for (int e = tid; e < D; e += blockDim.x) Xi[e] = a.Xc[i * XS + e];
-  for (int e = tid; e < EJ; e += blockDim.x) Ei[e] = a.E[i * a.ES + e];
   __syncthreads();
-
-  auto prefetch = [&](int n) {  // thread 0 only
-    const int64_t jb = jb0 + (int64_t)n * TJ;
-    const unsigned npair = (unsigned)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
-    const int buf = NBUF == 2 ? (n & 1) : 0;
-    const unsigned bp = npair * PW * 8, bx = npair * (unsigned)XS * 8, be = npair * (unsigned)EJ * 8;
-    mbar_arrive_expect_tx(&bar[buf], bp + bx + be);
+  auto prefetch = [&](int n) {  // thread 0 only: operands of step n (geometry i_lo + n)
+    const int64_t i = i_lo + n;
+    const int buf = n & 1;
+    const unsigned be = (unsigned)EJ * 8, bx = (unsigned)XS * 8, bp = (unsigned)npair * PW * 8;
+    mbar_arrive_expect_tx(&bar[buf], be + bx + bp);
+    bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
+    bulk_g2s(Xib + (size_t)buf * XS, a.Xc + i * XS, bx, &bar[buf]);
     bulk_g2s(Pb + (size_t)buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
-    bulk_g2s(Xj + (size_t)buf * TJ * XS, a.Xc + jb * XS, bx, &bar[buf]);
-    bulk_g2s(Ejs + (size_t)buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
   };
-  if (tid == 0) prefetch(0);
+  if (tid == 0) {
+    const unsigned be = (unsigned)npair * EJ * 8, bx = (unsigned)npair * XS * 8;
+    mbar_arrive_expect_tx(&bar[2], be + bx);
+    bulk_g2s(Ejs, a.E + jb * a.ES, be, &bar[2]);
+    bulk_g2s(Xj, a.Xc + jb * XS, bx, &bar[2]);
+    prefetch(0);
+  }
+  for (int e = tid; e < D; e += blockDim.x) {
+    int lo, hi;
+    pair_from_index(nat, e, lo, hi);
+    ptab[e] = (unsigned short)(lo | (hi << 8));
+  }
+  for (int e = tid; e < TJ * nat; e += blockDim.x) Dsq[(size_t)e * NS + (e % nat)] = 0.0;  // diagonals: never rewritten
+  mbar_wait(&bar[2], 0);
+  const double *ej = Ejs + (size_t)jl * EJ + cc;  // E_j[c][b][u] at ej[c * G3]  (= -E_j(b,c)[u])
 
   for (int n = 0; n < nsteps; n++) {
-    __syncthreads();  // NBUF = 2: everyone left buffer (n+1)&1 (read during step n-1); NBUF = 1: everyone left the buffer
-    if (NBUF == 2) {
-      if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
-    } else if (tid == 0 && n > 0) {
-      prefetch(n);
+    __syncthreads();  // everyone left the buffer about to be refilled, and Dsq of the previous step; ptab / Dsq ready
+    if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    const int buf = n & 1;
+    mbar_wait(&bar[buf], (n >> 1) & 1);
+    const int64_t i = i_lo + n;
+    const double *Xi = Xib + (size_t)buf * XS;
+    for (int e = tid; e < npair * D; e += blockDim.x) {  // consecutive threads -> consecutive d: conflict-free reads
+      const int jj = e / D, d = e - jj * D;
+      const int lo = ptab[d] & 0xff, hi = ptab[d] >> 8;
+      const double v = Xj[jj * XS + d] - Xi[d];
+      double *dq = Dsq + (size_t)jj * nat * NS;
+      dq[lo * NS + hi] = v;
+      dq[hi * NS + lo] = v;
     }
-    const int buf = NBUF == 2 ? (n & 1) : 0;
-    mbar_wait(&bar[buf], NBUF == 2 ? ((n >> 1) & 1) : (n & 1));
-    const int64_t jb = jb0 + (int64_t)n * TJ;
-    const double *pbuf = Pb + (size_t)buf * TJ * PW;
-    const double *xbuf = Xj + (size_t)buf * TJ * XS;
-    const double *ebuf = Ejs + (size_t)buf * TJ * EJ;
-
-    double kj[NV], c2[NV], kjd[NV][3];
-    bool work[NV];
-    const double *pb[NV], *ej[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-      const int64_t j = jb + jl[v];
-      work[v] = okc[v] && j < jend;
-      pb[v] = pbuf + jl[v] * PW;
-      ej[v] = ebuf + (size_t)jl[v] * EJ + cc[v];  // E_j[c][b][u] at ej[c * G3]  (= -E_j(b,c)[u])
-      kj[v] = pb[v][0];
-      const double *xj = xbuf + jl[v] * XS;
-      const double *ei = Ei + 3 * bb[v];          // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
-      const int b = bb[v];
-      double sj = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
-      if (work[v]) {
-        for (int c = 0; c < nat; c++) {
-          const double nej = ej[v][c * G3];
-          if (c != b) {
-            const int d = pair_index(nat, b < c ? b : c, b < c ? c : b);
-            sj = fma(nej, xj[d] - Xi[d], sj);
-          }
-          a0 = fma(-ei[c * G3 + 0], nej, a0);
-          a1 = fma(-ei[c * G3 + 1], nej, a1);
-          a2 = fma(-ei[c * G3 + 2], nej, a2);
-        }
-      }
-      c2[v] = (sj * a.inv_s2) * kj[v];  // -(k/s^2) u_j[col] / s^2
-      kjd[v][0] = -a0 * kj[v];
-      kjd[v][1] = -a1 * kj[v];
-      kjd[v][2] = -a2 * kj[v];
+    __syncthreads();
+    if (!okc || (!full && j > i)) continue;
+    const int64_t rbase = a.nv + i * G3;
+    const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
+    const double *pb = Pb + (size_t)buf * TJ * PW + jl * PW;
+    const double *ei = Eib + (size_t)buf * EJ + 3 * b;  // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
+    const double kj = pb[0];
+    double sj = 0.0;
+    {
+      const double *dq = Dsq + (size_t)jl * nat * NS + b;
+      for (int c = 0; c < nat; c++) sj = fma(ej[c * G3], dq[c * NS], sj);  // -u_j[col]
     }
-    // fast path: whole block wanted, not the diagonal block, and (NV = 2) both columns live and 16-byte aligned
-    const int64_t j_first = jb + jl[0], j_last = jb + jl[NV - 1];
-    bool fast = interior && work[0] && work[NV - 1] && j_first != i && j_last != i;
-    if (NV == 2) fast = fast && okc[0] && okc[1] && (ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
-    if (fast) {
-      double *dst = a.K + rbase * ld + a.nv + jb * G3 + rr[0];
+    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+    double *dst = a.K + rbase * ld + a.nv + j * G3 + cc;
+    if (interior && j != i) {
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0;  // sums of the J_i^T J_j products over the rows, per t
+      const double *ui = pb + 2;
       for (int aa = 0; aa < nat; aa++) {
-        double nej[NV];
-#pragma unroll
-        for (int v = 0; v < NV; v++) nej[v] = ej[v][aa * G3];
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-          const int q = aa * 3 + t;
-          double val[NV];
-#pragma unroll
-          for (int v = 0; v < NV; v++) {
-            const double e27 = -Ei[aa * G3 + 3 * bb[v] + t];
-            val[v] = fma(pb[v][2 + q], c2[v], kj[v] * (e27 * nej[v]));
-            if (aa == bb[v]) val[v] += kjd[v][t];
-          }
-          if (NV == 2)
-            *reinterpret_cast<double2 *>(dst) = make_double2(val[0], val[NV - 1]);
-          else
-            *dst = val[0];
-          dst += ld;
+        // explicit roundings (no FMA contraction of p into m): the boundary path below forms the same numbers, so a
+        // block comes out bit-identical whether it is written whole or clipped to a row slab (sharded assembly)
+        const double knej = __dmul_rn(kj, ej[aa * G3]);
+        const double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
+                     p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
+        m0 = __dadd_rn(m0, p0);
+        m1 = __dadd_rn(m1, p1);
+        m2 = __dadd_rn(m2, p2);
+        if (aa != b) {  // the three a == b rows are completed after the loop
+          KREG_CHECK_STORE(dst + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          KREG_CHECK(dst >= a.K + a.row_begin * ld, 3);
+          dst[0] = fma(ui[3 * aa + 0], c2, p0);
+          dst[ld] = fma(ui[3 * aa + 1], c2, p1);
+          dst[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
         }
+        dst += 3 * ld;
       }
+      // diagonal 3x3 block: (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u] = -(sum over rows of the products above)
+      dst = a.K + (rbase + 3 * b) * ld + a.nv + j * G3 + cc;
+      dst[0] = fma(ui[3 * b + 0], c2, -m0);
+      dst[ld] = fma(ui[3 * b + 1], c2, -m1);
+      dst[2 * ld] = fma(ui[3 * b + 2], c2, -m2);
     } else {
-      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal, columns one at a time
-#pragma unroll
-      for (int v = 0; v < NV; v++) {
-        if (!work[v]) continue;
-        const int64_t j = jb + jl[v];
-        double *dst = a.K + rbase * ld + a.nv + j * G3 + cc[v];
-        for (int q = 0; q < G3; q++) {
-          const int aa = q / 3, t = q - aa * 3;
-          const double e27 = -Ei[aa * G3 + 3 * bb[v] + t];
-          double val = fma(pb[v][2 + q], c2[v], kj[v] * (e27 * ej[v][aa * G3]));
-          if (aa == bb[v]) val += (t == 0 ? kjd[v][0] : t == 1 ? kjd[v][1] : kjd[v][2]);
-          if (j == i && q == cc[v]) val += a.lambdag;
-          const int64_t r = rbase + q;
-          if (r >= a.row_begin && r < a.row_end) dst[(int64_t)q * ld] = val;
+      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal
+      double m[3] = {0.0, 0.0, 0.0};
+      for (int aa = 0; aa < nat; aa++)
+        for (int t = 0; t < 3; t++) m[t] = __dadd_rn(m[t], __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
+      for (int q = 0; q < G3; q++) {
+        const int aa = q / 3, t = q - aa * 3;
+        double val = fma(pb[2 + q], c2, aa == b ? -(t == 0 ? m[0] : t == 1 ? m[1] : m[2])
+                                               : __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
+        if (j == i && q == cc) val += a.lambdag;
+        const int64_t rr = rbase + q;
+        if (rr >= a.row_begin && rr < a.row_end) {
+          KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          dst[(int64_t)q * ld] = val;
         }
       }
     }
@@ -1179,13 +1198,20 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
 
 // launch plan of the run-time kernels (KREG_RT_* environment variables override, for tuning runs)
 struct RtPlan {
-  int JT, TJ, NJB, NBUF, NV, threads;
+  int JT, TJ, NIB, threads;
   size_t pair_smem, emit_smem;
 };
 
 static int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
+}
+
+static size_t emit_smem_doubles(int nat, int XS, int EJ, int tj) {
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, NS = nat | 1;
+  size_t n = (size_t)tj * ((size_t)EJ + XS) + 2 * ((size_t)EJ + XS + (size_t)tj * PW) + (((size_t)tj * nat * NS + 1) & ~(size_t)1);
+  n += 4 + (D + 3) / 4;  // barriers, pair table (unsigned short)
+  return n;
 }
 
 static RtPlan rt_plan(int nat, const GradArgs &a) {
@@ -1200,59 +1226,40 @@ static RtPlan rt_plan(int nat, const GradArgs &a) {
   if (jt < 1) jt = 1;
   p.JT = env_int("KREG_RT_JT", (int)jt);
   p.pair_smem = (fixed + (((size_t)p.JT * DP + 1) & ~(size_t)1) + (((size_t)p.JT * PWS + 1) & ~(size_t)1)) * sizeof(double);
-  // emit: NV = 2 columns per thread; TJ even; TJ * G3 <= 510 columns; double-buffered while three CTAs still fit an SM
-  p.NV = env_int("KREG_RT_NV", 2);
-  const size_t per_geom = (size_t)PW + XS + EJ;
-  int tj = (256 * p.NV - 2) / G3;
-  tj &= ~1;
-  if (tj < 2) tj = 2;
+  // emit: one column per thread, up to 256 columns per j-block; two CTAs per SM when the resident block allows it
+  int tj = 256 / G3;
+  if (tj < 1) tj = 1;
   if (tj > 16) tj = 16;
-  const size_t budget = 72 * 1024 / 8;  // doubles: three CTAs per SM
-  const size_t own = (size_t)XS + EJ + 4;
-  auto fit = [&](int nb, size_t lim) {  // largest even TJ <= tj whose buffers fit `lim` doubles (0: none)
-    int t = tj;
-    while (t >= 2 && own + (size_t)nb * per_geom * t > lim) t -= 2;
-    return t < 2 ? 0 : t;
-  };
-  int nbuf = 2;
-  int t2 = fit(2, budget), t1 = fit(1, budget);
-  if (t2 >= tj / 2 && t2 >= 2) {
+  const size_t two_ctas = 112 * 1024 / 8, one_cta = 224 * 1024 / 8;
+  int t2 = tj;
+  while (t2 > 1 && emit_smem_doubles(nat, XS, EJ, t2) > two_ctas) t2--;
+  if (emit_smem_doubles(nat, XS, EJ, t2) <= two_ctas && 2 * t2 >= tj) {
     tj = t2;
-  } else if (t1 >= 2) {
-    nbuf = 1;
-    tj = t1;
-  } else {  // large molecules: one CTA per SM, single buffer, whatever fits
-    nbuf = 1;
-    t1 = fit(1, 220 * 1024 / 8);
-    tj = t1 >= 2 ? t1 : 2;
+  } else {
+    while (tj > 1 && emit_smem_doubles(nat, XS, EJ, tj) > one_cta) tj--;
   }
-  p.TJ = env_int("KREG_RT_TJ", tj) & ~1;
-  if (p.TJ < 2) p.TJ = 2;
-  p.NBUF = env_int("KREG_RT_NBUF", nbuf);
-  p.NJB = env_int("KREG_RT_NJB", 8);
-  const int need = (p.TJ * G3 + p.NV - 1) / p.NV + 1;
-  p.threads = ((need + 31) / 32) * 32;
-  p.emit_smem = (own + (size_t)p.NBUF * per_geom * p.TJ) * sizeof(double);
+  p.TJ = env_int("KREG_RT_TJ", tj);
+  if (p.TJ < 1) p.TJ = 1;
+  p.NIB = env_int("KREG_RT_NIB", 16);
+  if (p.NIB < 1) p.NIB = 1;
+  p.threads = ((p.TJ * G3 + 31) / 32) * 32;
+  p.emit_smem = emit_smem_doubles(nat, XS, EJ, p.TJ) * sizeof(double);
   return p;
 }
 
 static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, cudaStream_t st) {
   const RtPlan p = rt_plan(nat, a);
   if (p.threads > 256 || p.pair_smem > 227 * 1024 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
+  if (a.p_i1 <= a.p_i0) return KREG_OK;
   if (pair_terms) {
     KREG_CUDA_TRY(cudaFuncSetAttribute(pair_terms_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pair_smem));
     dim3 grid((unsigned)((a.ntr + p.JT - 1) / p.JT), (unsigned)a.ntr);
     pair_terms_rt_kernel<<<grid, 256, p.pair_smem, st>>>(a, nat, p.JT);
     KREG_LAUNCH_CHECK();
   }
-  dim3 grid((unsigned)((a.ntr + (int64_t)p.NJB * p.TJ - 1) / ((int64_t)p.NJB * p.TJ)), (unsigned)a.ntr);
-  if (p.NV == 2) {
-    KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
-    grad_emit_rt_kernel<2><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NJB, p.NBUF);
-  } else {
-    KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
-    grad_emit_rt_kernel<1><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NJB, p.NBUF);
-  }
+  dim3 grid((unsigned)((a.ntr + p.TJ - 1) / p.TJ), (unsigned)((a.p_i1 - a.p_i0 + p.NIB - 1) / p.NIB));
+  KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
+  grad_emit_rt_kernel<<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NIB);
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
@@ -1394,8 +1401,16 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
   if (!(ntrval == 0 || ntrval == ntrain) || !(ntrgr == 0 || ntrgr == G3 * ntrain) || ntrval + ntrgr == 0)
     return KREG_E_BADARG;
   const int64_t M = ntrval + ntrgr;
-  if (ldk < M || row_begin < 0 || row_end > M || row_begin > row_end) return KREG_E_BADARG;
+  if (row_begin < 0 || row_end > M || row_begin > row_end) return KREG_E_BADARG;
   if (fill != KREG_FILL_LOWER && fill != KREG_FILL_FULL) return KREG_E_BADARG;
+  {
+    // FILL_LOWER writes columns j <= i only (whole 3 Nat-wide diagonal blocks in the gradient part), so a row-slab buffer
+    // may have a row stride shorter than M: at least the defined length of its last row
+    int64_t need = M;
+    if (fill == KREG_FILL_LOWER && row_end < M)
+      need = row_end <= ntrval ? row_end : ntrval + (row_end - ntrval + G3 - 1) / G3 * G3;
+    if (ldk < need) return KREG_E_BADARG;
+  }
   // gradient models: the mirrored (FULL) layout is only produced for the whole matrix
   if (fill == KREG_FILL_FULL && ntrgr > 0 && !(row_begin == 0 && row_end == M)) return KREG_E_BADARG;
   int64_t gi0 = 0, gi1 = 0;
@@ -1470,6 +1485,7 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     g.ldk = ldk;
     g.P = reinterpret_cast<double *>(ws + w.off_P);
     g.p_i0 = gi0;
+    g.p_i1 = gi1;
     g.ES = (natoms * natoms * 3 + 1) & ~1;
     rc = launch_grad(natoms, g, st);
     if (rc) return rc;

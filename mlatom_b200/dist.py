@@ -47,10 +47,35 @@ def triangle_row_slabs(m: int, world_size: int, align: int = 1) -> List[Tuple[in
     return [(cuts[i], cuts[i + 1]) for i in range(world_size)]
 
 
+def sub_slabs(slab: Tuple[int, int], pieces: int, align: int = 1) -> List[Tuple[int, int]]:
+    """Split one rank's row slab [r0, r1) of the lower triangle into `pieces` consecutive row ranges of (nearly) equal
+    AREA -- the unit of the pipelined gather: a piece is sent while the next one is still being assembled."""
+    r0, r1 = slab
+    if r1 <= r0:
+        return []
+    cuts = [r0]
+    a0, a1 = r0 * (r0 + 1) / 2.0, r1 * (r1 + 1) / 2.0
+    for k in range(1, pieces):
+        t = a0 + (a1 - a0) * k / pieces
+        r = int(round((-1.0 + math.sqrt(1.0 + 8.0 * t)) / 2.0))
+        if align > 1:
+            r = int(round(r / align)) * align
+        cuts.append(min(max(r, cuts[-1]), r1))
+    cuts.append(r1)
+    return [(cuts[i], cuts[i + 1]) for i in range(pieces) if cuts[i + 1] > cuts[i]]
+
+
+def piece_width(b: int, m: int) -> int:
+    """Stored row length of a piece that ends at row b: only columns j < b of the lower triangle are defined, so a piece
+    travels as a (rows x b) trapezoid instead of full M-wide rows (half the NVLink bytes on average); even, so that the
+    assembly kernels keep their 16-byte stores."""
+    return min(m + (m & 1), b + (b & 1))
+
+
 def gather_row_slabs(k_full: Optional[torch.Tensor], slab: torch.Tensor, slabs: Sequence[Tuple[int, int]],
                      root: int = 0) -> None:
-    """Point-to-point gather of row slabs into the root's matrix.  Rank r owns rows slabs[r] in `slab`
-    ((r1-r0) x M, contiguous); the root receives each directly into k_full[r0:r1] (no staging copy)."""
+    """Point-to-point gather of whole, full-width row slabs into the root's matrix (kept for callers that hold their
+    slab as (r1-r0) x M; the sharded assembly below sends trapezoid pieces instead)."""
     rank, ws = world()
     if ws == 1:
         return
@@ -69,23 +94,51 @@ def gather_row_slabs(k_full: Optional[torch.Tensor], slab: torch.Tensor, slabs: 
 
 
 def build_kernel_matrix_sharded(build_rows: Callable[[int, int, torch.Tensor, int], None], m: int, device,
-                                root: int = 0, align: int = 1) -> Optional[torch.Tensor]:
-    """Assemble K on all ranks, gather on `root`.  `build_rows(r0, r1, out, row_offset)` must fill rows
-    [r0, r1) of the matrix into `out` whose row 0 is matrix row `row_offset`.  Returns K on the root, None
-    elsewhere."""
+                                root: int = 0, align: int = 1, pieces: int = 4,
+                                stats: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """Assemble the lower triangle of K on all ranks, gather on `root`.  `build_rows(r0, r1, out, row_offset)` must fill
+    rows [r0, r1) (columns j <= i) into `out`, whose row 0 is matrix row `row_offset` and whose row stride may be
+    SHORTER than M (>= the last row's defined length).  Returns K on the root, None elsewhere.
+
+    Every rank cuts its slab into `pieces` equal-area sub-slabs, each in its own contiguous trapezoid buffer; a piece
+    is handed to the communication stream (NCCL runs P2P on its own stream, ordered after the work already queued on
+    the caller's stream) as soon as its assembly kernels are queued, so the transfer of piece s overlaps the assembly
+    of piece s+1.  The root receives into staging buffers and scatters them into its M x M matrix with one strided
+    device copy per piece.  `stats` (optional dict) receives the byte count sent to the root."""
     rank, ws = world()
     slabs = triangle_row_slabs(m, ws, align)
-    r0, r1 = slabs[rank]
+    plans = [sub_slabs(slabs[r], pieces, align) for r in range(ws)]
     if rank == root:
         k = torch.empty((m, m), dtype=torch.float64, device=device)
+        stages, reqs = [], []
+        for r in range(ws):  # post every receive first: the senders' pieces arrive while the root assembles its own slab
+            if r == root:
+                continue
+            for (a, b) in plans[r]:
+                st = torch.empty((b - a, piece_width(b, m)), dtype=torch.float64, device=device)
+                stages.append((a, b, st))
+                reqs.append(dist.irecv(st, r))
+        r0, r1 = slabs[root]
         if r1 > r0:
             build_rows(r0, r1, k, 0)
-        gather_row_slabs(k, k[r0:r1], slabs, root)
+        nbytes = 0
+        for (a, b, st), req in zip(stages, reqs):
+            req.wait()
+            k[a:b, :b].copy_(st[:, :b])
+            nbytes += st.numel() * 8
+        if stats is not None:
+            stats["gather_bytes"] = nbytes
         return k
-    slab = torch.empty((max(r1 - r0, 0), m), dtype=torch.float64, device=device)
-    if r1 > r0:
-        build_rows(r0, r1, slab, r0)
-    gather_row_slabs(None, slab, slabs, root)
+    reqs, keep = [], []
+    for (a, b) in plans[rank]:
+        buf = torch.empty((b - a, piece_width(b, m)), dtype=torch.float64, device=device)
+        build_rows(a, b, buf, a)
+        reqs.append(dist.isend(buf, root))
+        keep.append(buf)
+    for req in reqs:
+        req.wait()
+    if stats is not None:
+        stats["gather_bytes"] = sum(t.numel() * 8 for t in keep)
     return None
 
 
@@ -130,23 +183,25 @@ def grid_shard(points: Sequence, rank: Optional[int] = None, world_size: Optiona
 
 
 def allgather_losses(local: dict, n_points: int) -> List[float]:
-    """local: {point index: loss} -> list of all losses on every rank."""
+    """local: {point index: loss} -> list of all losses on every rank.  Which points a rank evaluated travels as an
+    explicit mask (a NaN loss -- a NaN alpha -- is a RESULT, not a marker): evaluated NaN losses come back as +inf so
+    that optimize_grid's strict '<' stays well defined and a failed point can never win; points nobody evaluated stay
+    NaN."""
     _, ws = world()
-    vals = torch.full((n_points,), float("nan"), dtype=torch.float64)
+    vals = torch.zeros(n_points, dtype=torch.float64)
+    mask = torch.zeros(n_points, dtype=torch.float64)
+    bad = torch.zeros(n_points, dtype=torch.float64)  # evaluated, but +inf or NaN
     for i, v in local.items():
-        vals[i] = v
-    if ws == 1:
-        return vals.tolist()
-    backend = dist.get_backend()
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    vals = vals.to(dev)
-    mask = (~torch.isnan(vals)).to(torch.float64)
-    # +inf (a grid point whose matrix was not positive definite) must survive the sum: reduce finite values and
-    # the "is infinite" flags separately
-    inf = torch.isinf(vals).to(torch.float64)
-    filled = torch.nan_to_num(vals, nan=0.0, posinf=0.0, neginf=0.0)
-    dist.all_reduce(filled)
-    dist.all_reduce(mask)
-    dist.all_reduce(inf)
-    out = torch.where(inf > 0, torch.full_like(filled, float("inf")), filled)
-    return torch.where(mask > 0, out, torch.full_like(filled, float("nan"))).cpu().tolist()
+        mask[i] = 1.0
+        if v != v or v == float("inf"):
+            bad[i] = 1.0
+        else:
+            vals[i] = v
+    if ws > 1:
+        backend = dist.get_backend()
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        packed = torch.stack((vals, mask, bad)).to(dev)
+        dist.all_reduce(packed)
+        vals, mask, bad = packed.cpu()
+    out = torch.where(bad > 0, torch.full_like(vals, float("inf")), vals)
+    return torch.where(mask > 0, out, torch.full_like(vals, float("nan"))).tolist()

@@ -140,7 +140,9 @@ def build_kernel_matrix(
     if out is None:
         out = torch.empty((m, m), dtype=F64, device=xyz.device)
     r0, r1 = (0, m) if rows is None else rows
-    assert out.is_cuda and out.dtype == F64 and out.stride(1) == 1 and out.shape[1] >= m
+    # a slab buffer may be narrower than M under FILL_LOWER: only columns j < (row range end) are ever written
+    assert out.is_cuda and out.dtype == F64 and out.stride(1) == 1
+    assert out.shape[1] >= (m if fill != FILL_LOWER else min(m, r1))
     assert out.shape[0] >= r1 - row_offset and row_offset <= r0
     ws_bytes = build_workspace_bytes(nat, ntr, ntrgr, None if rows is None else (r0, r1))
     if workspace is not None and workspace.numel() >= ws_bytes and workspace.device == xyz.device:

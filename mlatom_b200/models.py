@@ -260,32 +260,63 @@ class kreg:
                 g_pred = pk["xyz_derivative_property_to_predict"] = f"estimated_{g_learn}"
         return tk, pk, p_learn, g_learn, p_pred, g_pred
 
+    def cross_validation(self, cv_splits_molecular_databases=None, training_kwargs=None, prediction_kwargs=None):
+        """k-fold cross-validation (mlatom/model_cls.py:742-770): for every split, train on the union of the others and
+        predict the split; predictions are left in the splits' molecules."""
+        tk, pk = dict(training_kwargs or {}), dict(prediction_kwargs or {})
+        splits = list(cv_splits_molecular_databases)
+        for ii, held_out in enumerate(splits):
+            sub = type(held_out)()
+            for jj, other in enumerate(splits):
+                if ii != jj:
+                    sub.molecules += other.molecules
+            self.reset()
+            self.train(molecular_database=sub, **tk)
+            self.predict(molecular_database=held_out, **pk)
+
     def calculate_validation_loss(self, training_kwargs=None, prediction_kwargs=None,
+                                  cv_splits_molecular_databases=None, calculate_CV_split_errors=False,
                                   subtraining_molecular_database=None, validation_molecular_database=None,
                                   validation_loss_function=None, validation_loss_function_kwargs={}, debug=False,
                                   **unsupported):
-        """Hold-out validation loss: RMSE, geometric mean over scalar and XYZ-vectorial properties
-        (mlatom/model_cls.py:577-585)."""
-        for k, v in unsupported.items():
+        """Validation loss for the current hyper-parameters: RMSE, geometric mean over scalar and XYZ-vectorial
+        properties (mlatom/model_cls.py:450-607) -- hold-out (sub-training / validation databases) or k-fold
+        cross-validation over ``cv_splits_molecular_databases`` (then over all splits' predictions together, and with
+        ``calculate_CV_split_errors`` also per split, returned as ``(error, [split errors])``)."""
+        for k, v in unsupported.items():  # the ml_database variants (cv_splits_ml_databases, subtraining_ml_database, ...)
             if v is not None and v is not False:
-                raise NotImplementedError(f"{k} is not supported by mlatom_b200.kreg")
+                raise NotImplementedError(f"{k} is not supported by mlatom_b200.kreg (use the molecular_database arguments)")
         tk, pk, p_learn, g_learn, p_pred, g_pred = self._names(training_kwargs, prediction_kwargs)
-        self.holdout_validation(subtraining_molecular_database, validation_molecular_database, tk, pk)
-        vdb = validation_molecular_database
-        total = 1.0
-        if p_learn is not None:
-            total *= rmse(vdb.get_properties(p_pred), vdb.get_properties(p_learn))
-        if g_learn is not None:
-            total *= rmse(vdb.get_xyz_vectorial_properties(g_pred), vdb.get_xyz_vectorial_properties(g_learn))
-        if p_learn is not None and g_learn is not None:
-            total = float(np.sqrt(total))
-        error = total if validation_loss_function is None else validation_loss_function(**validation_loss_function_kwargs)
+
+        def geom_rmse(dbs):
+            total = 1.0
+            if p_learn is not None:
+                total *= rmse(np.concatenate([np.asarray(d.get_properties(p_pred)).reshape(-1) for d in dbs]),
+                              np.concatenate([np.asarray(d.get_properties(p_learn)).reshape(-1) for d in dbs]))
+            if g_learn is not None:
+                total *= rmse(np.concatenate([np.asarray(d.get_xyz_vectorial_properties(g_pred)).reshape(-1) for d in dbs]),
+                              np.concatenate([np.asarray(d.get_xyz_vectorial_properties(g_learn)).reshape(-1) for d in dbs]))
+            if p_learn is not None and g_learn is not None:
+                total = float(np.sqrt(total))
+            return total
+
+        split_errors = None
+        if cv_splits_molecular_databases is None:
+            self.holdout_validation(subtraining_molecular_database, validation_molecular_database, tk, pk)
+            scored = [validation_molecular_database]
+        else:
+            self.cross_validation(cv_splits_molecular_databases, tk, pk)
+            scored = list(cv_splits_molecular_databases)
+        error = geom_rmse(scored) if validation_loss_function is None else validation_loss_function(**validation_loss_function_kwargs)
         self.reset()
+        if cv_splits_molecular_databases is not None and calculate_CV_split_errors:
+            split_errors = [geom_rmse([d]) if validation_loss_function is None
+                            else validation_loss_function(**validation_loss_function_kwargs) for d in scored]
         if debug:
             for name in self.hyperparameters.keys():
                 print(f"  Hyperparameter {name} = {self.hyperparameters[name].value}")
             print(f"    Validation loss: {error}")
-        return error
+        return (error, split_errors) if split_errors is not None else error
 
     def _grid(self, names, grid_size):
         slices = []
@@ -303,7 +334,7 @@ class kreg:
                                  subtraining_molecular_database=None, validation_molecular_database=None,
                                  optimization_algorithm=None, optimization_algorithm_kwargs={}, maximum_evaluations=10000,
                                  validation_loss_function=None, validation_loss_function_kwargs={}, debug=False,
-                                 fused=True, **unsupported):
+                                 fused=True, cv_splits_molecular_databases=None, **unsupported):
         """Minimise the hold-out validation loss over the named hyper-parameters, then retrain with the
         winners (mlatom/model_cls.py:609-727).  'grid' over 'lambda'/'sigma' takes the fused device path
         (K assembled once per sigma, re-factorised per lambda, validation kernels stay in HBM); every other
@@ -314,7 +345,8 @@ class kreg:
                    subtraining_molecular_database=subtraining_molecular_database,
                    validation_molecular_database=validation_molecular_database,
                    validation_loss_function=validation_loss_function,
-                   validation_loss_function_kwargs=validation_loss_function_kwargs, debug=debug, **unsupported)
+                   validation_loss_function_kwargs=validation_loss_function_kwargs, debug=debug,
+                   cv_splits_molecular_databases=cv_splits_molecular_databases, **unsupported)
 
         def loss_at(values):
             for name, v in zip(names, values):
@@ -329,7 +361,7 @@ class kreg:
             if algo in ("grid", "brute"):
                 slices = self._grid(names, optimization_algorithm_kwargs.get("grid_size", 9))
                 can_fuse = (fused and set(names) <= {"lambda", "sigma"} and validation_loss_function is None
-                            and not any(v for v in unsupported.values()))
+                            and cv_splits_molecular_databases is None and not any(v for v in unsupported.values()))
                 if can_fuse:
                     table = self._fused_grid_losses(names, slices, training_kwargs, prediction_kwargs,
                                                     subtraining_molecular_database, validation_molecular_database)
@@ -346,6 +378,22 @@ class kreg:
                                                                   prediction_kwargs, subtraining_molecular_database,
                                                                   validation_molecular_database)
                 params = [best[n] for n in names]
+            elif algo == "tpe":
+                # Tree-structured Parzen estimator through hyperopt, exactly the reference's call (model_cls.py:688-727);
+                # hyperopt is an optional dependency there too (a plain ImportError if it is not installed)
+                import hyperopt
+
+                def space_of(key):
+                    hp = self.hyperparameters[key]
+                    if hp.optimization_space == "log":
+                        return hyperopt.hp.loguniform(key, np.log(hp.minval), np.log(hp.maxval))
+                    if hp.optimization_space == "linear":
+                        return hyperopt.hp.uniform(key, hp.minval, hp.maxval)
+                    raise NotImplementedError(hp.optimization_space)
+
+                res = hyperopt.fmin(fn=lambda d: loss_at([d[k] for k in names]), space={k: space_of(k) for k in names},
+                                    algo=hyperopt.tpe.suggest, max_evals=maximum_evaluations, show_progressbar=False)
+                params = [res[k] for k in names]
             else:
                 import scipy.optimize
 

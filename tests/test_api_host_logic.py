@@ -367,3 +367,60 @@ def test_active_learning_trainer_call_sequence(fake_engine, tmp_path):
         assert len(uq) == 6 and all(np.isfinite(uq))
     finally:
         os.chdir(cwd)
+
+
+def test_cross_validation_loss_matches_the_reference_class(fake_engine, oracle, tmp_path):
+    """k-fold cross-validation (model_cls.py:742-770 and the CV branch of calculate_validation_loss :529-575): this
+    package's kreg against the REFERENCE's own kreg class driving the same backend, on the reference's data objects."""
+    ref_data = reference_mlatom()
+    if ref_data is None:
+        pytest.skip("reference checkout not available")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import make_golden_grid as G
+
+    saved = sys.modules.get("mlatom.kreg_api")
+    try:
+        ref_models, _ = G.reference_kreg_class(oracle)  # binds mlatom.kreg_api.KREG_API to this package's class
+        splits_a = [make_db(ref_data, 5, 9, 20 + k)[0] for k in range(3)]
+        splits_b = [make_db(ref_data, 5, 9, 20 + k)[0] for k in range(3)]
+        tk = {"property_to_learn": "energy", "xyz_derivative_property_to_learn": "energy_gradients"}
+        pk = {"property_to_predict": "estimated_energy", "xyz_derivative_property_to_predict": "estimated_energy_gradients"}
+        cwd = os.getcwd()
+        os.chdir(tmp_path)
+        try:
+            ref = ref_models.kreg(model_file="cv_ref", hyperparameters={"sigma": 1.3, "lambda": 1e-7})
+            ref.equilibrium_molecule = splits_a[0].molecules[0]
+            want, want_splits = ref.calculate_validation_loss(training_kwargs=dict(tk), prediction_kwargs=dict(pk),
+                                                              cv_splits_molecular_databases=splits_a,
+                                                              calculate_CV_split_errors=True)
+        finally:
+            os.chdir(cwd)
+        ours = M.kreg(model_file=str(tmp_path / "cv_ours"), hyperparameters={"sigma": 1.3, "lambda": 1e-7})
+        ours.equilibrium_molecule = splits_b[0].molecules[0]
+        got, got_splits = ours.calculate_validation_loss(training_kwargs=dict(tk), prediction_kwargs=dict(pk),
+                                                         cv_splits_molecular_databases=splits_b,
+                                                         calculate_CV_split_errors=True)
+        assert abs(got - want) <= 1e-12 * want
+        assert np.allclose(got_splits, want_splits, rtol=1e-12, atol=0)
+        # and through the optimiser: a 3 x 3 grid scored by cross-validation picks the same point
+        for m_, cls_splits in ((ref, splits_a), (ours, splits_b)):
+            m_.hyperparameters["lambda"].minval, m_.hyperparameters["lambda"].maxval = 1e-9, 1e-3
+            m_.hyperparameters["sigma"].minval, m_.hyperparameters["sigma"].maxval = 0.5, 8.0
+        os.chdir(tmp_path)
+        try:
+            ref.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="grid",
+                                         optimization_algorithm_kwargs={"grid_size": 3}, training_kwargs=dict(tk),
+                                         prediction_kwargs=dict(pk), cv_splits_molecular_databases=splits_a)
+        finally:
+            os.chdir(cwd)
+        ours.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="grid",
+                                      optimization_algorithm_kwargs={"grid_size": 3}, training_kwargs=dict(tk),
+                                      prediction_kwargs=dict(pk), cv_splits_molecular_databases=splits_b)
+        assert ours.hyperparameters["lambda"].value == ref.hyperparameters["lambda"].value
+        assert ours.hyperparameters["sigma"].value == ref.hyperparameters["sigma"].value
+        assert abs(ours.validation_loss - ref.validation_loss) <= 1e-12 * ref.validation_loss
+    finally:
+        if saved is None:
+            sys.modules.pop("mlatom.kreg_api", None)
+        else:
+            sys.modules["mlatom.kreg_api"] = saved

@@ -49,13 +49,32 @@ def _worker(rank, ws, port, tmp):
         ref = torch.arange(m * m, dtype=torch.float64).reshape(m, m)
 
         def build_rows(r0, r1, out, row_offset):
-            out[r0 - row_offset:r1 - row_offset] = ref[r0:r1]
+            # like the assembly kernels under FILL_LOWER: only j <= i is written; the buffer may be narrower than m
+            w = min(out.shape[1], m)
+            view = out[r0 - row_offset:r1 - row_offset, :w]
+            view.fill_(float("nan"))
+            keep = torch.tril(torch.ones(r1 - r0, w, dtype=torch.bool), diagonal=r0)
+            view[keep] = ref[r0:r1, :w][keep]
 
-        k = kd.build_kernel_matrix_sharded(build_rows, m, torch.device("cpu"), root=0)
+        stats = {}
+        k = kd.build_kernel_matrix_sharded(build_rows, m, torch.device("cpu"), root=0, pieces=3, stats=stats)
         if rank == 0:
-            assert torch.equal(k, ref)
+            assert torch.equal(torch.tril(k), torch.tril(ref))
+            assert 0 < stats["gather_bytes"] < 8 * m * m  # trapezoids, not full-width rows
         else:
-            assert k is None
+            assert k is None and stats["gather_bytes"] > 0
+        # pieces: equal-area split of a slab, aligned
+        for slab, pieces, align in (((1000, 5000), 4, 1), ((27 * 10, 27 * 200), 5, 27), ((3, 4), 4, 1)):
+            sub = kd.sub_slabs(slab, pieces, align)
+            assert sub[0][0] == slab[0] and sub[-1][1] == slab[1]
+            assert all(sub[i][1] == sub[i + 1][0] for i in range(len(sub) - 1))
+            assert all(a % align == 0 for a, _ in sub)
+            if slab[1] - slab[0] > 100:
+                areas = [b * (b + 1) / 2 - a * (a + 1) / 2 for a, b in sub]
+                assert max(areas) / (sum(areas) / len(areas)) < 1.1
+        # a NaN loss is a result, not "not evaluated": it must come back as +inf, unevaluated points as NaN
+        got = kd.allgather_losses({0: float("nan")} if rank == 0 else {1: 2.0}, 3)
+        assert got[0] == float("inf") and got[1] == 2.0 and got[2] != got[2]
         # alpha broadcast
         alpha = torch.arange(5, dtype=torch.float64) if rank == 0 else torch.zeros(5, dtype=torch.float64)
         kd.broadcast_tensor(alpha, 0)

@@ -277,3 +277,33 @@ def test_active_learning_sampler_on_device(M):
         assert (fin["uq"][fin["uncertain"]] > thr).all() and (fin["uq"][~fin["uncertain"]] <= thr).all()
         assert int(fin["stop_step"].max()) <= 300
     assert all(torch.equal(a, c) for a, c in zip(runs[True], runs[False]))
+
+
+def test_batched_md_reproduces_the_reference_md_driver():
+    """tests/golden/md/md_nve_nat9.npz is a 100-step NVE trajectory produced by the REFERENCE's own driver, mlatom.md
+    (md.py:158-205), on a KREG model trained through this package's API (tools/make_golden_md.py).  BatchedNVE -- fused
+    velocity-Verlet kernels + kreg_predict replayed as one CUDA graph -- must reproduce it: positions to 1e-9 Angstrom,
+    energies to 1e-9 Hartree, for a single trajectory and for every member of a batch of identical ones."""
+    from mlatom_b200 import engine, md
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "md", "md_nve_nat9.npz"))
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    c_acc, c_kin = md.mlatom_unit_factors()
+    assert abs(c_acc - float(z["c_acc"])) <= 1e-15 * c_acc and abs(c_kin - float(z["c_kin"])) <= 1e-15 * c_kin
+    pm = engine.PackedModel.from_training_set(t(z["xyz_train"]), engine.xeq(t(z["req"])), t(z["alpha"]), float(z["sigma"]),
+                                              float(z["prior"]), int(z["ntrval"]), int(z["ntrgr"]))
+    nsteps = int(z["nsteps"])
+    for batch, use_graph in ((1, True), (1, False), (64, True)):
+        x0 = t(np.repeat(z["x0"][None], batch, 0))
+        v0 = t(np.repeat(z["v0"][None], batch, 0))
+        sim = md.BatchedNVE(pm, x0, v0, t(z["masses"]), dt=float(z["dt"]), use_graph=use_graph, units="mlatom")
+        assert abs(sim.epot[0].item() - z["epot"][0]) <= 1e-9 and abs(sim.ekin[0].item() - z["ekin"][0]) <= 1e-12
+        out = sim.run(nsteps, record_every=1, record_xyz=True)
+        traj = out["trajectory"].cpu().numpy()           # (nsteps, B, Nat, 3)
+        en = out["energies"].cpu().numpy()               # (nsteps, 2, B)
+        for k in range(batch if batch == 1 else 3):
+            assert np.abs(traj[:, k] - z["xyz"][1:]).max() <= 1e-9, (batch, use_graph, np.abs(traj[:, k] - z["xyz"][1:]).max())
+            assert np.abs(en[:, 0, k] - z["epot"][1:]).max() <= 1e-9 and np.abs(en[:, 1, k] - z["ekin"][1:]).max() <= 1e-9
+        assert np.abs(out["velocities"][0].cpu().numpy() - z["vel"][-1]).max() <= 1e-9
+        if batch > 1:
+            assert (out["xyz"] - out["xyz"][0]).abs().max().item() <= 1e-12  # members of the batch stay together
