@@ -293,8 +293,8 @@ def kbuild_sharded(engine, dev, world, rank, barrier, max_over_ranks):
     out = {"workload": f"cfg3: K 50k x 50k values (lower triangle, 4*M*(M+1) = {4.0 * m * (m + 1) / 1e9:.1f} GB), "
                        f"row slabs over {world} GPU(s), gathered onto rank 0",
            "assembly_ms_max_over_ranks": build_ms, "assembly_gb_per_s_aggregate": 4.0 * m * (m + 1) / build_ms * 1e-6,
-           "assembly_plus_gather_ms": total, "gather_bytes_into_root": gbytes,
-           "gather_ms_not_hidden": max(total - build_ms, 0.0),
+           "assembly_plus_gather_ms": total if world > 1 else None, "gather_bytes_into_root": gbytes,
+           "gather_ms_not_hidden": max(total - build_ms, 0.0) if world > 1 else None,
            "inbound_gb_per_s": (gbytes / (max(total - build_ms, 1e-3)) * 1e-6) if world > 1 else None,
            "nvlink_reference_gb_per_s": 770.0,
            "note": "slabs travel as trapezoids (columns j <= i only), in 4 equal-area pieces per rank, each sent while the "

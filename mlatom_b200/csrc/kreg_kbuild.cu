@@ -46,7 +46,11 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
   // Row-slab FULL assembly of the values block computes K[i][j] and K[j][i] in different tiles (possibly on different
   // GPUs): there the exponent is formed symmetrically, c1 s + (b_i + b_j) with s = X'_i.X'_j alone (the accumulators were
   // started from zero), so that the two are bit-identical like the reference's mirrored copy (KREG.f90:317-318).
+#ifdef KREG_DEBUG_ZEROINIT
+  const bool symx = true;
+#else
   const bool symx = a.symmetric && a.all_cols;
+#endif
   // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
   const bool interior = !diag_tile && !symx && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
                         j0 + kTileJ <= a.nb && (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
@@ -188,6 +192,10 @@ __device__ __forceinline__ void lin_tile_epilogue(const ValuesArgs &a, double (&
 //   MULTI = true: the descriptor is walked in chunks of KC k-steps; a stage = the A chunk and the B chunk of one
 //           (tile, chunk) step, both contiguous in the chunk-major copy of the workspace; column biases travel with chunk 0
 //           into a slot selected by tile parity.
+#ifdef KREG_DEBUG_BIAS
+__device__ unsigned long long g_bias_dbg[8];
+#endif
+
 template <int KC, bool MULTI, int EPI = EPI_K>
 __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
@@ -252,8 +260,13 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       if (ch == 0) bulk_g2s(bBs + (tile & 1) * kTileJ, a.biasB + j0, bb, &full[s]);
     } else {
       mbar_arrive_expect_tx(&full[s], bx + bb);
+#ifdef KREG_DEBUG_SWAP
+      bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
+      bulk_g2s(st, a.XB + j0 * a.XS, bx, &full[s]);
+#else
       bulk_g2s(st, a.XB + j0 * a.XS, bx, &full[s]);
       bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
+#endif
     }
   };
   if (tid == 0) {
@@ -263,6 +276,7 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
     bulk_g2s(bA, a.biasA + i0, bb, fullA);
     for (int s = 0; s < NST && s < nsteps; s++) issue(s);
   }
+  __syncwarp();
 
   double S[4][4][2];
   const bool lower_only = a.symmetric && !a.all_cols && !a.mirror;
@@ -270,7 +284,11 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
 
   // accumulators start from the column term of their tile (-n_j/2; an arbitrary additive term for EPI_LIN), which
   // arrived with the tile's first stage: the epilogue then has no per-element bias add
+#ifdef KREG_DEBUG_ZEROINIT  /* experiment: accumulators always start from zero, the column term is added in the epilogue */
+  const bool zero_init = true;
+#else
   const bool zero_init = EPI == EPI_K && a.symmetric && a.all_cols;  // see values_tile_epilogue: symmetric exponent
+#endif
   auto init_acc = [&](const double *bcol) {
 #pragma unroll
     for (int nt = 0; nt < 4; nt++) {
@@ -293,10 +311,17 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
   };
 
   for (int step = 0; step < nsteps; step++) {
-    // producer duty: refill the slot every warp left in the previous iteration
-    if (tid == 0 && step >= 1 && step - 1 + NST < nsteps) {
-      mbar_wait(&empty[(step - 1) % NST], ((step - 1) / NST) & 1);
-      issue(step - 1 + NST);
+    // producer duty: refill the slot every warp left in the previous iteration.  The branch is warp-uniform with the
+    // single issuing lane inside it and an explicit reconvergence after it: with a bare `if (tid == 0)` the other
+    // lanes of warp 0 ran ahead into the tile code while lane 0 was still issuing, and the uniform registers the two
+    // paths share were clobbered -- warp 0's 32 x 32 sub-tile came out wrong in every tile after the first refill
+    // (found with tools/debug_kvals.py once the accumulators started from the column term instead of zero).
+    if (warp == 0 && step >= 1 && step - 1 + NST < nsteps) {
+      if (lane == 0) {
+        mbar_wait(&empty[(step - 1) % NST], ((step - 1) / NST) & 1);
+        issue(step - 1 + NST);
+      }
+      __syncwarp();
     }
     const int s = step % NST;
     mbar_wait(&full[s], (step / NST) & 1);
@@ -306,7 +331,37 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       const int tile = step / nch;
       if (step - tile * nch == 0) init_acc(bBs + (tile & 1) * kTileJ);
     } else {
+#ifdef KREG_DEBUG_SLEEP
+      __nanosleep(4000);
+#endif
+#ifdef KREG_DEBUG_GLOBALBIAS
+      init_acc(a.biasB + (tj_lo + step) * kTileJ);
+#else
       init_acc(bBs + s * kTileJ);
+#endif
+#ifdef KREG_DEBUG_BIAS
+      {
+        const int c = wj * 32 + 2 * q;
+        const double early = bBs[s * kTileJ + c];
+        const double truth = a.biasB[(tj_lo + step) * kTileJ + c];
+        __nanosleep(3000);
+        const double late = *(volatile double *)(bBs + s * kTileJ + c);
+        const int64_t jj = (tj_lo + step) * kTileJ + c;
+        if (jj < a.nb) {
+          atomicAdd(&g_bias_dbg[3], 1ull);
+          if (early != truth) atomicAdd(&g_bias_dbg[0], 1ull);
+          if (late != truth) atomicAdd(&g_bias_dbg[1], 1ull);
+          if (early != late) atomicAdd(&g_bias_dbg[2], 1ull);
+          if (early != truth && step == 0) atomicAdd(&g_bias_dbg[4], 1ull);
+          if (early != truth && step >= NST) atomicAdd(&g_bias_dbg[5], 1ull);
+          if (early != truth) {
+            // does the wrong value belong to another tile of this CTA?
+            for (int t = 0; t < 8; t++)
+              if (early == a.biasB[(tj_lo + t) * kTileJ + c] && t != step) atomicAdd(&g_bias_dbg[6], 1ull);
+          }
+        }
+      }
+#endif
     }
 #pragma unroll
     for (int ks = 0; ks < KC; ks++) {
@@ -880,6 +935,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
     bulk_g2s(Ejs + buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
   };
   if (tid == 0) prefetch(0);
+  __syncwarp();
   double e27[G3P];  // E_i(b, c)[t] for all (c, t);  E_i(a, b)[t] = -E_i(b, a)[t]
   if (colthread) {
 #pragma unroll
@@ -889,6 +945,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
   for (int n = 0; n < nsteps; n++) {
     __syncthreads();  // everyone left buffer (n+1)&1 (read during step n-1)
     if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    __syncwarp();  // warp 0 reconverges before the tile code (uniform registers are shared with the issuing lane)
     mbar_wait(&bar[n & 1], (n >> 1) & 1);  // step n's operands have landed
     const int64_t jb = jb0 + (int64_t)n * TJ;
     const int64_t j = jb + jl;
@@ -1055,13 +1112,20 @@ __global__ void __launch_bounds__(256) pair_terms_rt_kernel(const GradArgs a, in
 //  * the 3x3 diagonal blocks (a == b) need sum_c E_i(b,c)[t] E_j(b,c)[u], which is exactly minus the sum over the rows
 //    (c, t) of the products the thread forms anyway while walking the rows: it is accumulated on the way and the three
 //    a == b rows are stored last, instead of a separate prologue loop.
-__global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int nat, int TJ, int NIB) {
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, EJ = a.ES, XS = a.XS, NS = nat | 1;
+// NAT_CT > 0 fixes the molecule size at compile time (11..24 atoms: every stride below becomes an immediate and the row
+// loops unroll -- 8 instead of 22 instructions per element, profiles/r02_gradk21_rt_v3_ncu.txt); NAT_CT = 0 takes it at
+// run time (any size).
+template <int NAT_CT>
+__global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int nat_rt, int TJ, int NIB, int ei_global,
+                                                           int inorder) {
+  const int nat = NAT_CT > 0 ? NAT_CT : nat_rt;
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, NS = nat | 1;
+  const int EJ = NAT_CT > 0 ? ((NAT_CT * NAT_CT * 3 + 1) & ~1) : a.ES, XS = a.XS;
   extern __shared__ __align__(128) double esm[];
   double *Ejs = esm;                                // [TJ*EJ]     resident
   double *Xj = Ejs + (size_t)TJ * EJ;               // [TJ*XS]     resident
-  double *Eib = Xj + (size_t)TJ * XS;               // [2][EJ]     streamed
-  double *Xib = Eib + 2 * (size_t)EJ;               // [2][XS]
+  double *Eib = Xj + (size_t)TJ * XS;               // [2][EJ]     streamed (very large molecules: read through L1 instead)
+  double *Xib = Eib + (ei_global ? 0 : 2 * (size_t)EJ);  // [2][XS]
   double *Pb = Xib + 2 * (size_t)XS;                // [2][TJ*PW]
   double *Dsq = Pb + 2 * (size_t)TJ * PW;           // [TJ][nat*NS]   Dsq[j][c*NS + b] = (X_j - X_i)[d_bc], 0 for b == c
   uint64_t *bar = reinterpret_cast<uint64_t *>(Dsq + (((size_t)TJ * nat * NS + 1) & ~(size_t)1));  // [3]
@@ -1095,9 +1159,9 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
   auto prefetch = [&](int n) {  // thread 0 only: operands of step n (geometry i_lo + n)
     const int64_t i = i_lo + n;
     const int buf = n & 1;
-    const unsigned be = (unsigned)EJ * 8, bx = (unsigned)XS * 8, bp = (unsigned)npair * PW * 8;
+    const unsigned be = ei_global ? 0u : (unsigned)EJ * 8, bx = (unsigned)XS * 8, bp = (unsigned)npair * PW * 8;
     mbar_arrive_expect_tx(&bar[buf], be + bx + bp);
-    bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
+    if (!ei_global) bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
     bulk_g2s(Xib + (size_t)buf * XS, a.Xc + i * XS, bx, &bar[buf]);
     bulk_g2s(Pb + (size_t)buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
   };
@@ -1108,6 +1172,7 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
     bulk_g2s(Xj, a.Xc + jb * XS, bx, &bar[2]);
     prefetch(0);
   }
+  __syncwarp();
   for (int e = tid; e < D; e += blockDim.x) {
     int lo, hi;
     pair_from_index(nat, e, lo, hi);
@@ -1120,6 +1185,7 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
   for (int n = 0; n < nsteps; n++) {
     __syncthreads();  // everyone left the buffer about to be refilled, and Dsq of the previous step; ptab / Dsq ready
     if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    __syncwarp();  // warp 0 reconverges before the tile code (uniform registers are shared with the issuing lane)
     const int buf = n & 1;
     mbar_wait(&bar[buf], (n >> 1) & 1);
     const int64_t i = i_lo + n;
@@ -1137,11 +1203,13 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
     const int64_t rbase = a.nv + i * G3;
     const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
     const double *pb = Pb + (size_t)buf * TJ * PW + jl * PW;
-    const double *ei = Eib + (size_t)buf * EJ + 3 * b;  // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
+    // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
+    const double *ei = (ei_global ? a.E + i * a.ES : Eib + (size_t)buf * EJ) + 3 * b;
     const double kj = pb[0];
     double sj = 0.0;
     {
       const double *dq = Dsq + (size_t)jl * nat * NS + b;
+#pragma unroll
       for (int c = 0; c < nat; c++) sj = fma(ej[c * G3], dq[c * NS], sj);  // -u_j[col]
     }
     const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
@@ -1149,6 +1217,35 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
     if (interior && j != i) {
       double m0 = 0.0, m1 = 0.0, m2 = 0.0;  // sums of the J_i^T J_j products over the rows, per t
       const double *ui = pb + 2;
+      if (inorder) {
+        // rows strictly in order: the diagonal sums come from a pass of their own, so that no 24-byte holes are left in
+        // the row segments for later (partial 32-byte sectors cost more at the memory side than the extra reads here)
+#pragma unroll 3
+        for (int aa = 0; aa < nat; aa++) {
+          const double knej = __dmul_rn(kj, ej[aa * G3]);
+          m0 = __dadd_rn(m0, __dmul_rn(knej, -ei[aa * G3 + 0]));
+          m1 = __dadd_rn(m1, __dmul_rn(knej, -ei[aa * G3 + 1]));
+          m2 = __dadd_rn(m2, __dmul_rn(knej, -ei[aa * G3 + 2]));
+        }
+#pragma unroll 3
+        for (int aa = 0; aa < nat; aa++) {
+          const double knej = __dmul_rn(kj, ej[aa * G3]);
+          double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
+                 p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
+          if (aa == b) {
+            p0 = -m0;
+            p1 = -m1;
+            p2 = -m2;
+          }
+          double *d3 = dst + (int64_t)(3 * aa) * ld;
+          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          d3[0] = fma(ui[3 * aa + 0], c2, p0);
+          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
+          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
+        }
+        continue;
+      }
+#pragma unroll
       for (int aa = 0; aa < nat; aa++) {
         // explicit roundings (no FMA contraction of p into m): the boundary path below forms the same numbers, so a
         // block comes out bit-identical whether it is written whole or clipped to a row slab (sharded assembly)
@@ -1159,13 +1256,13 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
         m1 = __dadd_rn(m1, p1);
         m2 = __dadd_rn(m2, p2);
         if (aa != b) {  // the three a == b rows are completed after the loop
-          KREG_CHECK_STORE(dst + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          KREG_CHECK(dst >= a.K + a.row_begin * ld, 3);
-          dst[0] = fma(ui[3 * aa + 0], c2, p0);
-          dst[ld] = fma(ui[3 * aa + 1], c2, p1);
-          dst[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
+          double *d3 = dst + (int64_t)(3 * aa) * ld;
+          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          KREG_CHECK(d3 >= a.K + a.row_begin * ld, 3);
+          d3[0] = fma(ui[3 * aa + 0], c2, p0);
+          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
+          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
         }
-        dst += 3 * ld;
       }
       // diagonal 3x3 block: (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u] = -(sum over rows of the products above)
       dst = a.K + (rbase + 3 * b) * ld + a.nv + j * G3 + cc;
@@ -1192,13 +1289,131 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
   }
 }
 
-#ifndef KREG_EMIT_RT_FROM
-#define KREG_EMIT_RT_FROM 11  // first molecule size whose gradient-gradient blocks are emitted by the run-time kernel
+// Variant with the roles swapped: CTA = ONE geometry i (E_i resident) x up to NJB steps of TJ geometries j whose pair
+// terms, X_j rows and E_j blocks stream through a double buffer; rows are written strictly in order (the a == b rows
+// included: their 3x3 diagonal terms come from a prologue loop), one barrier per step.
+template <int NAT_CT>
+__global__ void __launch_bounds__(256) grad_emit_seq_kernel(const GradArgs a, int nat_rt, int TJ, int NJB) {
+  const int nat = NAT_CT > 0 ? NAT_CT : nat_rt;
+  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1;
+  const int EJ = NAT_CT > 0 ? ((NAT_CT * NAT_CT * 3 + 1) & ~1) : a.ES, XS = a.XS;
+  extern __shared__ __align__(128) double esm[];
+  double *Pb = esm;                              // [2][TJ*PW]
+  double *Xj = Pb + 2 * (size_t)TJ * PW;         // [2][TJ*XS]
+  double *Ejs = Xj + 2 * (size_t)TJ * XS;        // [2][TJ*EJ]
+  double *Xi = Ejs + 2 * (size_t)TJ * EJ;        // [XS]
+  double *Ei = Xi + XS;                          // [EJ]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(Ei + EJ);  // [2]
+
+  const int64_t i = blockIdx.y + a.p_i0;
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t jend = full ? a.ntr : i + 1;
+  const int64_t jb0 = (int64_t)blockIdx.x * ((int64_t)NJB * TJ);
+  if (jb0 >= jend || i >= a.p_i1) return;
+  const int64_t rbase = a.nv + i * G3;
+  const int nsteps = (int)(((jend - jb0 < (int64_t)NJB * TJ ? jend - jb0 : (int64_t)NJB * TJ) + TJ - 1) / TJ);
+
+  const int tid = threadIdx.x;
+  const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
+  const int64_t ld = a.ldk;
+  const bool okc = tid < TJ * G3;
+  const int r = okc ? tid : 0;
+  const int jl = r / G3, cc = r - jl * G3, b = cc / 3;
+  const double *ei = Ei + 3 * b;  // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  for (int e = tid; e < D; e += blockDim.x) Xi[e] = a.Xc[i * XS + e];
+  for (int e = tid; e < EJ; e += blockDim.x) Ei[e] = a.E[i * a.ES + e];
+  __syncthreads();
+  auto prefetch = [&](int n) {  // thread 0 only
+    const int64_t jb = jb0 + (int64_t)n * TJ;
+    const unsigned npair = (unsigned)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
+    const int buf = n & 1;
+    const unsigned bp = npair * PW * 8, bx = npair * (unsigned)XS * 8, be = npair * (unsigned)EJ * 8;
+    mbar_arrive_expect_tx(&bar[buf], bp + bx + be);
+    bulk_g2s(Pb + (size_t)buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
+    bulk_g2s(Xj + (size_t)buf * TJ * XS, a.Xc + jb * XS, bx, &bar[buf]);
+    bulk_g2s(Ejs + (size_t)buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
+  };
+  if (tid == 0) prefetch(0);
+  __syncwarp();
+
+  for (int n = 0; n < nsteps; n++) {
+    __syncthreads();  // everyone left buffer (n+1)&1 (read during step n-1)
+    if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    __syncwarp();  // warp 0 reconverges before the tile code (uniform registers are shared with the issuing lane)
+    const int buf = n & 1;
+    mbar_wait(&bar[buf], (n >> 1) & 1);
+    const int64_t j = jb0 + (int64_t)n * TJ + jl;
+    if (!(okc && j < jend)) continue;
+    const double *pb = Pb + (size_t)buf * TJ * PW + jl * PW;
+    const double *xj = Xj + (size_t)buf * TJ * XS + jl * XS;
+    const double *ej = Ejs + (size_t)buf * TJ * EJ + (size_t)jl * EJ + cc;  // E_j[c][b][u] at ej[c * G3]
+    const double kj = pb[0];
+    double sj = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < nat; c++) {
+      const double nej = ej[c * G3];
+      if (c != b) {
+        const int d = pair_index(nat, b < c ? b : c, b < c ? c : b);
+        sj = fma(nej, xj[d] - Xi[d], sj);
+      }
+      a0 = fma(-ei[c * G3 + 0], nej, a0);
+      a1 = fma(-ei[c * G3 + 1], nej, a1);
+      a2 = fma(-ei[c * G3 + 2], nej, a2);
+    }
+    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+    const double kd0 = -a0 * kj, kd1 = -a1 * kj, kd2 = -a2 * kj;
+    double *dst = a.K + rbase * ld + a.nv + j * G3 + cc;
+    if (interior && j != i) {
+      const double *ui = pb + 2;
+#pragma unroll
+      for (int aa = 0; aa < nat; aa++) {
+        const double knej = kj * ej[aa * G3];
+        double v0 = fma(ui[3 * aa + 0], c2, knej * -ei[aa * G3 + 0]);
+        double v1 = fma(ui[3 * aa + 1], c2, knej * -ei[aa * G3 + 1]);
+        double v2 = fma(ui[3 * aa + 2], c2, knej * -ei[aa * G3 + 2]);
+        if (aa == b) {
+          v0 += kd0;
+          v1 += kd1;
+          v2 += kd2;
+        }
+        double *d3 = dst + (int64_t)(3 * aa) * ld;
+        KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+        d3[0] = v0;
+        d3[ld] = v1;
+        d3[2 * ld] = v2;
+      }
+    } else {
+      for (int q = 0; q < G3; q++) {
+        const int aa = q / 3, t = q - aa * 3;
+        double val = fma(pb[2 + q], c2, (kj * ej[aa * G3]) * -ei[aa * G3 + t]);
+        if (aa == b) val += (t == 0 ? kd0 : t == 1 ? kd1 : kd2);
+        if (j == i && q == cc) val += a.lambdag;
+        const int64_t rr = rbase + q;
+        if (rr >= a.row_begin && rr < a.row_end) {
+          KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          dst[(int64_t)q * ld] = val;
+        }
+      }
+    }
+  }
+}
+
+#ifndef KREG_EMIT_TEMPLATE_MAX
+#define KREG_EMIT_TEMPLATE_MAX 10  // largest molecule emitted by the register-resident grad_emit_kernel<NAT>
+#endif
+#ifndef KREG_EMIT_SEQ_MAX
+#define KREG_EMIT_SEQ_MAX 22       // largest molecule emitted by grad_emit_seq_kernel; above: grad_emit_rt_kernel
 #endif
 
 // launch plan of the run-time kernels (KREG_RT_* environment variables override, for tuning runs)
 struct RtPlan {
-  int JT, TJ, NIB, threads;
+  int JT, TJ, NIB, threads, ei_global;
   size_t pair_smem, emit_smem;
 };
 
@@ -1207,9 +1422,10 @@ static int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-static size_t emit_smem_doubles(int nat, int XS, int EJ, int tj) {
+static size_t emit_smem_doubles(int nat, int XS, int EJ, int tj, int ei_global = 0) {
   const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, NS = nat | 1;
-  size_t n = (size_t)tj * ((size_t)EJ + XS) + 2 * ((size_t)EJ + XS + (size_t)tj * PW) + (((size_t)tj * nat * NS + 1) & ~(size_t)1);
+  size_t n = (size_t)tj * ((size_t)EJ + XS) + 2 * ((ei_global ? 0 : (size_t)EJ) + XS + (size_t)tj * PW) +
+             (((size_t)tj * nat * NS + 1) & ~(size_t)1);
   n += 4 + (D + 3) / 4;  // barriers, pair table (unsigned short)
   return n;
 }
@@ -1238,28 +1454,46 @@ static RtPlan rt_plan(int nat, const GradArgs &a) {
   } else {
     while (tj > 1 && emit_smem_doubles(nat, XS, EJ, tj) > one_cta) tj--;
   }
+  p.ei_global = env_int("KREG_RT_EIG", emit_smem_doubles(nat, XS, EJ, tj) > one_cta ? 1 : 0);
   p.TJ = env_int("KREG_RT_TJ", tj);
   if (p.TJ < 1) p.TJ = 1;
   p.NIB = env_int("KREG_RT_NIB", 16);
   if (p.NIB < 1) p.NIB = 1;
   p.threads = ((p.TJ * G3 + 31) / 32) * 32;
-  p.emit_smem = emit_smem_doubles(nat, XS, EJ, p.TJ) * sizeof(double);
+  p.emit_smem = emit_smem_doubles(nat, XS, EJ, p.TJ, p.ei_global) * sizeof(double);
   return p;
 }
 
-static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, cudaStream_t st) {
+// emit variants: 0 = grad_emit_kernel<NAT> (templated, operands in registers), 3 = grad_emit_rt_kernel (j-block resident),
+// 4 = grad_emit_seq_kernel (geometry i resident, rows in order)
+static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, int variant, cudaStream_t st) {
   const RtPlan p = rt_plan(nat, a);
-  if (p.threads > 256 || p.pair_smem > 227 * 1024 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
   if (a.p_i1 <= a.p_i0) return KREG_OK;
   if (pair_terms) {
+    if (p.pair_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
     KREG_CUDA_TRY(cudaFuncSetAttribute(pair_terms_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pair_smem));
     dim3 grid((unsigned)((a.ntr + p.JT - 1) / p.JT), (unsigned)a.ntr);
     pair_terms_rt_kernel<<<grid, 256, p.pair_smem, st>>>(a, nat, p.JT);
     KREG_LAUNCH_CHECK();
   }
+  if (variant == 4) {
+    const int G3 = 3 * nat, PW = (G3 + 3) & ~1;
+    const int tj = env_int("KREG_RT_TJ", 256 / G3 < 1 ? 1 : 256 / G3);
+    const int njb = env_int("KREG_RT_NJB", 8);
+    const size_t smem = (2 * (size_t)tj * ((size_t)PW + a.XS + a.ES) + a.XS + a.ES + 4) * sizeof(double);
+    const int threads = ((tj * G3 + 31) / 32) * 32;
+    if (smem > 227 * 1024 || threads > 256) return KREG_E_UNSUPPORTED;
+    dim3 grid((unsigned)((a.ntr + (int64_t)njb * tj - 1) / ((int64_t)njb * tj)), (unsigned)(a.p_i1 - a.p_i0));
+    KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grad_emit_seq_kernel<0><<<grid, threads, smem, st>>>(a, nat, tj, njb);
+    KREG_LAUNCH_CHECK();
+    return KREG_OK;
+  }
+  if (p.threads > 256 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
   dim3 grid((unsigned)((a.ntr + p.TJ - 1) / p.TJ), (unsigned)((a.p_i1 - a.p_i0 + p.NIB - 1) / p.NIB));
-  KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
-  grad_emit_rt_kernel<<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NIB);
+  KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
+  grad_emit_rt_kernel<0><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NIB, p.ei_global,
+                                                               env_int("KREG_RT_INORDER", 1));
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
@@ -1285,27 +1519,37 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st, bool do_pair, boo
     KREG_LAUNCH_CHECK();
   }
   if (!do_emit) return KREG_OK;
-  dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)a.ntr);
-  auto emit = grad_emit_kernel<NAT>;
-  const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
-  KREG_CUDA_TRY(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-  emit<<<grid, C::THREADS, esmem, st>>>(a);
-  KREG_LAUNCH_CHECK();
-  return KREG_OK;
+  if constexpr (NAT <= KREG_EMIT_TEMPLATE_MAX) {
+    dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)a.ntr);
+    auto emit = grad_emit_kernel<NAT>;
+    const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
+    KREG_CUDA_TRY(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    emit<<<grid, C::THREADS, esmem, st>>>(a);
+    KREG_LAUNCH_CHECK();
+    return KREG_OK;
+  } else {
+    return KREG_E_UNSUPPORTED;  // no register-resident emit kernel is built for this size
+  }
 }
 
-// Which kernels run (defaults from the measurements in DESIGN.md 4.3; KREG_PAIR_RT / KREG_EMIT_RT = 0 / 1 override for
-// A/B runs): molecules above 24 atoms have no templated instantiation and always take the run-time kernels.
+// Which kernels run, by molecule size (measured on B200; KREG_PAIR_RT = 0/1 and KREG_EMIT_VARIANT = 0/3/4
+// override for A/B runs):
+//   pair terms : templated kernels up to 24 atoms, the run-time kernel above
+//   emit       : <= 10 atoms  grad_emit_kernel<NAT> (operands in registers, 5.1 TB/s at 9 atoms)
+//                11..22       grad_emit_seq_kernel  (geometry i resident, rows in order: 4.4 TB/s at 12, 3.5 at 21 atoms;
+//                             the register version spills from 11 atoms up: 3.2)
+//                >= 23        grad_emit_rt_kernel   (j-block resident: the E_j blocks no longer stream, 2.9 TB/s at 24-32)
 static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
-  if (nat > KREG_FUSED_MAX_NATOMS) return launch_grad_rt(nat, a, true, st);
-  const bool pair_rt = env_int("KREG_PAIR_RT", 0) != 0;
-  const bool emit_rt = env_int("KREG_EMIT_RT", nat >= KREG_EMIT_RT_FROM ? 1 : 0) != 0;
-  if (pair_rt && emit_rt) return launch_grad_rt(nat, a, true, st);
+  const int dflt = nat <= KREG_EMIT_TEMPLATE_MAX ? 0 : (nat <= KREG_EMIT_SEQ_MAX ? 4 : 3);
+  int variant = env_int("KREG_EMIT_VARIANT", dflt);
+  if (variant == 0 && nat > KREG_EMIT_TEMPLATE_MAX) variant = dflt;
+  const bool pair_rt = nat > KREG_FUSED_MAX_NATOMS || env_int("KREG_PAIR_RT", 0) != 0;
+  if (pair_rt) return launch_grad_rt(nat, a, true, variant == 0 ? dflt == 0 ? 4 : dflt : variant, st);
   int rc = KREG_E_UNSUPPORTED;
   switch (nat) {
-#define KREG_CASE(N)                                           \
-  case N:                                                      \
-    rc = launch_grad_nat<N>(a, st, !pair_rt, !emit_rt);        \
+#define KREG_CASE(N)                                        \
+  case N:                                                   \
+    rc = launch_grad_nat<N>(a, st, true, variant == 0);     \
     break;
 #ifdef KREG_ONLY_NAT9  /* experiment builds (tools/ab_kbuild.sh): one instantiation, seconds to compile */
     KREG_CASE(9)
@@ -1318,13 +1562,8 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
     default:
       return KREG_E_UNSUPPORTED;
   }
-  if (rc) return rc;
-  if (pair_rt || emit_rt) {
-    // mixed: one stage from the templated kernels (above), the other from the run-time ones
-    if (pair_rt) return KREG_E_BADARG;  // run-time pair terms are only combined with the run-time emit kernel
-    return launch_grad_rt(nat, a, false, st);
-  }
-  return KREG_OK;
+  if (rc || variant == 0) return rc;
+  return launch_grad_rt(nat, a, false, variant, st);
 }
 
 // workspace carve-up helpers ---------------------------------------------------------------
@@ -1377,6 +1616,13 @@ extern "C" size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain < 0) return 0;
   return build_ws(natoms, ntrain, ntrgr > 0).total;
 }
+
+#ifdef KREG_DEBUG_BIAS
+extern "C" int kreg_debug_bias(unsigned long long *out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, kreg::g_bias_dbg, sizeof(unsigned long long) * 8);
+}
+#endif
 
 extern "C" size_t kreg_build_workspace_bytes_rows(int natoms, int64_t ntrain, int64_t ntrgr, int64_t row_begin,
                                                   int64_t row_end) {

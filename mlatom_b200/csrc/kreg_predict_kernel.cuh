@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
       bulk_g2s(ring + s * C::STAGE, args.packed + (size_t)(stage0 + s) * C::STAGE, bytes, &full_bar[s]);
     }
   }
+  __syncwarp();  // the issuing lane rejoins its warp before the prologue
 
   // ---- prologue: centred descriptors of this CTA's test rows -> shared tile ----
   const int64_t rows_left = args.npoints - row0;
@@ -268,15 +269,20 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
 
   // ---- main loop over the training set ----
   for (int it = 0; it < total_stages; it++) {
-    // producer duty: refill the stage every warp finished in the previous iteration
-    if (tid == 0 && it >= 1 && it - 1 + NSTAGE < total_stages) {
-      const int sp = (it - 1) % NSTAGE;
-      const int nxt = it - 1 + NSTAGE;
-      mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
-      int ng = min(GPS, args.ngroups - (stage0 + nxt) * GPS);
-      unsigned bytes = (unsigned)(ng * C::CHUNK * 8);
-      mbar_arrive_expect_tx(&full_bar[sp], bytes);
-      bulk_g2s(ring + sp * C::STAGE, args.packed + (size_t)(stage0 + nxt) * C::STAGE, bytes, &full_bar[sp]);
+    // producer duty: refill the stage every warp finished in the previous iteration.  Warp-uniform branch with the one
+    // issuing lane inside and an explicit reconvergence after it (see values_ring_kernel: with a bare `if (tid == 0)`
+    // the other lanes of warp 0 may run ahead while lane 0 is still issuing, sharing the warp's uniform registers)
+    if (warp == 0 && it >= 1 && it - 1 + NSTAGE < total_stages) {
+      if (lane == 0) {
+        const int sp = (it - 1) % NSTAGE;
+        const int nxt = it - 1 + NSTAGE;
+        mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
+        int ng = min(GPS, args.ngroups - (stage0 + nxt) * GPS);
+        unsigned bytes = (unsigned)(ng * C::CHUNK * 8);
+        mbar_arrive_expect_tx(&full_bar[sp], bytes);
+        bulk_g2s(ring + sp * C::STAGE, args.packed + (size_t)(stage0 + nxt) * C::STAGE, bytes, &full_bar[sp]);
+      }
+      __syncwarp();
     }
     const int s = it % NSTAGE;
     mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
