@@ -124,6 +124,24 @@ int kreg_kernel_block(int natoms, int64_t na, const double *xyz_a, int64_t nb, c
                       const double *xeq, double sigma, double *Kout, int64_t ldk, void *workspace,
                       size_t workspace_bytes, void *stream);
 
+/* MLatomF's other kernel functions on the RE descriptor (Kfunk, A_KRR_kernel.f90:806-851; distance :2040-2074):
+ *   KREG_KERNEL_GAUSSIAN     exp(-|Xi-Xj|_2^2 / (2 sigma^2))
+ *   KREG_KERNEL_EXPONENTIAL  exp(-|Xi-Xj|_2 / sigma)
+ *   KREG_KERNEL_MATERN       exp(-r/sigma) n!/(2n)! sum_k (n+k)!/(k!(n-k)!) (2r/sigma)^(n-k),  r = |Xi-Xj|_2,  n = nn <= 10
+ *   KREG_KERNEL_LAPLACIAN    exp(-|Xi-Xj|_1 / sigma)
+ * Value-value blocks only (calcKernel / calc_Kvalidate for models trained on values): Kout[i][j] = k(X(xyz_a[i]),
+ * X(xyz_b[j])), row-major na x ldk, both triangles.  symmetric != 0 (then xyz_a and xyz_b must be the same set) puts
+ * exactly 1 + lambda on the diagonal, i.e. the matrix kreg_solve factorises.  The three Euclidean kernels run on the
+ * FP64 tensor-core tile kernel; the Laplacian's L1 distance is not a GEMM and has a plain tiled kernel. */
+#define KREG_KERNEL_GAUSSIAN 0
+#define KREG_KERNEL_EXPONENTIAL 1
+#define KREG_KERNEL_MATERN 2
+#define KREG_KERNEL_LAPLACIAN 3
+size_t kreg_kernel_block_ex_workspace_bytes(int natoms, int64_t na, int64_t nb);
+int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double *xyz_a, int64_t nb, const double *xyz_b,
+                         const double *xeq, double sigma, int symmetric, double lambda, double *Kout, int64_t ldk,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* Linear solve ------------------------------------------------------------------------------ */
 
 /* Device / pinned-host scratch needed by kreg_solve for an m x m system. */

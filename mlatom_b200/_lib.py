@@ -53,6 +53,12 @@ PROTOTYPES = {
         [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_void_p, c_int64, c_void_p, c_size_t,
          c_void_p],
     ),
+    "kreg_kernel_block_ex_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64]),
+    "kreg_kernel_block_ex": (
+        c_int,
+        [c_int, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_int, c_double, c_void_p,
+         c_int64, c_void_p, c_size_t, c_void_p],
+    ),
     "kreg_solve_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t), POINTER(c_size_t)]),
     "kreg_solve": (c_int, [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "kreg_solve_indefinite_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t)]),

@@ -35,6 +35,12 @@ struct ValuesArgs {
   int64_t ldc;
   double *Wch, *Kfch;  // [nchunks_w][na][wkc]
   int wkc;             // columns per output chunk (the second GEMM's K chunk)
+  // EPI_KR (MLatomF's other radial kernels, A_KRR_kernel.f90:806-851): k = f(|X_i - X_j| / sigma); biasA is then the
+  // UNSCALED row term -n_i/2
+  int kind;            // KREG_KERNEL_EXPONENTIAL / KREG_KERNEL_MATERN
+  int nn;              // Matern order n (nu = n + 1/2)
+  double inv_sigma;
+  double mat_c[12];    // Matern polynomial coefficients in (2 r / sigma)^m, m = 0..nn
 };
 
 constexpr int kGemmKC = 9;  // k-steps per chunk of the GEMM modes (chunk width 36 doubles, conflict-free stride 36)
@@ -44,6 +50,7 @@ constexpr int EPI_K = 0;    // K-matrix / validation block: exp, diagonal, mirro
 constexpr int EPI_W = 1;    // prediction GEMM1: exp * column scale -> chunk-major W
 constexpr int EPI_WV = 2;   // prediction GEMM1, gradient models: exp * Cin -> chunk-major W and K
 constexpr int EPI_LIN = 3;  // plain GEMM: C = A B^T + column term (row-major)
+constexpr int EPI_KR = 4;   // radial kernels of the Euclidean distance: exponential, Matern
 
 // kreg_kbuild.cu
 int launch_gemm_epi(const ValuesArgs &a, int epi, cudaStream_t st);

@@ -159,6 +159,49 @@ __device__ __forceinline__ void w_tile_epilogue(const ValuesArgs &a, double (&S)
   }
 }
 
+// Radial kernels of the Euclidean descriptor distance (MLatomF Kfunk, A_KRR_kernel.f90:806-851, with distance()
+// :2040-2074): r^2 = n_i + n_j - 2 X'_i.X'_j = -2 (s + b_i) with the accumulator s = X'_i.X'_j - n_j/2 and the unscaled
+// row term b_i = -n_i/2;  exponential k = exp(-r/sigma);  Matern k = exp(-r/sigma) sum_m c_m (2r/sigma)^m.
+// The square root amplifies the cancellation error of r^2 (~1e-16 n) to ~1e-16 n / r in r: 1e-13 parity holds for
+// r >~ 1e-3, i.e. for everything but near-duplicate geometries (the diagonal itself is set exactly).
+__device__ __forceinline__ double radial_kernel_value(const ValuesArgs &a, double s_plus_bi) {
+  const double r2 = fmax(-2.0 * s_plus_bi, 0.0);
+  const double x = sqrt(r2) * a.inv_sigma;
+  double p = 1.0;
+  if (a.kind == KREG_KERNEL_MATERN) {
+    const double y = 2.0 * x;
+    p = a.mat_c[a.nn];
+    for (int m = a.nn - 1; m >= 0; m--) p = fma(p, y, a.mat_c[m]);
+  }
+  return exp(-x) * p;
+}
+
+__device__ __forceinline__ void radial_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
+                                                     const double *bA, int wi, int wj, int g, int q) {
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int ri = wi * 32 + mt * 8 + g;
+    const int64_t i = i0 + ri;
+    if (i >= a.na) continue;
+    const double bi = bA[ri];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
+      double k0 = radial_kernel_value(a, S[mt][nt][0] + bi), k1 = radial_kernel_value(a, S[mt][nt][1] + bi);
+      if (a.symmetric) {
+        if (i == j) k0 = 1.0 + a.lambda;
+        if (i == j + 1) k1 = 1.0 + a.lambda;
+      }
+      double *dst = a.K + i * a.ldk + j;
+      if (j < a.nb) {
+        KREG_CHECK_STORE(dst, a.K, a.na * a.ldk);
+        dst[0] = k0;
+      }
+      if (j + 1 < a.nb) dst[1] = k1;
+    }
+  }
+}
+
 // Plain GEMM epilogue: C[i][j] = accumulator (A_i . B_j + column term), row-major.
 __device__ __forceinline__ void lin_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
                                                   int wi, int wj, int g, int q) {
@@ -306,6 +349,8 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       values_tile_epilogue(a, S, i0, j0, bA, tab, wi, wj, g, q, lower_only);
     else if (EPI == EPI_LIN)
       lin_tile_epilogue(a, S, i0, j0, wi, wj, g, q);
+    else if (EPI == EPI_KR)
+      radial_tile_epilogue(a, S, i0, j0, bA, wi, wj, g, q);
     else
       w_tile_epilogue<EPI>(a, S, i0, j0, bA, tab, wi, wj, g, q);
   };
@@ -404,6 +449,17 @@ __global__ void __launch_bounds__(256) chunk_rows_kernel(int64_t n, int XS, int 
   }
 }
 
+__global__ void set_diagonal_kernel(int64_t n, double *__restrict__ K, int64_t ldk, double v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) K[i * ldk + i] = v;
+}
+
+static int launch_set_diagonal(int64_t n, double *K, int64_t ldk, double v, cudaStream_t st) {
+  set_diagonal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, K, ldk, v);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
+}
+
 int launch_chunk_rows(int64_t n, int XS, int KC, int nchunks, int XSC, const double *Xc, double *Xch, cudaStream_t st) {
   if (n <= 0) return KREG_OK;
   chunk_rows_kernel<<<1184, 256, 0, st>>>(n, XS, KC, nchunks, XSC, Xc, Xch);
@@ -453,6 +509,8 @@ int launch_gemm_epi(const ValuesArgs &a, int epi, cudaStream_t st) {
       return launch_values_kc<kGemmKC, EPI_WV>(a, st);
     case EPI_LIN:
       return launch_values_kc<kGemmKC, EPI_LIN>(a, st);
+    case EPI_KR:
+      return launch_values_kc<kGemmKC, EPI_KR>(a, st);
     case EPI_K:
       return launch_values_kc<kGemmKC, EPI_K>(a, st);
     default:
@@ -1289,126 +1347,11 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
   }
 }
 
-// Variant with the roles swapped: CTA = ONE geometry i (E_i resident) x up to NJB steps of TJ geometries j whose pair
-// terms, X_j rows and E_j blocks stream through a double buffer; rows are written strictly in order (the a == b rows
-// included: their 3x3 diagonal terms come from a prologue loop), one barrier per step.
-template <int NAT_CT>
-__global__ void __launch_bounds__(256) grad_emit_seq_kernel(const GradArgs a, int nat_rt, int TJ, int NJB) {
-  const int nat = NAT_CT > 0 ? NAT_CT : nat_rt;
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1;
-  const int EJ = NAT_CT > 0 ? ((NAT_CT * NAT_CT * 3 + 1) & ~1) : a.ES, XS = a.XS;
-  extern __shared__ __align__(128) double esm[];
-  double *Pb = esm;                              // [2][TJ*PW]
-  double *Xj = Pb + 2 * (size_t)TJ * PW;         // [2][TJ*XS]
-  double *Ejs = Xj + 2 * (size_t)TJ * XS;        // [2][TJ*EJ]
-  double *Xi = Ejs + 2 * (size_t)TJ * EJ;        // [XS]
-  double *Ei = Xi + XS;                          // [EJ]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(Ei + EJ);  // [2]
-
-  const int64_t i = blockIdx.y + a.p_i0;
-  const bool full = a.fill == KREG_FILL_FULL;
-  const int64_t jend = full ? a.ntr : i + 1;
-  const int64_t jb0 = (int64_t)blockIdx.x * ((int64_t)NJB * TJ);
-  if (jb0 >= jend || i >= a.p_i1) return;
-  const int64_t rbase = a.nv + i * G3;
-  const int nsteps = (int)(((jend - jb0 < (int64_t)NJB * TJ ? jend - jb0 : (int64_t)NJB * TJ) + TJ - 1) / TJ);
-
-  const int tid = threadIdx.x;
-  const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
-  const int64_t ld = a.ldk;
-  const bool okc = tid < TJ * G3;
-  const int r = okc ? tid : 0;
-  const int jl = r / G3, cc = r - jl * G3, b = cc / 3;
-  const double *ei = Ei + 3 * b;  // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
-
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_fence_init();
-  }
-  for (int e = tid; e < D; e += blockDim.x) Xi[e] = a.Xc[i * XS + e];
-  for (int e = tid; e < EJ; e += blockDim.x) Ei[e] = a.E[i * a.ES + e];
-  __syncthreads();
-  auto prefetch = [&](int n) {  // thread 0 only
-    const int64_t jb = jb0 + (int64_t)n * TJ;
-    const unsigned npair = (unsigned)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
-    const int buf = n & 1;
-    const unsigned bp = npair * PW * 8, bx = npair * (unsigned)XS * 8, be = npair * (unsigned)EJ * 8;
-    mbar_arrive_expect_tx(&bar[buf], bp + bx + be);
-    bulk_g2s(Pb + (size_t)buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
-    bulk_g2s(Xj + (size_t)buf * TJ * XS, a.Xc + jb * XS, bx, &bar[buf]);
-    bulk_g2s(Ejs + (size_t)buf * TJ * EJ, a.E + jb * a.ES, be, &bar[buf]);
-  };
-  if (tid == 0) prefetch(0);
-  __syncwarp();
-
-  for (int n = 0; n < nsteps; n++) {
-    __syncthreads();  // everyone left buffer (n+1)&1 (read during step n-1)
-    if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
-    __syncwarp();  // warp 0 reconverges before the tile code (uniform registers are shared with the issuing lane)
-    const int buf = n & 1;
-    mbar_wait(&bar[buf], (n >> 1) & 1);
-    const int64_t j = jb0 + (int64_t)n * TJ + jl;
-    if (!(okc && j < jend)) continue;
-    const double *pb = Pb + (size_t)buf * TJ * PW + jl * PW;
-    const double *xj = Xj + (size_t)buf * TJ * XS + jl * XS;
-    const double *ej = Ejs + (size_t)buf * TJ * EJ + (size_t)jl * EJ + cc;  // E_j[c][b][u] at ej[c * G3]
-    const double kj = pb[0];
-    double sj = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-    for (int c = 0; c < nat; c++) {
-      const double nej = ej[c * G3];
-      if (c != b) {
-        const int d = pair_index(nat, b < c ? b : c, b < c ? c : b);
-        sj = fma(nej, xj[d] - Xi[d], sj);
-      }
-      a0 = fma(-ei[c * G3 + 0], nej, a0);
-      a1 = fma(-ei[c * G3 + 1], nej, a1);
-      a2 = fma(-ei[c * G3 + 2], nej, a2);
-    }
-    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
-    const double kd0 = -a0 * kj, kd1 = -a1 * kj, kd2 = -a2 * kj;
-    double *dst = a.K + rbase * ld + a.nv + j * G3 + cc;
-    if (interior && j != i) {
-      const double *ui = pb + 2;
-#pragma unroll
-      for (int aa = 0; aa < nat; aa++) {
-        const double knej = kj * ej[aa * G3];
-        double v0 = fma(ui[3 * aa + 0], c2, knej * -ei[aa * G3 + 0]);
-        double v1 = fma(ui[3 * aa + 1], c2, knej * -ei[aa * G3 + 1]);
-        double v2 = fma(ui[3 * aa + 2], c2, knej * -ei[aa * G3 + 2]);
-        if (aa == b) {
-          v0 += kd0;
-          v1 += kd1;
-          v2 += kd2;
-        }
-        double *d3 = dst + (int64_t)(3 * aa) * ld;
-        KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-        d3[0] = v0;
-        d3[ld] = v1;
-        d3[2 * ld] = v2;
-      }
-    } else {
-      for (int q = 0; q < G3; q++) {
-        const int aa = q / 3, t = q - aa * 3;
-        double val = fma(pb[2 + q], c2, (kj * ej[aa * G3]) * -ei[aa * G3 + t]);
-        if (aa == b) val += (t == 0 ? kd0 : t == 1 ? kd1 : kd2);
-        if (j == i && q == cc) val += a.lambdag;
-        const int64_t rr = rbase + q;
-        if (rr >= a.row_begin && rr < a.row_end) {
-          KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          dst[(int64_t)q * ld] = val;
-        }
-      }
-    }
-  }
-}
-
 #ifndef KREG_EMIT_TEMPLATE_MAX
 #define KREG_EMIT_TEMPLATE_MAX 10  // largest molecule emitted by the register-resident grad_emit_kernel<NAT>
 #endif
-#ifndef KREG_EMIT_SEQ_MAX
-#define KREG_EMIT_SEQ_MAX 22       // largest molecule emitted by grad_emit_seq_kernel; above: grad_emit_rt_kernel
+#ifndef KREG_EMIT_INORDER_MAX
+#define KREG_EMIT_INORDER_MAX 28   // up to here grad_emit_rt_kernel writes the rows strictly in order (see the kernel)
 #endif
 
 // launch plan of the run-time kernels (KREG_RT_* environment variables override, for tuning runs)
@@ -1464,9 +1407,7 @@ static RtPlan rt_plan(int nat, const GradArgs &a) {
   return p;
 }
 
-// emit variants: 0 = grad_emit_kernel<NAT> (templated, operands in registers), 3 = grad_emit_rt_kernel (j-block resident),
-// 4 = grad_emit_seq_kernel (geometry i resident, rows in order)
-static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, int variant, cudaStream_t st) {
+static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, cudaStream_t st) {
   const RtPlan p = rt_plan(nat, a);
   if (a.p_i1 <= a.p_i0) return KREG_OK;
   if (pair_terms) {
@@ -1476,24 +1417,11 @@ static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, int varia
     pair_terms_rt_kernel<<<grid, 256, p.pair_smem, st>>>(a, nat, p.JT);
     KREG_LAUNCH_CHECK();
   }
-  if (variant == 4) {
-    const int G3 = 3 * nat, PW = (G3 + 3) & ~1;
-    const int tj = env_int("KREG_RT_TJ", 256 / G3 < 1 ? 1 : 256 / G3);
-    const int njb = env_int("KREG_RT_NJB", 8);
-    const size_t smem = (2 * (size_t)tj * ((size_t)PW + a.XS + a.ES) + a.XS + a.ES + 4) * sizeof(double);
-    const int threads = ((tj * G3 + 31) / 32) * 32;
-    if (smem > 227 * 1024 || threads > 256) return KREG_E_UNSUPPORTED;
-    dim3 grid((unsigned)((a.ntr + (int64_t)njb * tj - 1) / ((int64_t)njb * tj)), (unsigned)(a.p_i1 - a.p_i0));
-    KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    grad_emit_seq_kernel<0><<<grid, threads, smem, st>>>(a, nat, tj, njb);
-    KREG_LAUNCH_CHECK();
-    return KREG_OK;
-  }
   if (p.threads > 256 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
   dim3 grid((unsigned)((a.ntr + p.TJ - 1) / p.TJ), (unsigned)((a.p_i1 - a.p_i0 + p.NIB - 1) / p.NIB));
   KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
   grad_emit_rt_kernel<0><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NIB, p.ei_global,
-                                                               env_int("KREG_RT_INORDER", 1));
+                                                               env_int("KREG_RT_INORDER", nat <= KREG_EMIT_INORDER_MAX ? 1 : 0));
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
@@ -1532,24 +1460,21 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st, bool do_pair, boo
   }
 }
 
-// Which kernels run, by molecule size (measured on B200; KREG_PAIR_RT = 0/1 and KREG_EMIT_VARIANT = 0/3/4
-// override for A/B runs):
+// Which kernels run, by molecule size (measured on B200; KREG_PAIR_RT = 1 and KREG_EMIT_RT = 0/1 override
+// for A/B runs):
 //   pair terms : templated kernels up to 24 atoms, the run-time kernel above
-//   emit       : <= 10 atoms  grad_emit_kernel<NAT> (operands in registers, 5.1 TB/s at 9 atoms)
-//                11..22       grad_emit_seq_kernel  (geometry i resident, rows in order: 4.4 TB/s at 12, 3.5 at 21 atoms;
-//                             the register version spills from 11 atoms up: 3.2)
-//                >= 23        grad_emit_rt_kernel   (j-block resident: the E_j blocks no longer stream, 2.9 TB/s at 24-32)
+//   emit       : <= 10 atoms  grad_emit_kernel<NAT> (operands in registers: 5.1 TB/s at 9 atoms)
+//                >= 11        grad_emit_rt_kernel (operands in shared memory, j-block resident: 4.3 TB/s at 12, 3.6 at 21
+//                             and 24 atoms; the register version spills from 11 atoms up and stays at 3.2)
 static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
-  const int dflt = nat <= KREG_EMIT_TEMPLATE_MAX ? 0 : (nat <= KREG_EMIT_SEQ_MAX ? 4 : 3);
-  int variant = env_int("KREG_EMIT_VARIANT", dflt);
-  if (variant == 0 && nat > KREG_EMIT_TEMPLATE_MAX) variant = dflt;
+  const bool emit_rt = nat > KREG_EMIT_TEMPLATE_MAX || env_int("KREG_EMIT_RT", 0) != 0;
   const bool pair_rt = nat > KREG_FUSED_MAX_NATOMS || env_int("KREG_PAIR_RT", 0) != 0;
-  if (pair_rt) return launch_grad_rt(nat, a, true, variant == 0 ? dflt == 0 ? 4 : dflt : variant, st);
+  if (pair_rt) return launch_grad_rt(nat, a, true, st);
   int rc = KREG_E_UNSUPPORTED;
   switch (nat) {
-#define KREG_CASE(N)                                        \
-  case N:                                                   \
-    rc = launch_grad_nat<N>(a, st, true, variant == 0);     \
+#define KREG_CASE(N)                                    \
+  case N:                                               \
+    rc = launch_grad_nat<N>(a, st, true, !emit_rt);     \
     break;
 #ifdef KREG_ONLY_NAT9  /* experiment builds (tools/ab_kbuild.sh): one instantiation, seconds to compile */
     KREG_CASE(9)
@@ -1562,8 +1487,8 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
     default:
       return KREG_E_UNSUPPORTED;
   }
-  if (rc || variant == 0) return rc;
-  return launch_grad_rt(nat, a, false, variant, st);
+  if (rc || !emit_rt) return rc;
+  return launch_grad_rt(nat, a, false, st);
 }
 
 // workspace carve-up helpers ---------------------------------------------------------------
@@ -1615,6 +1540,158 @@ using namespace kreg;
 extern "C" size_t kreg_build_workspace_bytes(int natoms, int64_t ntrain, int64_t ntrgr) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain < 0) return 0;
   return build_ws(natoms, ntrain, ntrgr > 0).total;
+}
+
+namespace kreg {
+
+// Laplacian kernel exp(-|X_i - X_j|_1 / sigma) (A_KRR_kernel.f90:830-831 with the L1 distance of :2066-2069): not a GEMM;
+// a 32 x 32 tile of pairs per CTA, descriptor chunks of 32 staged in shared memory (odd stride: conflict-free columns).
+__global__ void __launch_bounds__(256) laplacian_block_kernel(int D, int64_t na, const double *__restrict__ XA, int64_t nb,
+                                                              const double *__restrict__ XB, int XS, double inv_sigma,
+                                                              int symmetric, double lambda, double *__restrict__ K,
+                                                              int64_t ldk) {
+  __shared__ double As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      const int d = d0 + tx;
+      As[r][tx] = (i0 + r < na && d < D) ? XA[(i0 + r) * XS + d] : 0.0;
+      Bs[r][tx] = (j0 + r < nb && d < D) ? XB[(j0 + r) * XS + d] : 0.0;
+    }
+    __syncthreads();
+    for (int d = 0; d < 32; d++) {
+      const double b = Bs[tx][d];
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[k] += fabs(As[ty + 8 * k][d] - b);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int64_t i = i0 + ty + 8 * k, j = j0 + tx;
+    if (i < na && j < nb) K[i * ldk + j] = (symmetric && i == j) ? 1.0 + lambda : exp(-acc[k] * inv_sigma);
+  }
+}
+
+struct ExWs {
+  int XS, nchD;
+  size_t off_center, off_XA, off_XAch, off_bA, off_bAc, off_XB, off_XBch, off_bB, off_bBc, total;
+};
+
+static ExWs ex_ws(int nat, int64_t na, int64_t nb) {
+  ExWs w;
+  const int D = descr_size(nat), KS = (D + 3) / 4;
+  w.nchD = (KS + kGemmKC - 1) / kGemmKC;
+  w.XS = w.nchD * 4 * kGemmKC;
+  if (w.XS % 8 == 0) w.XS += 4;
+  size_t off = 0;
+  auto take = [&](size_t doubles) {
+    size_t o = off;
+    off += (doubles * sizeof(double) + 255) / 256 * 256;
+    return o;
+  };
+  w.off_center = take(D);
+  w.off_XA = take((size_t)na * w.XS);
+  w.off_XAch = take((size_t)w.nchD * na * 4 * kGemmKC);
+  w.off_bA = take((size_t)na + 2);
+  w.off_bAc = take((size_t)na + 2);
+  w.off_XB = take((size_t)nb * w.XS);
+  w.off_XBch = take((size_t)w.nchD * nb * 4 * kGemmKC);
+  w.off_bB = take((size_t)nb + 2);
+  w.off_bBc = take((size_t)nb + 2);
+  w.total = off;
+  return w;
+}
+
+}  // namespace kreg
+
+extern "C" size_t kreg_kernel_block_ex_workspace_bytes(int natoms, int64_t na, int64_t nb) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || na < 0 || nb < 0) return 0;
+  return ex_ws(natoms, na, nb).total;
+}
+
+extern "C" int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double *xyz_a, int64_t nb,
+                                    const double *xyz_b, const double *xeq, double sigma, int symmetric, double lambda,
+                                    double *Kout, int64_t ldk, void *workspace, size_t workspace_bytes, void *stream) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  if (kind < KREG_KERNEL_GAUSSIAN || kind > KREG_KERNEL_LAPLACIAN) return KREG_E_BADARG;
+  if (kind == KREG_KERNEL_MATERN && (nn < 0 || nn > 10)) return KREG_E_UNSUPPORTED;
+  if (na < 0 || nb < 0 || !xeq || !(sigma > 0.0) || ldk < nb) return KREG_E_BADARG;
+  if (symmetric && na != nb) return KREG_E_BADARG;
+  if (na == 0 || nb == 0) return KREG_OK;
+  if (!xyz_a || !xyz_b || !Kout || !workspace) return KREG_E_BADARG;
+  const ExWs w = ex_ws(natoms, na, nb);
+  if (workspace_bytes < w.total) return KREG_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char *ws = static_cast<char *>(workspace);
+  auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
+  double *center = at(w.off_center);
+  const double c1 = kExpScale / (sigma * sigma);
+  int rc = launch_descriptor_mean(natoms, nb, xyz_b, xeq, center, st);  // the centre comes from set B (the training side)
+  if (rc) return rc;
+  rc = launch_prep_rows(natoms, na, xyz_a, xeq, center, w.XS, c1, at(w.off_XA), at(w.off_bA), at(w.off_bAc), st);
+  if (rc) return rc;
+  rc = launch_prep_rows(natoms, nb, xyz_b, xeq, center, w.XS, c1, at(w.off_XB), at(w.off_bB), at(w.off_bBc), st);
+  if (rc) return rc;
+  if (kind == KREG_KERNEL_LAPLACIAN) {
+    dim3 grid((unsigned)((nb + 31) / 32), (unsigned)((na + 31) / 32));
+    laplacian_block_kernel<<<grid, 256, 0, st>>>(descr_size(natoms), na, at(w.off_XA), nb, at(w.off_XB), w.XS, 1.0 / sigma,
+                                                 symmetric, lambda, Kout, ldk);
+    KREG_LAUNCH_CHECK();
+    return KREG_OK;
+  }
+  rc = launch_chunk_rows(na, w.XS, kGemmKC, w.nchD, 4 * kGemmKC, at(w.off_XA), at(w.off_XAch), st);
+  if (rc) return rc;
+  rc = launch_chunk_rows(nb, w.XS, kGemmKC, w.nchD, 4 * kGemmKC, at(w.off_XB), at(w.off_XBch), st);
+  if (rc) return rc;
+  ValuesArgs a = {};
+  a.XA = at(w.off_XA);
+  a.XB = at(w.off_XB);
+  a.XAch = at(w.off_XAch);
+  a.XBch = at(w.off_XBch);
+  a.XSC = 4 * kGemmKC;
+  a.XS = w.XS;
+  a.na = na;
+  a.nb = nb;
+  a.strideA = na;
+  a.strideB = nb;
+  a.nchunks = w.nchD;
+  a.c1 = c1;
+  a.lambda = lambda;
+  a.all_cols = 1;
+  a.row_begin = 0;
+  a.row_end = na;
+  a.K = Kout;
+  a.ldk = ldk;
+  a.biasB = at(w.off_bBc);
+  if (kind == KREG_KERNEL_GAUSSIAN) {
+    a.biasA = at(w.off_bA);
+    rc = launch_gemm_epi(a, EPI_K, st);
+    if (rc || !symmetric) return rc;
+    // exact 1 + lambda on the diagonal of a symmetric block (the tile kernel's own diagonal logic belongs to the K build)
+    return launch_set_diagonal(na, Kout, ldk, 1.0 + lambda, st);
+  }
+  a.symmetric = 0;  // every tile is computed; the diagonal is set in the epilogue through the flag below
+  a.biasA = at(w.off_bAc);
+  a.kind = kind;
+  a.nn = nn;
+  a.inv_sigma = 1.0 / sigma;
+  if (kind == KREG_KERNEL_MATERN) {
+    auto fact = [](int n) {
+      double f = 1.0;
+      for (int i = 1; i <= n; i++) f *= i;
+      return f;
+    };
+    for (int m = 0; m <= nn; m++) {
+      const int kk = nn - m;  // MLatomF's summation index (A_KRR_kernel.f90:839-844)
+      a.mat_c[m] = fact(nn) / fact(2 * nn) * (fact(nn + kk) / fact(kk) / fact(nn - kk));
+    }
+  }
+  rc = launch_gemm_epi(a, EPI_KR, st);
+  if (rc || !symmetric) return rc;
+  return launch_set_diagonal(na, Kout, ldk, 1.0 + lambda, st);
 }
 
 #ifdef KREG_DEBUG_BIAS

@@ -32,22 +32,29 @@ def shard_range(n: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def triangle_row_slabs(m: int, world_size: int, align: int = 1) -> List[Tuple[int, int]]:
+def _snap(r: int, align: int, offset: int) -> int:
+    """Nearest row boundary that does not split a geometry's gradient rows: offset + k * align for rows past `offset`
+    (offset = NtrVal, align = 3 Nat); rows of the value block are left where they are."""
+    if align <= 1 or r <= offset:
+        return r
+    return offset + int(round((r - offset) / align)) * align
+
+
+def triangle_row_slabs(m: int, world_size: int, align: int = 1, offset: int = 0) -> List[Tuple[int, int]]:
     """Row ranges of an m x m LOWER triangle with (nearly) equal element counts: boundary r_k solves
-    r(r+1)/2 = k/world * m(m+1)/2.  `align` rounds interior boundaries (e.g. to 3*Nat so a geometry's
-    gradient rows are never split)."""
+    r(r+1)/2 = k/world * m(m+1)/2.  `align` / `offset` snap interior boundaries to offset + k * align (3*Nat rows per
+    geometry after the NtrVal value rows) so that a geometry's gradient rows are never split."""
     cuts = [0]
     total = m * (m + 1) / 2.0
     for k in range(1, world_size):
         r = int(round((-1.0 + math.sqrt(1.0 + 8.0 * total * k / world_size)) / 2.0))
-        if align > 1:
-            r = int(round(r / align)) * align
+        r = _snap(r, align, offset)
         cuts.append(min(max(r, cuts[-1]), m))
     cuts.append(m)
     return [(cuts[i], cuts[i + 1]) for i in range(world_size)]
 
 
-def sub_slabs(slab: Tuple[int, int], pieces: int, align: int = 1) -> List[Tuple[int, int]]:
+def sub_slabs(slab: Tuple[int, int], pieces: int, align: int = 1, offset: int = 0) -> List[Tuple[int, int]]:
     """Split one rank's row slab [r0, r1) of the lower triangle into `pieces` consecutive row ranges of (nearly) equal
     AREA -- the unit of the pipelined gather: a piece is sent while the next one is still being assembled."""
     r0, r1 = slab
@@ -57,9 +64,7 @@ def sub_slabs(slab: Tuple[int, int], pieces: int, align: int = 1) -> List[Tuple[
     a0, a1 = r0 * (r0 + 1) / 2.0, r1 * (r1 + 1) / 2.0
     for k in range(1, pieces):
         t = a0 + (a1 - a0) * k / pieces
-        r = int(round((-1.0 + math.sqrt(1.0 + 8.0 * t)) / 2.0))
-        if align > 1:
-            r = int(round(r / align)) * align
+        r = _snap(int(round((-1.0 + math.sqrt(1.0 + 8.0 * t)) / 2.0)), align, offset)
         cuts.append(min(max(r, cuts[-1]), r1))
     cuts.append(r1)
     return [(cuts[i], cuts[i + 1]) for i in range(pieces) if cuts[i + 1] > cuts[i]]
@@ -95,7 +100,7 @@ def gather_row_slabs(k_full: Optional[torch.Tensor], slab: torch.Tensor, slabs: 
 
 def build_kernel_matrix_sharded(build_rows: Callable[[int, int, torch.Tensor, int], None], m: int, device,
                                 root: int = 0, align: int = 1, pieces: int = 4,
-                                stats: Optional[dict] = None) -> Optional[torch.Tensor]:
+                                stats: Optional[dict] = None, offset: int = 0) -> Optional[torch.Tensor]:
     """Assemble the lower triangle of K on all ranks, gather on `root`.  `build_rows(r0, r1, out, row_offset)` must fill
     rows [r0, r1) (columns j <= i) into `out`, whose row 0 is matrix row `row_offset` and whose row stride may be
     SHORTER than M (>= the last row's defined length).  Returns K on the root, None elsewhere.
@@ -106,8 +111,10 @@ def build_kernel_matrix_sharded(build_rows: Callable[[int, int, torch.Tensor, in
     of piece s+1.  The root receives into staging buffers and scatters them into its M x M matrix with one strided
     device copy per piece.  `stats` (optional dict) receives the byte count sent to the root."""
     rank, ws = world()
-    slabs = triangle_row_slabs(m, ws, align)
-    plans = [sub_slabs(slabs[r], pieces, align) for r in range(ws)]
+    # boundaries fall on offset + k * align (gradient matrices: offset = NtrVal, align = 3 Nat): a piece that ends at row b
+    # then also ends at COLUMN b, so its rows fit a buffer of width b
+    slabs = triangle_row_slabs(m, ws, align, offset)
+    plans = [sub_slabs(slabs[r], pieces, align, offset) for r in range(ws)]
     if rank == root:
         k = torch.empty((m, m), dtype=torch.float64, device=device)
         stages, reqs = [], []

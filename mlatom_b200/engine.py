@@ -173,6 +173,27 @@ def kernel_block(xyz_a: torch.Tensor, xyz_b: torch.Tensor, xeq_: torch.Tensor, s
     return out
 
 
+KERNEL_KINDS = {"gaussian": 0, "exponential": 1, "matern": 2, "laplacian": 3}
+
+
+def kernel_block_ex(kind: str, xyz_a: torch.Tensor, xyz_b: torch.Tensor, xeq_: torch.Tensor, sigma: float, nn: int = 2,
+                    symmetric: bool = False, lam: float = 0.0) -> torch.Tensor:
+    """Value-value kernel block for MLatomF's other kernel functions on the RE descriptor ('Gaussian', 'exponential',
+    'Matern' of order nn, 'Laplacian'; Kfunk, A_KRR_kernel.f90:806-851).  symmetric=True (same geometry set on both
+    sides) puts exactly 1 + lam on the diagonal: the matrix ``solve`` factorises for a values-trained model."""
+    xyz_a, xyz_b = _dev(xyz_a, xeq_.device), _dev(xyz_b, xeq_.device)
+    na, nat, _ = xyz_a.shape
+    nb = xyz_b.shape[0]
+    out = torch.empty((na, nb), dtype=F64, device=xyz_a.device)
+    ws_bytes = _lib.load().kreg_kernel_block_ex_workspace_bytes(nat, na, nb)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xyz_a.device)
+    with _on(xyz_a):
+        call("kreg_kernel_block_ex", KERNEL_KINDS[kind.lower()], int(nn), nat, na, _ptr(xyz_a), nb, _ptr(xyz_b), _ptr(xeq_),
+             float(sigma), 1 if symmetric else 0, float(lam), _ptr(out), out.stride(0), _ptr(ws), ws_bytes,
+             _stream(xyz_a.device))
+    return out
+
+
 def solve(k: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """alpha = (K)^-1 y by in-place Cholesky (cuSOLVER potrf/potrs; mathUtils.f90:8-104).
 
@@ -499,6 +520,7 @@ class GraphPredictor:
     def __call__(self, xyz: np.ndarray):
         """xyz (n, Nat, 3) numpy -> (E (n,), dE/dxyz (n, Nat, 3)) numpy views of the pinned result buffers."""
         self._x_np[...] = xyz
-        self.graph.replay()
-        call("kreg_stream_synchronize", self._current_stream())
+        with _on(self.x):  # a graph replays on the CURRENT device's stream: make that the device it was captured on
+            self.graph.replay()
+            call("kreg_stream_synchronize", self._current_stream())
         return (self._e_np if self.energy else None), (self._g_np if self.gradient else None)

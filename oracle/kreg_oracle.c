@@ -532,6 +532,47 @@ void kro_kernel_matrix_factored(int nat, int ntr, int ntrval, int ntrgr, const d
   free(J);
 }
 
+/* ---- MLatomF's other kernel functions on the same descriptor -------------------------------
+ * distance (A_KRR_kernel.f90:2040-2074): sum of squares for Gaussian, its square root for exponential and Matern,
+ * sum of absolute differences for Laplacian.  Kfunk (A_KRR_kernel.f90:806-851): Gaussian exp(-d/(2 sigma^2)),
+ * Laplacian / exponential exp(-d/sigma), Matern exp(-d/sigma) n!/(2n)! sum_k (n+k)!/(k!(n-k)!) (2d/sigma)^(n-k).
+ * kind: 0 Gaussian, 1 exponential, 2 Matern (order nn), 3 Laplacian.  PARITY UNPINNED: the MLatomF binary is absent
+ * from the reference checkout and KREG.so only has the Gaussian kernel, so nothing executable pins these three. */
+static double factorial_rprec(int nn) { /* mathUtils.f90:577-590 */
+  double f = 1.0;
+  for (int ii = 1; ii <= nn; ii++) f = f * ii;
+  return f;
+}
+
+static double mlatomf_distance(int kind, int D, const double *xi, const double *xj) {
+  double d = 0.0;
+  if (kind == 3) {
+    for (int k = 0; k < D; k++) d = d + fabs(xi[k] - xj[k]);
+  } else {
+    for (int k = 0; k < D; k++) d = d + (xi[k] - xj[k]) * (xi[k] - xj[k]);
+    if (kind == 1 || kind == 2) d = sqrt(d);
+  }
+  return d;
+}
+
+static double mlatomf_kfunk(int kind, int nn, int D, const double *xi, const double *xj, double sigma) {
+  const double dist = mlatomf_distance(kind, D, xi, xj);
+  if (kind == 0) return exp(-1.0 * dist / (2 * sigma * sigma));
+  if (kind == 1 || kind == 3) return exp(-1.0 * dist / sigma);
+  double k = 0.0;
+  for (int kk = 0; kk <= nn; kk++)
+    k = k + factorial_rprec(nn + kk) / factorial_rprec(kk) / factorial_rprec(nn - kk) * pow(2 * dist / sigma, nn - kk);
+  return exp(-1.0 * dist / sigma) * factorial_rprec(nn) / factorial_rprec(2 * nn) * k;
+}
+
+/* K[i][j] = Kfunk(Xa[i], Xb[j]), row-major na x nb (calcKernel / calc_Kvalidate loops, A_KRR_kernel.f90:130-223) */
+void kro_kernel_block_generic(int kind, int nn, int D, long na, const double *Xa, long nb, const double *Xb,
+                              double sigma, double *K) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < na; i++)
+    for (long j = 0; j < nb; j++) K[i * nb + j] = mlatomf_kfunk(kind, nn, D, Xa + i * D, Xb + j * D, sigma);
+}
+
 int kro_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

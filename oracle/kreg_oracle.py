@@ -173,3 +173,16 @@ def hessian_kregf90(x_tr, alpha, sigma, ntrval, xyz_te, x_te):
     load().kro_hessian_kregf90(c_int(nat), c_int(ntrval), _d(x_tr), _d(a), c_double(sigma), c_long(npred), _d(xyz_te),
                                _d(x_te), _d(h))
     return h
+
+
+KERNEL_KINDS = {"gaussian": 0, "exponential": 1, "matern": 2, "laplacian": 3}
+
+
+def kernel_block_generic(kind: str, x_a, x_b, sigma: float, nn: int = 2) -> np.ndarray:
+    """MLatomF's Kfunk (A_KRR_kernel.f90:806-851) between two descriptor sets: (na, D) x (nb, D) -> (na, nb).
+    Parity unpinned (no executable MLatomF here); restated literally from the Fortran."""
+    x_a, x_b = _c(x_a), _c(x_b)
+    out = np.zeros((x_a.shape[0], x_b.shape[0]))
+    load().kro_kernel_block_generic(c_int(KERNEL_KINDS[kind.lower()]), c_int(nn), c_int(x_a.shape[1]), c_long(x_a.shape[0]),
+                                    _d(x_a), c_long(x_b.shape[0]), _d(x_b), c_double(sigma), _d(out))
+    return out

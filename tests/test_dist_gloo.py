@@ -24,12 +24,12 @@ def test_shard_range_covers_everything():
 
 
 def test_triangle_slabs_balanced_and_aligned():
-    for m, ws, align in ((50000, 8, 1), (56000, 8, 27), (100, 3, 1), (5, 8, 1)):
-        slabs = kd.triangle_row_slabs(m, ws, align)
+    for m, ws, align, offset in ((50000, 8, 1, 0), (56000, 8, 27, 2000), (100, 3, 1, 0), (5, 8, 1, 0), (54000, 4, 27, 0)):
+        slabs = kd.triangle_row_slabs(m, ws, align, offset)
         assert slabs[0][0] == 0 and slabs[-1][1] == m and len(slabs) == ws
         assert all(slabs[i][1] == slabs[i + 1][0] for i in range(ws - 1))
-        if align > 1:
-            assert all(a % align == 0 for a, _ in slabs)
+        if align > 1:  # boundaries inside the gradient part never split a geometry's 3 Nat rows
+            assert all(a <= offset or (a - offset) % align == 0 for a, _ in slabs)
         if m >= 1000:
             areas = [b * (b + 1) / 2 - a * (a + 1) / 2 for a, b in slabs]
             assert max(areas) / (sum(areas) / ws) < 1.02
@@ -64,11 +64,12 @@ def _worker(rank, ws, port, tmp):
         else:
             assert k is None and stats["gather_bytes"] > 0
         # pieces: equal-area split of a slab, aligned
-        for slab, pieces, align in (((1000, 5000), 4, 1), ((27 * 10, 27 * 200), 5, 27), ((3, 4), 4, 1)):
-            sub = kd.sub_slabs(slab, pieces, align)
+        for slab, pieces, align, offset in (((1000, 5000), 4, 1, 0), ((200 + 27 * 10, 200 + 27 * 200), 5, 27, 200),
+                                            ((3, 4), 4, 1, 0)):
+            sub = kd.sub_slabs(slab, pieces, align, offset)
             assert sub[0][0] == slab[0] and sub[-1][1] == slab[1]
             assert all(sub[i][1] == sub[i + 1][0] for i in range(len(sub) - 1))
-            assert all(a % align == 0 for a, _ in sub)
+            assert all((a - offset) % align == 0 for a, _ in sub)
             if slab[1] - slab[0] > 100:
                 areas = [b * (b + 1) / 2 - a * (a + 1) / 2 for a, b in sub]
                 assert max(areas) / (sum(areas) / len(areas)) < 1.1

@@ -30,7 +30,10 @@ def _worker(rank, ws, port, tmp):
         os.environ["NCCL_DEBUG"] = "WARN"
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev)
+    import datetime
+
+    # a rank that raises must not leave its peer waiting for NCCL's default 10-minute watchdog
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev, timeout=datetime.timedelta(seconds=120))
     try:
         from mlatom_b200 import dist as kd, engine, synthetic as S
 
@@ -49,7 +52,7 @@ def _worker(rank, ws, port, tmp):
 
             stats = {}
             k = kd.build_kernel_matrix_sharded(build_rows, m, dev, root=0, align=3 * nat if grads else 1, pieces=3,
-                                               stats=stats)
+                                               stats=stats, offset=nv if grads else 0)
             y = t(np.concatenate([e_h - e_h.mean()] + ([g_h.reshape(-1)] if grads else [])))
             alpha = torch.empty(m, dtype=torch.float64, device=dev)
             if rank == 0:

@@ -90,3 +90,21 @@ def test_oracle_against_live_reference(oracle):
         e, g = ref_kreg.predict(xtr, X, xte, Xte, alpha, 1.4, nv, ng)
         eo, go = oracle.predict_kregf90(xtr, X, alpha, 1.4, nv, ng, xte, Xte)
         assert np.array_equal(e, eo) and np.array_equal(g, go)
+
+
+def test_other_kernel_functions_closed_forms(oracle):
+    """The oracle's restatement of MLatomF's Kfunk (A_KRR_kernel.f90:806-851) against the closed forms of the Matern
+    family (n = 0: exp(-x); 1: (1 + x) exp(-x); 2: (1 + x + x^2/3) exp(-x); 3: (1 + x + 2x^2/5 + x^3/15) exp(-x), x = r/sigma)
+    and the definitions of the exponential and Laplacian kernels."""
+    rng = np.random.default_rng(3)
+    a, b, sigma = rng.random((6, 11)), rng.random((5, 11)), 0.8
+    r = np.linalg.norm(a[:, None] - b[None], axis=-1)
+    x = r / sigma
+    forms = {0: np.exp(-x), 1: (1 + x) * np.exp(-x), 2: (1 + x + x * x / 3) * np.exp(-x),
+             3: (1 + x + 2 * x * x / 5 + x ** 3 / 15) * np.exp(-x)}
+    for nn, want in forms.items():
+        assert np.abs(oracle.kernel_block_generic("matern", a, b, sigma, nn=nn) - want).max() <= 1e-15
+    assert np.abs(oracle.kernel_block_generic("exponential", a, b, sigma) - np.exp(-x)).max() <= 1e-15
+    l1 = np.abs(a[:, None] - b[None]).sum(-1)
+    assert np.abs(oracle.kernel_block_generic("laplacian", a, b, sigma) - np.exp(-l1 / sigma)).max() <= 1e-15
+    assert np.abs(oracle.kernel_block_generic("gaussian", a, b, sigma) - np.exp(-r * r / (2 * sigma ** 2))).max() <= 1e-15

@@ -53,7 +53,7 @@ def main():
     prior = float(e_h.mean())
     y = torch.from_numpy(np.concatenate([e_h - prior] + ([g_h.reshape(-1)] if args.grads else []))).to(dev)
     align = 3 * nat if args.grads else 1
-    slabs = kd.triangle_row_slabs(m, ws, align)
+    slabs = kd.triangle_row_slabs(m, ws, align, nv if args.grads else 0)
 
     def build_rows(r0, r1, out, row_offset):
         engine.build_kernel_matrix(xyz, xeq, args.sigma, args.lam, args.lam, use_values=True, use_gradients=args.grads,
