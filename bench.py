@@ -78,6 +78,14 @@ def set_workload(name, world):
     TRAFFIC, TRAFFIC_SOURCE = measured_traffic(KERNEL)
 
 
+def shared_config():
+    """The workload description, IDENTICAL in both arms (`--impl ours` / `--impl reference`): what is arm-specific goes to
+    the top-level `notes` key, so that the driver's config comparison sees the same object."""
+    return {"workload": WORKLOAD, "natoms": NAT, "descriptor_size": D, "ntrain": NTRAIN, "ntest_per_gpu": NTEST,
+            "sigma": SIGMA, "lambda": LAMBDA, "prior": "mean",
+            "model": "values-trained KREG model (RE descriptor, Gaussian kernel), energies + gradients predicted"}
+
+
 def training_set():
     from mlatom_b200 import synthetic as S
 
@@ -198,34 +206,62 @@ def kbuild_configs(engine, dev, hbm_peak, fp64_peak):
     from mlatom_b200 import synthetic as S
 
     out = {}
-    eq = S.equilibrium(NAT)
-    xeq = engine.xeq(torch.from_numpy(eq).to(dev))
-    for name, ntr, grads in (("cfg3_values_50k", 50000, False), ("cfg5_gradients_56k", 2000, True)):
+    for name, nat, ntr, grads in (("cfg3_values_50k", NAT, 50000, False), ("cfg5_gradients_56k", NAT, 2000, True),
+                                  ("aspirin_gradients_55k", 21, 857, True), ("nat12_gradients_55k", 12, 1500, True)):
+        d = nat * (nat - 1) // 2
+        eq = S.equilibrium(nat)
+        xeq = engine.xeq(torch.from_numpy(eq).to(dev))
+        sigma = SIGMA if nat <= 12 else 2.0
         xyz = torch.from_numpy(S.geometries(eq, ntr, seed=1)).to(dev)
-        m = ntr + (3 * NAT * ntr if grads else 0)
+        m = ntr + (3 * nat * ntr if grads else 0)
         k = torch.empty((m, m), dtype=torch.float64, device=dev)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ms = []
         for it in range(4):
             torch.cuda.synchronize()
             ev[0].record()
-            engine.build_kernel_matrix(xyz, xeq, SIGMA, LAMBDA, LAMBDA, use_gradients=grads, out=k)
+            engine.build_kernel_matrix(xyz, xeq, sigma, LAMBDA, LAMBDA, use_gradients=grads, out=k)
             ev[1].record()
             torch.cuda.synchronize()
             if it:
                 ms.append(ev[0].elapsed_time(ev[1]))
         t = float(np.mean(ms))
         nbytes = 4.0 * m * (m + 1)
-        rec = {"M": m, "ms": t, "bytes_lower_triangle": nbytes, "gb_per_s": nbytes / t * 1e-6,
+        rec = {"natoms": nat, "ntrain": ntr, "M": m, "ms": t, "bytes_lower_triangle": nbytes, "gb_per_s": nbytes / t * 1e-6,
                "frac_of_hbm_copy_peak": nbytes / t * 1e-6 / hbm_peak}
         if not grads:
-            fp64_ms = ntr * (ntr + 1) / 2 * (3 * D + 3) / (fp64_peak * 1e12) * 1e3
+            fp64_ms = ntr * (ntr + 1) / 2 * (3 * d + 3) / (fp64_peak * 1e12) * 1e3
             rec.update({"bound": "fp64 issue (SURVEY.md App. D)", "fp64_bound_ms": fp64_ms, "frac_of_fp64_bound": fp64_ms / t})
         else:
             rec.update({"bound": "hbm write"})
         out[name] = rec
         del k
         torch.cuda.empty_cache()
+    return out
+
+
+def md_steps_per_s(engine, model, dev):
+    """Batched NVE (mlatom_b200.md.BatchedNVE: fused velocity-Verlet kernels + kreg_predict, one CUDA graph per step) on
+    this run's Ntrain = 10k model: steps/s for 1, 64 and 4096 trajectories (md.py:158-205 does one trajectory per call)."""
+    import torch
+
+    from mlatom_b200 import md, synthetic as S
+
+    eq = S.equilibrium(NAT)
+    masses = torch.from_numpy(np.where(S.atomic_numbers(NAT) == 1, 1.008, 12.011)).to(dev)
+    out = {}
+    for b in (1, 64, 4096):
+        x0 = torch.from_numpy(S.geometries(eq, b, 5, spread=0.02)).to(dev)
+        v0 = torch.zeros_like(x0)
+        sim = md.BatchedNVE(model, x0, v0, masses, dt=0.1, use_graph=True, units="mlatom")
+        sim.run(50)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 500 if b < 4096 else 200
+        sim.run(n)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[f"trajectories_{b}"] = {"steps_per_s": n / dt, "trajectory_steps_per_s": n * b / dt, "us_per_step": dt / n * 1e6}
     return out
 
 
@@ -488,11 +524,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "natoms": NAT, "ntrain": NTRAIN, "ntest_per_gpu": NTEST, "sigma": SIGMA,
-                   "note": "CPU only: MLatomF's optimised prediction loop restated in C/OpenMP (oracle/kreg_oracle.c), "
-                           "all host threads; geometries/s is independent of the sample size.  The port is the arm "
-                           "because it is the FASTER of the two reference programs (BASELINE metric: 'vs MLatomF CPU'); "
-                           "the reference's shipped KREG.so, run through oracle/_ref, is reported beside it"},
+        "config": shared_config(),
+        "notes": {"arm": "CPU only: MLatomF's optimised prediction loop restated in C/OpenMP (oracle/kreg_oracle.c), "
+                         "all host threads; geometries/s is independent of the sample size.  The port is the arm "
+                         "because it is the FASTER of the two reference programs (BASELINE metric: 'vs MLatomF CPU'); "
+                         "the reference's shipped KREG.so, run through oracle/_ref, is reported beside it"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "cpu_baseline_reference_as_shipped": shipped,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -516,6 +552,7 @@ def run_ours(args):
         # NCCL_DEBUG=VERSION (this image's default) makes NCCL print its version on STDOUT, next to the one JSON line
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL still prints must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     engine.device_check()
 
@@ -641,10 +678,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "natoms": NAT, "descriptor_size": D, "ntrain": NTRAIN, "ntest_per_gpu": NTEST,
-                   "sigma": SIGMA, "lambda": LAMBDA, "prior": "mean", "model": "values-trained, alpha solved by cuSOLVER potrf on rank 0",
-                   "parallelism": f"test batches sharded over {world} GPU(s), alpha broadcast once",
-                   "l2": f"inputs+outputs {NTEST * (NAT * 48 + 8) / 1e6:.0f} MB per step per GPU exceed the 126 MB L2; no flush needed"},
+        "config": shared_config(),
+        "notes": {"arm": "alpha solved by cuSOLVER potrf on rank 0 and broadcast once; "
+                         f"test batches sharded over {world} GPU(s)",
+                  "l2": f"inputs+outputs {NTEST * (NAT * 48 + 8) / 1e6:.0f} MB per step per GPU exceed the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "gpu_launches": args.steps,
         "roofline": {"bound": "tensor", "pipe": "FP64 tensor core (DMMA.8x8x4); shares the FP64 pipe with DFMA",
@@ -681,6 +718,7 @@ def run_ours(args):
     if world == 1 and args.workload == "cfg2":
         line["kbuild_configs"] = kbuild_configs(engine, dev, line["kbuild"]["hbm_peak_gbs"], peak_dmma)
         line["step_latency"] = step_latency(engine, model, dev)
+        line["md_steps_per_s"] = md_steps_per_s(engine, model, dev)
     if world == 1 and not args.no_cpu:
         base, n_cpu, _ = cpu_baseline(eq, xyz_tr, alpha.cpu().numpy(), prior, seconds=12.0)
         e_cpu, g_cpu = base.pop("results")

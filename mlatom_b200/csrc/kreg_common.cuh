@@ -178,7 +178,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
     asm("mov.u32 %0, %%total_smem_size;" : "=r"(tot_size));
     KREG_CHECK(bytes > 0 && (bytes & 15u) == 0, 1);
     KREG_CHECK((reinterpret_cast<uintptr_t>(src_gmem) & 15) == 0 && (smem_u32(dst_smem) & 15u) == 0, 2);
-    KREG_CHECK(smem_u32(dst_smem) + bytes <= tot_size, 4);
+    // shared-window addresses of user data start after the 1 KB the system reserves per CTA on sm_90+
+    // (cudaDevAttrReservedSharedMemoryPerBlock), which %total_smem_size does not include
+    KREG_CHECK(smem_u32(dst_smem) + bytes <= tot_size + 1024u, 4);
   }
 #endif
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

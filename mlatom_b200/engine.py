@@ -494,7 +494,9 @@ class GraphPredictor:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # capture on a stream of THIS device: torch's default capture stream is one process-wide object created
+            # on whichever device captured first, and a graph captured through it on another device comes out empty
+            with torch.cuda.graph(self.graph, stream=side):
                 self._body()
 
     def _current_stream(self) -> int:

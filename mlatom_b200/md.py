@@ -90,7 +90,7 @@ class BatchedNVE:
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize(dev)
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
+                with torch.cuda.graph(self.graph, stream=side):  # a stream of this device (see engine.GraphPredictor)
                     self._step()
                 for dst, src in zip(state, saved):
                     dst.copy_(src)  # warm-up and capture advanced the state: restore t = 0

@@ -62,3 +62,24 @@ def reference_mlatom_data():
         return None
     return ref_data
 
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """With the bounds-checking build (KREG_LIB=.../libkreg_b200_dbg.so) the in-kernel failure counter must be zero at
+    the end of the session (compute-sanitizer is closed on this GPU pool)."""
+    import ctypes
+    import os
+
+    if not os.environ.get("KREG_LIB", "").endswith("_dbg.so"):
+        return
+    try:
+        from mlatom_b200 import _lib
+
+        code, line = ctypes.c_int(0), ctypes.c_int(0)
+        n = _lib.load().kreg_debug_bounds_failures(ctypes.byref(code), ctypes.byref(line))
+    except Exception as err:  # pragma: no cover
+        print(f"\nkreg_debug_bounds_failures could not be read: {err}")
+        return
+    print(f"\nkreg_debug_bounds_failures = {n} (first code {code.value}, source line {line.value})")
+    if n > 0:
+        session.exitstatus = 1
