@@ -625,6 +625,7 @@ struct GradArgs {
   double *P;             // [i1 - i0][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
   int64_t p_i0;          // first geometry i whose gradient rows intersect [row_begin, row_end): row 0 of P
   int64_t p_i1;          // one past the last such geometry
+  int64_t c_i0, c_i1;    // the geometries THIS launch covers (a chunk of [p_i0, p_i1): the assembly is pipelined in chunks)
   int ES;                // doubles per E block: Nat*Nat*3 rounded up to even (16-byte aligned blocks for bulk copies)
 };
 
@@ -720,7 +721,7 @@ __global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
   double *tab = psm + SM::off_tab(XS);
   uint64_t *bar = reinterpret_cast<uint64_t *>(psm + SM::off_bar(XS));
 
-  const int64_t i = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.y + a.c_i0;  // this launch covers geometries [c_i0, c_i1)
   const int64_t rbase = a.nv + i * G3;
   if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
   const bool full = a.fill == KREG_FILL_FULL;
@@ -848,7 +849,7 @@ __global__ void __launch_bounds__(128, 5) pair_terms_small_kernel(const GradArgs
   double *Ei = qsm, *Xi = qsm + SM::OFF_XI, *Xj = qsm + SM::OFF_XJ, *Us = qsm + SM::OFF_US, *tab = qsm + SM::OFF_TAB;
   uint64_t *bar = reinterpret_cast<uint64_t *>(qsm + SM::OFF_BAR);
 
-  const int64_t i = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.y + a.c_i0;  // this launch covers geometries [c_i0, c_i1)
   const int64_t rbase = a.nv + i * G3;
   if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
   const bool full = a.fill == KREG_FILL_FULL;
@@ -958,7 +959,7 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
   uint64_t *bar = reinterpret_cast<uint64_t *>(esm + SM::OFF_BAR);
   const int XS = a.XS;
 
-  const int64_t i = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.y + a.c_i0;  // this launch covers geometries [c_i0, c_i1)
   const bool full = a.fill == KREG_FILL_FULL;
   const int64_t jend = full ? a.ntr : i + 1;
   const int64_t jb0 = (int64_t)blockIdx.x * (NJB * TJ);
@@ -1081,7 +1082,7 @@ __global__ void __launch_bounds__(256) pair_terms_rt_kernel(const GradArgs a, in
   double *Us = Dl + (((size_t)JT * DP + 1) & ~(size_t)1);  // [JT][PWS]
   double *tab = Us + (((size_t)JT * PWS + 1) & ~(size_t)1);
 
-  const int64_t i = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.y + a.c_i0;  // this launch covers geometries [c_i0, c_i1)
   const int64_t rbase = a.nv + i * G3;
   if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
   const bool full = a.fill == KREG_FILL_FULL;
@@ -1192,8 +1193,8 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
   const bool full = a.fill == KREG_FILL_FULL;
   const int64_t jb = (int64_t)blockIdx.x * TJ;
   // geometries i of this CTA: its chunk, clipped to the row range, and (lower fill) to i >= the block's first j
-  int64_t i_lo = (int64_t)blockIdx.y * NIB + a.p_i0, i_hi = i_lo + NIB;
-  if (i_hi > a.p_i1) i_hi = a.p_i1;
+  int64_t i_lo = (int64_t)blockIdx.y * NIB + a.c_i0, i_hi = i_lo + NIB;
+  if (i_hi > a.c_i1) i_hi = a.c_i1;
   if (!full && i_lo < jb) i_lo = jb;
   if (i_lo >= i_hi) return;
   const int nsteps = (int)(i_hi - i_lo);
@@ -1407,18 +1408,19 @@ static RtPlan rt_plan(int nat, const GradArgs &a) {
   return p;
 }
 
-static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, cudaStream_t st) {
+static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, bool emit, cudaStream_t st) {
   const RtPlan p = rt_plan(nat, a);
-  if (a.p_i1 <= a.p_i0) return KREG_OK;
+  if (a.c_i1 <= a.c_i0) return KREG_OK;
   if (pair_terms) {
     if (p.pair_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
     KREG_CUDA_TRY(cudaFuncSetAttribute(pair_terms_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pair_smem));
-    dim3 grid((unsigned)((a.ntr + p.JT - 1) / p.JT), (unsigned)a.ntr);
+    dim3 grid((unsigned)((a.ntr + p.JT - 1) / p.JT), (unsigned)(a.c_i1 - a.c_i0));
     pair_terms_rt_kernel<<<grid, 256, p.pair_smem, st>>>(a, nat, p.JT);
     KREG_LAUNCH_CHECK();
   }
+  if (!emit) return KREG_OK;
   if (p.threads > 256 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
-  dim3 grid((unsigned)((a.ntr + p.TJ - 1) / p.TJ), (unsigned)((a.p_i1 - a.p_i0 + p.NIB - 1) / p.NIB));
+  dim3 grid((unsigned)((a.ntr + p.TJ - 1) / p.TJ), (unsigned)((a.c_i1 - a.c_i0 + p.NIB - 1) / p.NIB));
   KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
   grad_emit_rt_kernel<0><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NIB, p.ei_global,
                                                                env_int("KREG_RT_INORDER", nat <= KREG_EMIT_INORDER_MAX ? 1 : 0));
@@ -1435,20 +1437,20 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st, bool do_pair, boo
     auto kern = pair_terms_small_kernel<NAT>;
     const size_t smem = (size_t)SM::DOUBLES * sizeof(double);
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((a.ntr + SM::JT - 1) / SM::JT), (unsigned)a.ntr);
+    dim3 grid((unsigned)((a.ntr + SM::JT - 1) / SM::JT), (unsigned)(a.c_i1 - a.c_i0));
     kern<<<grid, SM::JT, smem, st>>>(a);
     KREG_LAUNCH_CHECK();
   } else {
     auto kern = pair_terms_kernel<NAT>;
     const size_t smem = (size_t)PairSmem<NAT>::doubles(a.XS) * sizeof(double);
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((a.ntr + C::JT - 1) / C::JT), (unsigned)a.ntr);
+    dim3 grid((unsigned)((a.ntr + C::JT - 1) / C::JT), (unsigned)(a.c_i1 - a.c_i0));
     kern<<<grid, 256, smem, st>>>(a);
     KREG_LAUNCH_CHECK();
   }
   if (!do_emit) return KREG_OK;
   if constexpr (NAT <= KREG_EMIT_TEMPLATE_MAX) {
-    dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)a.ntr);
+    dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)(a.c_i1 - a.c_i0));
     auto emit = grad_emit_kernel<NAT>;
     const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
     KREG_CUDA_TRY(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
@@ -1466,16 +1468,17 @@ static int launch_grad_nat(const GradArgs &a, cudaStream_t st, bool do_pair, boo
 //   emit       : <= 10 atoms  grad_emit_kernel<NAT> (operands in registers: 5.1 TB/s at 9 atoms)
 //                >= 11        grad_emit_rt_kernel (operands in shared memory, j-block resident: 4.3 TB/s at 12, 3.6 at 21
 //                             and 24 atoms; the register version spills from 11 atoms up and stays at 3.2)
-static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
+// stage 1 = pair terms (+ value-gradient rows), stage 2 = emit, for the geometries [a.c_i0, a.c_i1)
+static int launch_grad(int nat, const GradArgs &a, int stage, cudaStream_t st) {
   const bool emit_rt = nat > KREG_EMIT_TEMPLATE_MAX || env_int("KREG_EMIT_RT", 0) != 0;
   const bool pair_rt = nat > KREG_FUSED_MAX_NATOMS || env_int("KREG_PAIR_RT", 0) != 0;
-  if (pair_rt) return launch_grad_rt(nat, a, true, st);
-  int rc = KREG_E_UNSUPPORTED;
+  const bool do_pair = stage == 1, do_emit = stage == 2;
+  if (do_pair && pair_rt) return launch_grad_rt(nat, a, true, false, st);
+  if (do_emit && emit_rt) return launch_grad_rt(nat, a, false, true, st);
   switch (nat) {
-#define KREG_CASE(N)                                    \
-  case N:                                               \
-    rc = launch_grad_nat<N>(a, st, true, !emit_rt);     \
-    break;
+#define KREG_CASE(N) \
+  case N:            \
+    return launch_grad_nat<N>(a, st, do_pair, do_emit);
 #ifdef KREG_ONLY_NAT9  /* experiment builds (tools/ab_kbuild.sh): one instantiation, seconds to compile */
     KREG_CASE(9)
 #else
@@ -1487,8 +1490,19 @@ static int launch_grad(int nat, const GradArgs &a, cudaStream_t st) {
     default:
       return KREG_E_UNSUPPORTED;
   }
-  if (rc || !emit_rt) return rc;
-  return launch_grad_rt(nat, a, false, st);
+}
+
+// Gradient blocks of the geometries [g.p_i0, g.p_i1): pair terms, then emit, on the caller's stream.  (Pipelining the two over
+// chunks of geometries on two side streams -- the pair-terms kernel of chunk c+1 under the emit kernel of chunk c -- was
+// measured and dropped: 3.57 -> 3.44 / 3.20 / 2.78 TB/s with 4 / 8 / 16 chunks at 21 atoms, 5.14 -> 5.02 / 4.89 / 4.70 at 9:
+// the emit kernel already fills every SM, so the second kernel only takes CTA slots away from it.)
+static int launch_grad_stages(int nat, GradArgs g, cudaStream_t st) {
+  if (g.p_i1 <= g.p_i0) return KREG_OK;
+  g.c_i0 = g.p_i0;
+  g.c_i1 = g.p_i1;
+  int rc = launch_grad(nat, g, 1, st);
+  if (rc) return rc;
+  return launch_grad(nat, g, 2, st);
 }
 
 // workspace carve-up helpers ---------------------------------------------------------------
@@ -1809,8 +1823,10 @@ extern "C" int kreg_build_kernel_matrix(int natoms, int64_t ntrain, int64_t ntrv
     g.P = reinterpret_cast<double *>(ws + w.off_P);
     g.p_i0 = gi0;
     g.p_i1 = gi1;
+    g.c_i0 = gi0;
+    g.c_i1 = gi1;
     g.ES = (natoms * natoms * 3 + 1) & ~1;
-    rc = launch_grad(natoms, g, st);
+    rc = launch_grad_stages(natoms, g, st);
     if (rc) return rc;
   }
   return KREG_OK;
