@@ -51,8 +51,9 @@ def measured_traffic(kernel):
     profiles/traffic.json (written by tools/ncu_summary.py next to the summary it was read from); None if the kernel
     has no entry -- never a constant kept in this file."""
     try:
+        norm = lambda k: k.replace("false", "0").replace("true", "1").replace(" ", "")  # ncu prints bool arguments as 0 / 1
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            rec = json.load(f).get(kernel)
+            rec = {norm(k): v for k, v in json.load(f).items()}.get(norm(kernel))
         return (rec["dram_bytes"], rec["source"]) if rec else (None, None)
     except (OSError, ValueError, KeyError):
         return None, None

@@ -170,6 +170,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+// non-blocking phase test: true once the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
 #ifdef KREG_DEBUG_BOUNDS

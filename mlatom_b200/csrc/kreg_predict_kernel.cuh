@@ -270,8 +270,11 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
   // ---- main loop over the training set ----
   for (int it = 0; it < total_stages; it++) {
     // producer duty: refill the stage every warp finished in the previous iteration.  Warp-uniform branch with the one
-    // issuing lane inside and an explicit reconvergence after it (see values_ring_kernel: with a bare `if (tid == 0)`
-    // the other lanes of warp 0 may run ahead while lane 0 is still issuing, sharing the warp's uniform registers)
+    // issuing lane inside it and an explicit reconvergence after it: with a bare `if (tid == 0) { wait; issue }` the other
+    // 31 lanes of warp 0 may run ahead into the tile code while lane 0 is still issuing, and the two paths share the
+    // warp's uniform registers.  Costs 0.7 % on cfg2 (51.5 -> 51.9 ms).  A non-blocking variant
+    // (mbarrier.test_wait, slots picked up one iteration later) was measured on the same box and dropped: equal at 9
+    // atoms, 2-5 % slower at 16-24 atoms where the copy needs the whole iteration to land.
     if (warp == 0 && it >= 1 && it - 1 + NSTAGE < total_stages) {
       if (lane == 0) {
         const int sp = (it - 1) % NSTAGE;

@@ -3,6 +3,7 @@
 
     python tools/ncu_summary.py launches <launches.csv> [title]     # from: ncu --metrics gpu__time_duration.sum --csv
     python tools/ncu_summary.py full <capture.ncu-rep> [title]      # from: ncu --set full (read here with ncu -i --page raw --csv)
+    python tools/ncu_summary.py traffic <capture.ncu-rep> <profiles/traffic.json>   # dram bytes per launch -> bench.py's roofline.traffic
 """
 import csv
 import io
@@ -48,6 +49,29 @@ def launches(path, title):
         print(f"{k[:72]:72s} {n:8d} {t * 1e-6:10.3f} {t / n * 1e-3:10.1f} {100 * t / total:6.2f}%")
 
 
+def traffic(path, out_json):
+    """dram bytes per launch of every kernel in an `ncu --set full` capture -> profiles/traffic.json (what bench.py's
+    roofline.traffic reads; never a constant kept in bench.py)."""
+    import json
+    import os
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    units = rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    table = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    for r in rows[2:]:
+        name = "kreg::" + r[ki].replace("void ", "").split("(")[0].replace(", ", ",")
+        rd, wr = float(r[ri]) * scale[units[ri]], float(r[wi]) * scale[units[wi]]
+        table[name] = {"dram_bytes": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                       "source": f"{os.path.basename(path)}: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                 f"--clock-control none (summary: profiles/{os.path.basename(path).replace('_prof_', '_').replace('.ncu-rep', '_ncu.txt')})"}
+    json.dump(table, open(out_json, "w"), indent=1)
+    print(json.dumps(table, indent=1))
+
+
 def full(path, title):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -69,4 +93,7 @@ def full(path, title):
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
     title = sys.argv[3] if len(sys.argv) > 3 else path
-    (launches if mode == "launches" else full)(path, title)
+    if mode == "traffic":
+        traffic(path, sys.argv[3])
+    else:
+        (launches if mode == "launches" else full)(path, title)
