@@ -46,11 +46,7 @@ __device__ __forceinline__ void values_tile_epilogue(const ValuesArgs &a, double
   // Row-slab FULL assembly of the values block computes K[i][j] and K[j][i] in different tiles (possibly on different
   // GPUs): there the exponent is formed symmetrically, c1 s + (b_i + b_j) with s = X'_i.X'_j alone (the accumulators were
   // started from zero), so that the two are bit-identical like the reference's mirrored copy (KREG.f90:317-318).
-#ifdef KREG_DEBUG_ZEROINIT
-  const bool symx = true;
-#else
   const bool symx = a.symmetric && a.all_cols;
-#endif
   // interior tile: every row wanted, every column valid, nothing on or above the diagonal, 16-byte aligned rows
   const bool interior = !diag_tile && !symx && i0 >= a.row_begin && i0 + kTileI <= a.row_end && i0 + kTileI <= a.na &&
                         j0 + kTileJ <= a.nb && (a.ldk & 1) == 0 && (reinterpret_cast<uintptr_t>(a.K) & 15) == 0;
@@ -235,10 +231,6 @@ __device__ __forceinline__ void lin_tile_epilogue(const ValuesArgs &a, double (&
 //   MULTI = true: the descriptor is walked in chunks of KC k-steps; a stage = the A chunk and the B chunk of one
 //           (tile, chunk) step, both contiguous in the chunk-major copy of the workspace; column biases travel with chunk 0
 //           into a slot selected by tile parity.
-#ifdef KREG_DEBUG_BIAS
-__device__ unsigned long long g_bias_dbg[8];
-#endif
-
 template <int KC, bool MULTI, int EPI = EPI_K>
 __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
@@ -303,13 +295,8 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       if (ch == 0) bulk_g2s(bBs + (tile & 1) * kTileJ, a.biasB + j0, bb, &full[s]);
     } else {
       mbar_arrive_expect_tx(&full[s], bx + bb);
-#ifdef KREG_DEBUG_SWAP
-      bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
-      bulk_g2s(st, a.XB + j0 * a.XS, bx, &full[s]);
-#else
       bulk_g2s(st, a.XB + j0 * a.XS, bx, &full[s]);
       bulk_g2s(bBs + s * kTileJ, a.biasB + j0, bb, &full[s]);
-#endif
     }
   };
   if (tid == 0) {
@@ -327,11 +314,7 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
 
   // accumulators start from the column term of their tile (-n_j/2; an arbitrary additive term for EPI_LIN), which
   // arrived with the tile's first stage: the epilogue then has no per-element bias add
-#ifdef KREG_DEBUG_ZEROINIT  /* experiment: accumulators always start from zero, the column term is added in the epilogue */
-  const bool zero_init = true;
-#else
   const bool zero_init = EPI == EPI_K && a.symmetric && a.all_cols;  // see values_tile_epilogue: symmetric exponent
-#endif
   auto init_acc = [&](const double *bcol) {
 #pragma unroll
     for (int nt = 0; nt < 4; nt++) {
@@ -376,37 +359,7 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       const int tile = step / nch;
       if (step - tile * nch == 0) init_acc(bBs + (tile & 1) * kTileJ);
     } else {
-#ifdef KREG_DEBUG_SLEEP
-      __nanosleep(4000);
-#endif
-#ifdef KREG_DEBUG_GLOBALBIAS
-      init_acc(a.biasB + (tj_lo + step) * kTileJ);
-#else
       init_acc(bBs + s * kTileJ);
-#endif
-#ifdef KREG_DEBUG_BIAS
-      {
-        const int c = wj * 32 + 2 * q;
-        const double early = bBs[s * kTileJ + c];
-        const double truth = a.biasB[(tj_lo + step) * kTileJ + c];
-        __nanosleep(3000);
-        const double late = *(volatile double *)(bBs + s * kTileJ + c);
-        const int64_t jj = (tj_lo + step) * kTileJ + c;
-        if (jj < a.nb) {
-          atomicAdd(&g_bias_dbg[3], 1ull);
-          if (early != truth) atomicAdd(&g_bias_dbg[0], 1ull);
-          if (late != truth) atomicAdd(&g_bias_dbg[1], 1ull);
-          if (early != late) atomicAdd(&g_bias_dbg[2], 1ull);
-          if (early != truth && step == 0) atomicAdd(&g_bias_dbg[4], 1ull);
-          if (early != truth && step >= NST) atomicAdd(&g_bias_dbg[5], 1ull);
-          if (early != truth) {
-            // does the wrong value belong to another tile of this CTA?
-            for (int t = 0; t < 8; t++)
-              if (early == a.biasB[(tj_lo + t) * kTileJ + c] && t != step) atomicAdd(&g_bias_dbg[6], 1ull);
-          }
-        }
-      }
-#endif
     }
 #pragma unroll
     for (int ks = 0; ks < KC; ks++) {
@@ -1348,6 +1301,225 @@ __global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int
   }
 }
 
+// Fused version of the resident-block kernel: the pair terms are formed IN the emit step instead of by a kernel of their
+// own (0.79 of 3.3 ms at 21 atoms, and a workspace of 3 Nat + 1 doubles per geometry pair written and read back).  With
+// Dsq[j][c][b] = (X_j - X_i)[d_bc] in shared memory, the thread that owns column (j, b, u) forms in ONE loop over c
+//     -u_j[(b,u)]   = sum_c E_j[c][b][u] Dsq[j][c][b]        (what it needed anyway)
+//      u_i^(j)[(b,u)] = -sum_c E_i[c][b][u] Dsq[j][c][b]      (one more shared load and FMA per c)
+//      |X_j - X_i|^2 = 1/2 sum_b sum_c Dsq[j][c][b]^2         (column b's share; summed over b in a fixed order)
+// and the value-gradient entries of BOTH orders of the pair come out of the same step:
+//      K[NtrVal + i*3Nat + (b,u)][j] = (k/s^2) u_i^(j)[(b,u)],     K[NtrVal + j*3Nat + (b,u)][i] = (k/s^2) u_j^(i)[(b,u)] = (k/s^2) sj.
+// A rank that owns only a row slab needs the second kind for its geometries j and EVERY i > j, also those whose rows
+// belong to other ranks: such steps run with the block emission switched off (`pair-only`).
+__global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int nat, int TJ, int NIB, int ei_global,
+                                                         int inorder, int64_t i_end) {
+  const int G3 = 3 * nat, D = descr_size(nat), NS = nat | 1, EJ = a.ES, XS = a.XS;
+  extern __shared__ __align__(128) double esm[];
+  double *Ejs = esm;                                // [TJ*EJ]     resident
+  double *Xj = Ejs + (size_t)TJ * EJ;               // [TJ*XS]     resident
+  double *Eib = Xj + (size_t)TJ * XS;               // [2][EJ]     streamed (very large molecules: read through L1 instead)
+  double *Xib = Eib + (ei_global ? 0 : 2 * (size_t)EJ);  // [2][XS]
+  double *Dsq = Xib + 2 * (size_t)XS;               // [TJ][nat*NS]
+  double *Us = Dsq + (((size_t)TJ * nat * NS + 1) & ~(size_t)1);  // [TJ][G3]   u_i^(j)
+  double *d2p = Us + (((size_t)TJ * G3 + 1) & ~(size_t)1);        // [TJ][nat]  per-column shares of |X_j - X_i|^2
+  double *tab = d2p + (((size_t)TJ * nat + 1) & ~(size_t)1);      // [64]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(tab + 64);          // [3]
+  unsigned short *ptab = reinterpret_cast<unsigned short *>(bar + 4);  // [D] d -> (lo | hi << 8)
+
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t jb = (int64_t)blockIdx.x * TJ;
+  const int npair = (int)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
+  // geometries i of this CTA: its chunk of [c_i0, i_end); steps with i >= c_i1 are pair-only and are needed only by j-blocks
+  // that contain geometries of this launch's own range
+  int64_t i_lo = (int64_t)blockIdx.y * NIB + a.c_i0, i_hi = i_lo + NIB;
+  if (i_hi > i_end) i_hi = i_end;
+  if (!full && i_lo < jb) i_lo = jb;
+  if (i_lo >= a.c_i1 && (jb + npair <= a.c_i0 || jb >= a.c_i1)) return;
+  if (i_lo >= i_hi) return;
+  const int nsteps = (int)(i_hi - i_lo);
+
+  const int tid = threadIdx.x;
+  const int64_t ld = a.ldk;
+  const int cols = npair * G3;
+  const bool okc = tid < cols;
+  const int r = okc ? tid : 0;
+  const int jl = r / G3, cc = r - jl * G3, b = cc / 3;
+  const int64_t j = jb + jl;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
+    mbar_fence_init();
+  }
+  fill_exp_table(tab, tid, blockDim.x);
+  __syncthreads();
+  auto prefetch = [&](int n) {  // thread 0 only: operands of step n (geometry i_lo + n)
+    const int64_t i = i_lo + n;
+    const int buf = n & 1;
+    const unsigned be = ei_global ? 0u : (unsigned)EJ * 8, bx = (unsigned)XS * 8;
+    mbar_arrive_expect_tx(&bar[buf], be + bx);
+    if (!ei_global) bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
+    bulk_g2s(Xib + (size_t)buf * XS, a.Xc + i * XS, bx, &bar[buf]);
+  };
+  if (tid == 0) {
+    const unsigned be = (unsigned)npair * EJ * 8, bx = (unsigned)npair * XS * 8;
+    mbar_arrive_expect_tx(&bar[2], be + bx);
+    bulk_g2s(Ejs, a.E + jb * a.ES, be, &bar[2]);
+    bulk_g2s(Xj, a.Xc + jb * XS, bx, &bar[2]);
+    prefetch(0);
+  }
+  __syncwarp();
+  for (int e = tid; e < D; e += blockDim.x) {
+    int lo, hi;
+    pair_from_index(nat, e, lo, hi);
+    ptab[e] = (unsigned short)(lo | (hi << 8));
+  }
+  for (int e = tid; e < TJ * nat; e += blockDim.x) Dsq[(size_t)e * NS + (e % nat)] = 0.0;  // diagonals: never rewritten
+  mbar_wait(&bar[2], 0);
+  const double *ej = Ejs + (size_t)jl * EJ + cc;  // E_j[c][b][u] at ej[c * G3]  (= -E_j(b,c)[u])
+  const double *dq = Dsq + (size_t)jl * nat * NS + b;
+  const double *ui = Us + (size_t)jl * G3;
+  const double half_c1 = -0.5 * a.c1;
+
+  for (int n = 0; n < nsteps; n++) {
+    __syncthreads();  // everyone left the buffer about to be refilled and the shared arrays of the previous step
+    if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
+    __syncwarp();  // warp 0 reconverges before the tile code (uniform registers are shared with the issuing lane)
+    const int buf = n & 1;
+    mbar_wait(&bar[buf], (n >> 1) & 1);
+    const int64_t i = i_lo + n;
+    const double *Xi = Xib + (size_t)buf * XS;
+    for (int e = tid; e < npair * D; e += blockDim.x) {  // consecutive threads -> consecutive d: conflict-free reads
+      const int jj = e / D, d = e - jj * D;
+      const int lo = ptab[d] & 0xff, hi = ptab[d] >> 8;
+      const double v = Xj[jj * XS + d] - Xi[d];
+      double *q = Dsq + (size_t)jj * nat * NS;
+      q[lo * NS + hi] = v;
+      q[hi * NS + lo] = v;
+    }
+    __syncthreads();
+    const bool pair_wanted = okc && (full || j <= i);
+    // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t]); with t = u the same array gives this column's own u_i component
+    const double *eibase = ei_global ? a.E + i * a.ES : Eib + (size_t)buf * EJ;
+    const double *ei = eibase + 3 * b;
+    double sj = 0.0, uo = 0.0, dd = 0.0;
+    if (pair_wanted) {
+      const double *eo = eibase + cc;
+      for (int c = 0; c < nat; c++) {
+        const double dl = dq[c * NS];
+        sj = fma(ej[c * G3], dl, sj);    // -u_j[col]
+        uo = fma(-eo[c * G3], dl, uo);   // u_i^(j)[col]
+        dd = fma(dl, dl, dd);
+      }
+      Us[(size_t)jl * G3 + cc] = uo;
+      if (cc == 3 * b) d2p[jl * nat + b] = dd;
+    }
+    __syncthreads();
+    if (!pair_wanted) continue;
+    double d2 = 0.0;
+    for (int c = 0; c < nat; c++) d2 += d2p[jl * nat + c];  // every thread of the pair sums in the same order
+    const double kk = (j == i) ? 1.0 : exp_from_scaled(half_c1 * (0.5 * d2), tab);
+    const double kj = kk * a.inv_s2;
+    const int64_t rbase = a.nv + i * G3;
+    // value-gradient entries of both orders of the pair
+    if (a.nv) {
+      const int64_t row1 = rbase + cc;
+      if (row1 >= a.row_begin && row1 < a.row_end) {
+        const double v = kj * uo;
+        KREG_CHECK_STORE(a.K + row1 * ld + j, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+        a.K[row1 * ld + j] = v;
+        if (full) a.K[j * ld + row1] = v;
+      }
+      const int64_t row2 = a.nv + j * G3 + cc;
+      if (!full && j != i && row2 >= a.row_begin && row2 < a.row_end) {
+        KREG_CHECK_STORE(a.K + row2 * ld + i, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+        a.K[row2 * ld + i] = kj * sj;
+      }
+    }
+    if (i >= a.c_i1 || rbase + G3 <= a.row_begin || rbase >= a.row_end) continue;  // pair-only step
+    const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
+    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+    double *dst = a.K + rbase * ld + a.nv + j * G3 + cc;
+    if (interior && j != i) {
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0;  // sums of the J_i^T J_j products over the rows, per t
+      if (inorder) {
+        // rows strictly in order: the diagonal sums come from a pass of their own, so that no 24-byte holes are left in
+        // the row segments for later (partial 32-byte sectors cost more at the memory side than the extra reads here)
+#pragma unroll 3
+        for (int aa = 0; aa < nat; aa++) {
+          const double knej = __dmul_rn(kj, ej[aa * G3]);
+          m0 = __dadd_rn(m0, __dmul_rn(knej, -ei[aa * G3 + 0]));
+          m1 = __dadd_rn(m1, __dmul_rn(knej, -ei[aa * G3 + 1]));
+          m2 = __dadd_rn(m2, __dmul_rn(knej, -ei[aa * G3 + 2]));
+        }
+#pragma unroll 3
+        for (int aa = 0; aa < nat; aa++) {
+          const double knej = __dmul_rn(kj, ej[aa * G3]);
+          double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
+                 p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
+          if (aa == b) {
+            p0 = -m0;
+            p1 = -m1;
+            p2 = -m2;
+          }
+          double *d3 = dst + (int64_t)(3 * aa) * ld;
+          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          d3[0] = fma(ui[3 * aa + 0], c2, p0);
+          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
+          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
+        }
+        continue;
+      }
+      for (int aa = 0; aa < nat; aa++) {
+        // explicit roundings (no FMA contraction of p into m): the boundary path below forms the same numbers, so a
+        // block comes out bit-identical whether it is written whole or clipped to a row slab (sharded assembly)
+        const double knej = __dmul_rn(kj, ej[aa * G3]);
+        const double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
+                     p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
+        m0 = __dadd_rn(m0, p0);
+        m1 = __dadd_rn(m1, p1);
+        m2 = __dadd_rn(m2, p2);
+        if (aa != b) {  // the three a == b rows are completed after the loop
+          double *d3 = dst + (int64_t)(3 * aa) * ld;
+          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          d3[0] = fma(ui[3 * aa + 0], c2, p0);
+          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
+          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
+        }
+      }
+      double *dg = a.K + (rbase + 3 * b) * ld + a.nv + j * G3 + cc;
+      dg[0] = fma(ui[3 * b + 0], c2, -m0);
+      dg[ld] = fma(ui[3 * b + 1], c2, -m1);
+      dg[2 * ld] = fma(ui[3 * b + 2], c2, -m2);
+    } else {
+      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal
+      double m[3] = {0.0, 0.0, 0.0};
+      for (int aa = 0; aa < nat; aa++)
+        for (int t = 0; t < 3; t++) m[t] = __dadd_rn(m[t], __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
+      for (int q = 0; q < G3; q++) {
+        const int aa = q / 3, t = q - aa * 3;
+        double val = fma(ui[q], c2, aa == b ? -(t == 0 ? m[0] : t == 1 ? m[1] : m[2])
+                                            : __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
+        if (j == i && q == cc) val += a.lambdag;
+        const int64_t rr = rbase + q;
+        if (rr >= a.row_begin && rr < a.row_end) {
+          KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+          dst[(int64_t)q * ld] = val;
+        }
+      }
+    }
+  }
+}
+
+static size_t fused_smem_doubles(int nat, int XS, int EJ, int tj, int ei_global) {
+  const int G3 = 3 * nat, D = descr_size(nat), NS = nat | 1;
+  size_t n = (size_t)tj * ((size_t)EJ + XS) + 2 * ((ei_global ? 0 : (size_t)EJ) + XS) + (((size_t)tj * nat * NS + 1) & ~(size_t)1) +
+             (((size_t)tj * G3 + 1) & ~(size_t)1) + (((size_t)tj * nat + 1) & ~(size_t)1) + 64;
+  n += 4 + (D + 3) / 4;  // barriers, pair table (unsigned short)
+  return n;
+}
+
 #ifndef KREG_EMIT_TEMPLATE_MAX
 #define KREG_EMIT_TEMPLATE_MAX 10  // largest molecule emitted by the register-resident grad_emit_kernel<NAT>
 #endif
@@ -1707,13 +1879,6 @@ extern "C" int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, co
   if (rc || !symmetric) return rc;
   return launch_set_diagonal(na, Kout, ldk, 1.0 + lambda, st);
 }
-
-#ifdef KREG_DEBUG_BIAS
-extern "C" int kreg_debug_bias(unsigned long long *out) {
-  cudaDeviceSynchronize();
-  return (int)cudaMemcpyFromSymbol(out, kreg::g_bias_dbg, sizeof(unsigned long long) * 8);
-}
-#endif
 
 extern "C" size_t kreg_build_workspace_bytes_rows(int natoms, int64_t ntrain, int64_t ntrgr, int64_t row_begin,
                                                   int64_t row_end) {
