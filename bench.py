@@ -215,7 +215,7 @@ def kbuild_configs(engine, dev, hbm_peak, fp64_peak):
         sigma = SIGMA if nat <= 12 else 2.0
         xyz = torch.from_numpy(S.geometries(eq, ntr, seed=1)).to(dev)
         m = ntr + (3 * nat * ntr if grads else 0)
-        k = torch.empty((m, m), dtype=torch.float64, device=dev)
+        k = engine.empty_kernel_matrix(m, ntr if grads else 0, dev)  # the layout the engine itself allocates
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ms = []
         for it in range(4):

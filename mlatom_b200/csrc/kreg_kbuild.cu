@@ -575,7 +575,7 @@ struct GradArgs {
   int64_t row_begin, row_end;  // absolute row range of K to produce
   double *K;
   int64_t ldk;
-  double *P;             // [i1 - i0][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_kernel -> grad_emit_kernel)
+  double *P;             // [i1 - i0][ntr][3 Nat + 1 (+pad)] per-pair terms (pair_terms_small_kernel -> grad_emit_kernel)
   int64_t p_i0;          // first geometry i whose gradient rows intersect [row_begin, row_end): row 0 of P
   int64_t p_i1;          // one past the last such geometry
   int64_t c_i0, c_i1;    // the geometries THIS launch covers (a chunk of [p_i0, p_i1): the assembly is pipelined in chunks)
@@ -606,8 +606,9 @@ __global__ void __launch_bounds__(128) jacobian_rows_kernel(int nat, int64_t n, 
   }
 }
 
-// The gradient-augmented blocks are produced by two kernels so that the store kernel has NO per-pair prologue:
-//   pair_terms_kernel : per geometry pair (i, j): k_ij/s^2 and u_i^(j) = J_i^T (X_j - X_i)  -> workspace P[i][j][PW]
+// Up to 10 atoms the gradient-augmented blocks are produced by two kernels so that the store kernel has NO per-pair prologue
+// (larger molecules: grad_fused_kernel below):
+//   pair_terms_small_kernel : per geometry pair (i, j): k_ij/s^2 and u_i^(j) = J_i^T (X_j - X_i)  -> workspace P[i][j][PW]
 //                       (PW = 3 Nat + 1 doubles, 4 % of the bytes of the block it describes); also emits the
 //                       value-gradient rows.
 //   grad_emit_kernel  : CTA = ONE geometry i x TJ geometries j, thread = matrix column (j, b, u); one round of global
@@ -640,141 +641,9 @@ struct GradCfg {
   static constexpr int TJ = KREG_EMIT_TJEVEN ? (TJ0 & ~1) : TJ0;
   static constexpr int COLS = TJ * G3;
   static constexpr int THREADS = ((COLS + 31) / 32) * 32;
-  static constexpr int JT = NAT <= 12 ? 64 : 16;  // geometries j per pair-terms CTA (shared-memory budget)
   static constexpr int NJB = KREG_EMIT_NJB;   // steps (of TJ geometries) walked by one emit CTA
 };
 
-// shared-memory carve-up of pair_terms_kernel (doubles), sized for the run-time descriptor row stride XS.  The X_j
-// staging rows are dead once X_j - X_i has been formed, so the output block Us reuses their space.
-template <int NAT>
-struct PairSmem {
-  using C = GradCfg<NAT>;
-  static constexpr int ES = (NAT * NAT * 3 + 1) & ~1;
-  static constexpr int DP = C::D | 1;                          // odd row stride: conflict-free column reads
-  static constexpr int DLN = (C::JT * DP + 1) & ~1;
-  static constexpr int PWS = C::PW | 1;                        // odd shared-memory stride of the output block
-  __host__ __device__ static int stage(int XS) { return C::JT * XS > C::JT * PWS ? C::JT * XS : C::JT * PWS; }
-  __host__ __device__ static int off_xi() { return ES; }                                   // [XS]      X_i
-  __host__ __device__ static int off_xj(int XS) { return ES + XS; }                        // [JT][XS]  X_j rows / Us
-  __host__ __device__ static int off_dl(int XS) { return off_xj(XS) + stage(XS); }         // [JT][DP]  X_j - X_i
-  __host__ __device__ static int off_tab(int XS) { return off_dl(XS) + DLN; }              // [64]
-  __host__ __device__ static int off_bar(int XS) { return off_tab(XS) + 64; }
-  __host__ __device__ static int doubles(int XS) { return off_bar(XS) + 2; }
-};
-
-template <int NAT>
-__global__ void __launch_bounds__(256) pair_terms_kernel(const GradArgs a) {
-  using C = GradCfg<NAT>;
-  using SM = PairSmem<NAT>;
-  constexpr int G3 = C::G3, PW = C::PW, PWS = SM::PWS, D = C::D, JT = C::JT, DP = SM::DP;
-  extern __shared__ __align__(128) double psm[];
-  const int XS = a.XS;
-  double *Ei = psm, *Xi = psm + SM::off_xi(), *Xjb = psm + SM::off_xj(XS), *Dl = psm + SM::off_dl(XS);
-  double *Us = Xjb;  // reused after the X_j - X_i pass
-  double *tab = psm + SM::off_tab(XS);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(psm + SM::off_bar(XS));
-
-  const int64_t i = (int64_t)blockIdx.y + a.c_i0;  // this launch covers geometries [c_i0, c_i1)
-  const int64_t rbase = a.nv + i * G3;
-  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
-  const bool full = a.fill == KREG_FILL_FULL;
-  const int64_t jend = (a.nv || full) ? a.ntr : i + 1;  // value-gradient rows need every j
-  const int64_t j0 = (int64_t)blockIdx.x * JT;
-  if (j0 >= jend) return;
-  const int nj = (int)(jend - j0 < JT ? jend - j0 : JT);
-  const int tid = threadIdx.x;
-
-  // one round of TMA bulk loads: E_i, X_i, and the nj rows X_j (contiguous in global memory)
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_fence_init();
-    const unsigned be = SM::ES * 8, bx = (unsigned)XS * 8, bj = (unsigned)nj * XS * 8;
-    mbar_arrive_expect_tx(&bar[0], be + bx + bj);
-    bulk_g2s(Ei, a.E + i * a.ES, be, &bar[0]);
-    bulk_g2s(Xi, a.Xc + i * XS, bx, &bar[0]);
-    bulk_g2s(Xjb, a.Xc + j0 * XS, bj, &bar[0]);
-  }
-  fill_exp_table(tab, tid, 256);
-  __syncthreads();  // barrier initialised (and table filled) before anyone waits on it
-  mbar_wait(&bar[0], 0);
-  // X_j - X_i into the odd-stride buffer: (256 / JT) lanes per geometry, no integer division
-  {
-    constexpr int LPG = 256 / JT;
-    const int jj = tid / LPG, sub = tid % LPG;
-    if (jj < nj)
-      for (int d = sub; d < D; d += LPG) Dl[jj * DP + d] = Xjb[jj * XS + d] - Xi[d];
-  }
-  __syncthreads();
-  {  // k_ij / s^2: four lanes per pair (JT * 4 == blockDim: every lane takes part in the shuffles)
-    const int jj = tid >> 2, sub = tid & 3;
-    const double *dd = Dl + (jj < nj ? jj : 0) * DP;
-    double d2 = 0.0;
-    for (int d = sub; d < D; d += 4) d2 = fma(dd[d], dd[d], d2);
-    d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
-    d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
-    if (sub == 0 && jj < nj) {
-      const double k = (j0 + jj == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
-      Us[jj * PWS] = k * a.inv_s2;
-      Us[jj * PWS + 1] = 0.0;
-    }
-  }
-  // u_i^(j)[(a,t)] = sum_c E_i(a,c)[t] D_j[d_ac]: thread = (j, atom a) produces the three components t, reading each
-  // D_j[d_ac] once (conflict-free columns, odd stride) and E_i(a, .)[.] as warp-wide broadcasts.  The atom index is
-  // uniform per warp and unrolled, so every descriptor index is a compile-time constant.
-  {
-    constexpr int GROUPS = 256 / JT;  // atoms handled concurrently
-    const int jj = tid % JT, grp = tid / JT;
-    if (jj < nj) {
-      const double *dd = Dl + jj * DP;
-#pragma unroll
-      for (int aa = 0; aa < NAT; aa++) {
-        if (aa % GROUPS != grp) continue;
-        const double *ea = Ei + aa * NAT * 3;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int c = 0; c < NAT; c++)
-          if (c != aa) {
-            const double dl = dd[pair_index(NAT, aa < c ? aa : c, aa < c ? c : aa)];
-            s0 = fma(ea[c * 3 + 0], dl, s0);
-            s1 = fma(ea[c * 3 + 1], dl, s1);
-            s2 = fma(ea[c * 3 + 2], dl, s2);
-          }
-        double *out = Us + jj * PWS + 2 + aa * 3;
-        out[0] = s0;
-        out[1] = s1;
-        out[2] = s2;
-      }
-    }
-  }
-  __syncthreads();
-  // pair terms -> workspace (coalesced)
-  double *P = a.P + ((i - a.p_i0) * a.ntr + j0) * PW;
-  {
-    // only pairs whose gradient-gradient block is emitted (j <= i unless mirrored) are read back by grad_emit_kernel
-    const int64_t jgg = full ? a.ntr : i + 1;
-    const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
-    for (int e = tid; e < np * PW; e += 256) P[e] = Us[(e / PW) * PWS + e % PW];
-  }
-  // value-gradient rows: K[rbase + q][j] = (k/s^2) u_i^(j)[q], consecutive threads -> consecutive j
-  if (a.nv) {
-    for (int e = tid; e < G3 * JT; e += 256) {
-      const int q = e / JT, jj = e % JT;
-      const int64_t row = rbase + q;
-      if (jj < nj && row >= a.row_begin && row < a.row_end) {
-        const double v = Us[jj * PWS] * Us[jj * PWS + 2 + q];
-        KREG_CHECK_STORE(a.K + row * a.ldk + j0 + jj, a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
-        a.K[row * a.ldk + j0 + jj] = v;
-        if (full) a.K[(j0 + jj) * a.ldk + row] = v;
-      }
-    }
-  }
-}
-
-// Small molecules (D <= 45): one THREAD per geometry pair.  X_j - X_i lives in that thread's registers (LDS.128 from rows
-// whose stride is an odd number of 16-byte units: conflict-free), E_i arrives as warp-wide broadcasts, d^2 needs no
-// shuffles, and the value-gradient rows go straight from registers to K (lanes = consecutive j: coalesced).  Only the
-// pair terms for grad_emit_kernel are staged through shared memory.  About a third of the shared-memory wavefronts of
-// the cooperative kernel above, which is what bounds it (profiles/r01_gradk_ncu.txt: L1 91 %).
 template <int NAT>
 struct PairSmall {
   using C = GradCfg<NAT>;
@@ -1017,313 +886,48 @@ __global__ void __launch_bounds__(GradCfg<NAT>::THREADS, (NAT <= 12 && GradCfg<N
   }
 }
 
-// =================================================================================================
-// Run-time-Natoms versions of the two gradient-block kernels: any molecule size (the reference takes Natoms as a
-// run-time argument, KREG.f90:293-346), and no per-thread register arrays -- every operand is read from shared memory,
-// so the kernels stay at a few dozen registers and several CTAs share an SM (the templated emit kernel keeps E_i(b, .)
-// in 6 Nat registers per thread: 255 registers and spills from 11 atoms up).
-// =================================================================================================
-
-// Pair terms, cooperative: CTA = (geometry i, JT geometries j), 256 threads.
-//   shared: E_i [Nat][Nat][3] | X_i [D] | D_j = X_j - X_i [JT][DP] (DP odd: conflict-free columns) | Us [JT][PWS] | exp table
-__global__ void __launch_bounds__(256) pair_terms_rt_kernel(const GradArgs a, int nat, int JT) {
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, PWS = PW | 1, DP = D | 1, XS = a.XS;
-  extern __shared__ __align__(16) double rsm[];
-  double *Ei = rsm;                  // [ES]
-  double *Xi = Ei + a.ES;            // [D (+1)]
-  double *Dl = Xi + ((D + 1) & ~1);  // [JT][DP]
-  double *Us = Dl + (((size_t)JT * DP + 1) & ~(size_t)1);  // [JT][PWS]
-  double *tab = Us + (((size_t)JT * PWS + 1) & ~(size_t)1);
-
-  const int64_t i = (int64_t)blockIdx.y + a.c_i0;  // this launch covers geometries [c_i0, c_i1)
-  const int64_t rbase = a.nv + i * G3;
-  if (rbase + G3 <= a.row_begin || rbase >= a.row_end) return;
-  const bool full = a.fill == KREG_FILL_FULL;
-  const int64_t jend = (a.nv || full) ? a.ntr : i + 1;  // value-gradient rows need every j
-  const int64_t j0 = (int64_t)blockIdx.x * JT;
-  if (j0 >= jend) return;
-  const int nj = (int)(jend - j0 < JT ? jend - j0 : JT);
-  const int tid = threadIdx.x;
-
-  fill_exp_table(tab, tid, 256);
-  for (int e = tid; e < a.ES; e += 256) Ei[e] = a.E[i * a.ES + e];
-  for (int e = tid; e < D; e += 256) Xi[e] = a.Xc[i * XS + e];
-  __syncthreads();
-  for (int e = tid; e < nj * D; e += 256) {  // consecutive threads -> consecutive d: coalesced rows
-    const int jj = e / D, d = e - jj * D;
-    Dl[jj * DP + d] = a.Xc[(j0 + jj) * XS + d] - Xi[d];
-  }
-  __syncthreads();
-  for (int base = 0; base < nj; base += 64) {  // k_ij / s^2: four lanes per pair, in the order the templated kernel sums
-    const int jj = base + (tid >> 2), sub = tid & 3;
-    const double *dd = Dl + (jj < nj ? jj : 0) * DP;
-    double d2 = 0.0;
-    for (int d = sub; d < D; d += 4) d2 = fma(dd[d], dd[d], d2);
-    d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
-    d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
-    if (sub == 0 && jj < nj) {
-      const double k = (j0 + jj == i) ? 1.0 : exp_from_scaled(-0.5 * a.c1 * d2, tab);
-      Us[jj * PWS] = k * a.inv_s2;
-      Us[jj * PWS + 1] = 0.0;
-    }
-  }
-  // u_i^(j)[(a,t)] = sum_c E_i(a,c)[t] D_j[d_ac]: item = (atom a, geometry j), consecutive threads -> consecutive j
-  for (int e = tid; e < nat * JT; e += 256) {
-    const int aa = e / JT, jj = e - aa * JT;
-    if (jj >= nj) continue;
-    const double *dd = Dl + jj * DP;
-    const double *ea = Ei + aa * G3;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int c = 0; c < nat; c++) {
-      if (c == aa) continue;
-      const double dl = dd[pair_index(nat, aa < c ? aa : c, aa < c ? c : aa)];
-      s0 = fma(ea[c * 3 + 0], dl, s0);
-      s1 = fma(ea[c * 3 + 1], dl, s1);
-      s2 = fma(ea[c * 3 + 2], dl, s2);
-    }
-    double *out = Us + jj * PWS + 2 + aa * 3;
-    out[0] = s0;
-    out[1] = s1;
-    out[2] = s2;
-  }
-  __syncthreads();
-  if ((G3 + 2) < PW)  // the pad element of a pair's record
-    for (int jj = tid; jj < nj; jj += 256) Us[jj * PWS + PW - 1] = 0.0;
-  __syncthreads();
-  double *P = a.P + ((i - a.p_i0) * a.ntr + j0) * PW;
-  {
-    const int64_t jgg = full ? a.ntr : i + 1;
-    const int np = (int)(jgg - j0 < nj ? (jgg - j0 > 0 ? jgg - j0 : 0) : nj);
-    for (int e = tid; e < np * PW; e += 256) P[e] = Us[(e / PW) * PWS + e % PW];
-  }
-  if (a.nv) {
-    for (int e = tid; e < G3 * JT; e += 256) {
-      const int q = e / JT, jj = e - q * JT;
-      const int64_t row = rbase + q;
-      if (jj < nj && row >= a.row_begin && row < a.row_end) {
-        const double v = Us[jj * PWS] * Us[jj * PWS + 2 + q];
-        KREG_CHECK_STORE(a.K + row * a.ldk + j0 + jj, a.K + a.row_begin * a.ldk, (a.row_end - a.row_begin) * a.ldk);
-        a.K[row * a.ldk + j0 + jj] = v;
-        if (full) a.K[(j0 + jj) * a.ldk + row] = v;
-      }
-    }
-  }
-}
-
-// Emit: CTA = a block of TJ geometries j (their E_j blocks and X_j rows stay RESIDENT in shared memory) x a run of NIB
-// geometries i, one per step; thread = one matrix column (j, b, u) of the block, which walks the 3 Nat rows (a, t) of the
-// step's geometry i: every row segment a warp writes is 256 contiguous bytes.  What streams per step is only E_i, X_i and
-// the TJ pair-term records of (i, j-block) -- (Nat^2 3 + D + TJ (3 Nat + 2)) doubles for TJ (3 Nat)^2 outputs -- as three
-// TMA bulk copies into the other buffer while this step's stores are issued.  (The first run-time version fixed i and
-// streamed the E_j blocks: 0.4 bytes in per byte out, and a third of all issue slots spent polling the mbarrier,
-// profiles/r02_gradk21_rt_v2_ncu.txt.)  Shared-memory reads are arranged to be conflict-free and few:
-//  * by antisymmetry E(b,c)[u] = -E(c,b)[u], the value column (j,b,u) needs for row atom c is E_j[c][b][u]: for a fixed c
-//    consecutive columns read consecutive doubles; likewise E_i[c][b][t] on the row side;
-//  * X_j - X_i is scattered once per step into an atom-pair matrix Dsq[j][c][b], so that -u_j[col] = sum_c E_j[c][b][u]
-//    Dsq[j][c][b] reads consecutive addresses instead of gathering descriptor elements;
-//  * the 3x3 diagonal blocks (a == b) need sum_c E_i(b,c)[t] E_j(b,c)[u], which is exactly minus the sum over the rows
-//    (c, t) of the products the thread forms anyway while walking the rows: it is accumulated on the way and the three
-//    a == b rows are stored last, instead of a separate prologue loop.
-// NAT_CT > 0 fixes the molecule size at compile time (11..24 atoms: every stride below becomes an immediate and the row
-// loops unroll -- 8 instead of 22 instructions per element, profiles/r02_gradk21_rt_v3_ncu.txt); NAT_CT = 0 takes it at
-// run time (any size).
-template <int NAT_CT>
-__global__ void __launch_bounds__(256) grad_emit_rt_kernel(const GradArgs a, int nat_rt, int TJ, int NIB, int ei_global,
-                                                           int inorder) {
-  const int nat = NAT_CT > 0 ? NAT_CT : nat_rt;
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, NS = nat | 1;
-  const int EJ = NAT_CT > 0 ? ((NAT_CT * NAT_CT * 3 + 1) & ~1) : a.ES, XS = a.XS;
-  extern __shared__ __align__(128) double esm[];
-  double *Ejs = esm;                                // [TJ*EJ]     resident
-  double *Xj = Ejs + (size_t)TJ * EJ;               // [TJ*XS]     resident
-  double *Eib = Xj + (size_t)TJ * XS;               // [2][EJ]     streamed (very large molecules: read through L1 instead)
-  double *Xib = Eib + (ei_global ? 0 : 2 * (size_t)EJ);  // [2][XS]
-  double *Pb = Xib + 2 * (size_t)XS;                // [2][TJ*PW]
-  double *Dsq = Pb + 2 * (size_t)TJ * PW;           // [TJ][nat*NS]   Dsq[j][c*NS + b] = (X_j - X_i)[d_bc], 0 for b == c
-  uint64_t *bar = reinterpret_cast<uint64_t *>(Dsq + (((size_t)TJ * nat * NS + 1) & ~(size_t)1));  // [3]
-  unsigned short *ptab = reinterpret_cast<unsigned short *>(bar + 4);                               // [D] d -> (lo | hi << 8)
-
-  const bool full = a.fill == KREG_FILL_FULL;
-  const int64_t jb = (int64_t)blockIdx.x * TJ;
-  // geometries i of this CTA: its chunk, clipped to the row range, and (lower fill) to i >= the block's first j
-  int64_t i_lo = (int64_t)blockIdx.y * NIB + a.c_i0, i_hi = i_lo + NIB;
-  if (i_hi > a.c_i1) i_hi = a.c_i1;
-  if (!full && i_lo < jb) i_lo = jb;
-  if (i_lo >= i_hi) return;
-  const int nsteps = (int)(i_hi - i_lo);
-  const int npair = (int)(a.ntr - jb < TJ ? a.ntr - jb : TJ);
-
-  const int tid = threadIdx.x;
-  const int64_t ld = a.ldk;
-  const int cols = npair * G3;
-  const bool okc = tid < cols;
-  const int r = okc ? tid : 0;
-  const int jl = r / G3, cc = r - jl * G3, b = cc / 3;
-  const int64_t j = jb + jl;
-
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_init(&bar[2], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto prefetch = [&](int n) {  // thread 0 only: operands of step n (geometry i_lo + n)
-    const int64_t i = i_lo + n;
-    const int buf = n & 1;
-    const unsigned be = ei_global ? 0u : (unsigned)EJ * 8, bx = (unsigned)XS * 8, bp = (unsigned)npair * PW * 8;
-    mbar_arrive_expect_tx(&bar[buf], be + bx + bp);
-    if (!ei_global) bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
-    bulk_g2s(Xib + (size_t)buf * XS, a.Xc + i * XS, bx, &bar[buf]);
-    bulk_g2s(Pb + (size_t)buf * TJ * PW, a.P + ((i - a.p_i0) * a.ntr + jb) * PW, bp, &bar[buf]);
-  };
-  if (tid == 0) {
-    const unsigned be = (unsigned)npair * EJ * 8, bx = (unsigned)npair * XS * 8;
-    mbar_arrive_expect_tx(&bar[2], be + bx);
-    bulk_g2s(Ejs, a.E + jb * a.ES, be, &bar[2]);
-    bulk_g2s(Xj, a.Xc + jb * XS, bx, &bar[2]);
-    prefetch(0);
-  }
-  __syncwarp();
-  for (int e = tid; e < D; e += blockDim.x) {
-    int lo, hi;
-    pair_from_index(nat, e, lo, hi);
-    ptab[e] = (unsigned short)(lo | (hi << 8));
-  }
-  for (int e = tid; e < TJ * nat; e += blockDim.x) Dsq[(size_t)e * NS + (e % nat)] = 0.0;  // diagonals: never rewritten
-  mbar_wait(&bar[2], 0);
-  const double *ej = Ejs + (size_t)jl * EJ + cc;  // E_j[c][b][u] at ej[c * G3]  (= -E_j(b,c)[u])
-
-  for (int n = 0; n < nsteps; n++) {
-    __syncthreads();  // everyone left the buffer about to be refilled, and Dsq of the previous step; ptab / Dsq ready
-    if (tid == 0 && n + 1 < nsteps) prefetch(n + 1);
-    __syncwarp();  // warp 0 reconverges before the tile code (uniform registers are shared with the issuing lane)
-    const int buf = n & 1;
-    mbar_wait(&bar[buf], (n >> 1) & 1);
-    const int64_t i = i_lo + n;
-    const double *Xi = Xib + (size_t)buf * XS;
-    for (int e = tid; e < npair * D; e += blockDim.x) {  // consecutive threads -> consecutive d: conflict-free reads
-      const int jj = e / D, d = e - jj * D;
-      const int lo = ptab[d] & 0xff, hi = ptab[d] >> 8;
-      const double v = Xj[jj * XS + d] - Xi[d];
-      double *dq = Dsq + (size_t)jj * nat * NS;
-      dq[lo * NS + hi] = v;
-      dq[hi * NS + lo] = v;
-    }
-    __syncthreads();
-    if (!okc || (!full && j > i)) continue;
-    const int64_t rbase = a.nv + i * G3;
-    const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
-    const double *pb = Pb + (size_t)buf * TJ * PW + jl * PW;
-    // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
-    const double *ei = (ei_global ? a.E + i * a.ES : Eib + (size_t)buf * EJ) + 3 * b;
-    const double kj = pb[0];
-    double sj = 0.0;
-    {
-      const double *dq = Dsq + (size_t)jl * nat * NS + b;
-#pragma unroll
-      for (int c = 0; c < nat; c++) sj = fma(ej[c * G3], dq[c * NS], sj);  // -u_j[col]
-    }
-    const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
-    double *dst = a.K + rbase * ld + a.nv + j * G3 + cc;
-    if (interior && j != i) {
-      double m0 = 0.0, m1 = 0.0, m2 = 0.0;  // sums of the J_i^T J_j products over the rows, per t
-      const double *ui = pb + 2;
-      if (inorder) {
-        // rows strictly in order: the diagonal sums come from a pass of their own, so that no 24-byte holes are left in
-        // the row segments for later (partial 32-byte sectors cost more at the memory side than the extra reads here)
-#pragma unroll 3
-        for (int aa = 0; aa < nat; aa++) {
-          const double knej = __dmul_rn(kj, ej[aa * G3]);
-          m0 = __dadd_rn(m0, __dmul_rn(knej, -ei[aa * G3 + 0]));
-          m1 = __dadd_rn(m1, __dmul_rn(knej, -ei[aa * G3 + 1]));
-          m2 = __dadd_rn(m2, __dmul_rn(knej, -ei[aa * G3 + 2]));
-        }
-#pragma unroll 3
-        for (int aa = 0; aa < nat; aa++) {
-          const double knej = __dmul_rn(kj, ej[aa * G3]);
-          double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
-                 p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
-          if (aa == b) {
-            p0 = -m0;
-            p1 = -m1;
-            p2 = -m2;
-          }
-          double *d3 = dst + (int64_t)(3 * aa) * ld;
-          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          d3[0] = fma(ui[3 * aa + 0], c2, p0);
-          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
-          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
-        }
-        continue;
-      }
-#pragma unroll
-      for (int aa = 0; aa < nat; aa++) {
-        // explicit roundings (no FMA contraction of p into m): the boundary path below forms the same numbers, so a
-        // block comes out bit-identical whether it is written whole or clipped to a row slab (sharded assembly)
-        const double knej = __dmul_rn(kj, ej[aa * G3]);
-        const double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
-                     p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
-        m0 = __dadd_rn(m0, p0);
-        m1 = __dadd_rn(m1, p1);
-        m2 = __dadd_rn(m2, p2);
-        if (aa != b) {  // the three a == b rows are completed after the loop
-          double *d3 = dst + (int64_t)(3 * aa) * ld;
-          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          KREG_CHECK(d3 >= a.K + a.row_begin * ld, 3);
-          d3[0] = fma(ui[3 * aa + 0], c2, p0);
-          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
-          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
-        }
-      }
-      // diagonal 3x3 block: (k/s^2) sum_c E_i(b,c)[t] E_j(b,c)[u] = -(sum over rows of the products above)
-      dst = a.K + (rbase + 3 * b) * ld + a.nv + j * G3 + cc;
-      dst[0] = fma(ui[3 * b + 0], c2, -m0);
-      dst[ld] = fma(ui[3 * b + 1], c2, -m1);
-      dst[2 * ld] = fma(ui[3 * b + 2], c2, -m2);
-    } else {
-      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal
-      double m[3] = {0.0, 0.0, 0.0};
-      for (int aa = 0; aa < nat; aa++)
-        for (int t = 0; t < 3; t++) m[t] = __dadd_rn(m[t], __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
-      for (int q = 0; q < G3; q++) {
-        const int aa = q / 3, t = q - aa * 3;
-        double val = fma(pb[2 + q], c2, aa == b ? -(t == 0 ? m[0] : t == 1 ? m[1] : m[2])
-                                               : __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
-        if (j == i && q == cc) val += a.lambdag;
-        const int64_t rr = rbase + q;
-        if (rr >= a.row_begin && rr < a.row_end) {
-          KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          dst[(int64_t)q * ld] = val;
-        }
-      }
-    }
-  }
-}
-
 // Fused version of the resident-block kernel: the pair terms are formed IN the emit step instead of by a kernel of their
 // own (0.79 of 3.3 ms at 21 atoms, and a workspace of 3 Nat + 1 doubles per geometry pair written and read back).  With
 // Dsq[j][c][b] = (X_j - X_i)[d_bc] in shared memory, the thread that owns column (j, b, u) forms in ONE loop over c
-//     -u_j[(b,u)]   = sum_c E_j[c][b][u] Dsq[j][c][b]        (what it needed anyway)
-//      u_i^(j)[(b,u)] = -sum_c E_i[c][b][u] Dsq[j][c][b]      (one more shared load and FMA per c)
-//      |X_j - X_i|^2 = 1/2 sum_b sum_c Dsq[j][c][b]^2         (column b's share; summed over b in a fixed order)
+//     -u_j[(b,u)]     = sum_c E_j[c][b][u] Dsq[j][c][b]
+//      u_i^(j)[(b,u)] = -sum_c E_i[c][b][u] Dsq[j][c][b]
+//      |X_j - X_i|^2  = 1/2 sum_b sum_c Dsq[j][c][b]^2         (column b's share; summed over b in a fixed order)
+//      m[t]           = sum_c E_j[c][b][u] E_i[c][b][t]        (the 3x3 diagonal blocks a == b are k/s^2 m[t] + rank-1 term)
 // and the value-gradient entries of BOTH orders of the pair come out of the same step:
 //      K[NtrVal + i*3Nat + (b,u)][j] = (k/s^2) u_i^(j)[(b,u)],     K[NtrVal + j*3Nat + (b,u)][i] = (k/s^2) u_j^(i)[(b,u)] = (k/s^2) sj.
 // A rank that owns only a row slab needs the second kind for its geometries j and EVERY i > j, also those whose rows
 // belong to other ranks: such steps run with the block emission switched off (`pair-only`).
-__global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int nat, int TJ, int NIB, int ei_global,
-                                                         int inorder, int64_t i_end) {
+// The kernel is bound by shared-memory wavefronts (84 % of the L1 data pipe at 21 atoms in its first version,
+// profiles/r02_gradfused21_v1_ncu.txt: every 64-bit LDS with more than one address costs two), hence:
+//  * NAT_CT > 0 (11..24 atoms): the thread's column of the RESIDENT E_j block, E_j[c][b][u] for all c, lives in Nat
+//    registers for the CTA's lifetime; NAT_CT = 0 takes the size at run time and reads it from shared memory;
+//  * EIG = false: E_i in shared memory is read with LDS (a run-time choice of pointer compiles to generic loads);
+//  * one pass over the rows, strictly in order (the diagonal sums m[t] come from the prologue loop);
+//  * at most 128 registers (two CTAs of 256 threads per SM): left alone, ptxas picks 128 for some sizes and 170-240 for
+//    others (hoisted loads of the unrolled loops), which halves the resident warps -- 3.1 against 4.4 TB/s at 11 atoms;
+//  * the value-gradient entries are 3 % of the bytes and 10 % of the time (small scattered writes: 5.0 TB/s without them,
+//    4.5 with, at 21 atoms).  K[row of j][i] comes one entry per row per step; the thread stages eight steps in shared
+//    memory and writes aligned 64-byte lines -- single 8-byte stores leave partial sectors behind that are evicted
+//    before the next steps complete them (+0.25 ms at 21 atoms, +1.3 ms at 11).  Writing both kinds cooperatively after
+//    the next step's barrier (TJ-wide runs; eight lanes per line) gained 1-3 % up to 21 atoms and cost an SM's second
+//    CTA from 24 atoms on (4.62 -> 2.62 TB/s): not kept.
+template <int NAT_CT, bool EIG>
+__global__ void __launch_bounds__(256, 2) grad_fused_kernel(const GradArgs a, int nat_rt, int TJ, int NIB, int64_t i_end) {
+  constexpr bool MFOLD = !EIG;  // diagonal sums from the prologue loop (E_i in shared memory: the extra loads are cheap)
+  const int nat = NAT_CT > 0 ? NAT_CT : nat_rt;
   const int G3 = 3 * nat, D = descr_size(nat), NS = nat | 1, EJ = a.ES, XS = a.XS;
+  const int T = blockDim.x;
   extern __shared__ __align__(128) double esm[];
   double *Ejs = esm;                                // [TJ*EJ]     resident
   double *Xj = Ejs + (size_t)TJ * EJ;               // [TJ*XS]     resident
   double *Eib = Xj + (size_t)TJ * XS;               // [2][EJ]     streamed (very large molecules: read through L1 instead)
-  double *Xib = Eib + (ei_global ? 0 : 2 * (size_t)EJ);  // [2][XS]
+  double *Xib = Eib + (EIG ? 0 : 2 * (size_t)EJ);   // [2][XS]
   double *Dsq = Xib + 2 * (size_t)XS;               // [TJ][nat*NS]
   double *Us = Dsq + (((size_t)TJ * nat * NS + 1) & ~(size_t)1);  // [TJ][G3]   u_i^(j)
   double *d2p = Us + (((size_t)TJ * G3 + 1) & ~(size_t)1);        // [TJ][nat]  per-column shares of |X_j - X_i|^2
   double *tab = d2p + (((size_t)TJ * nat + 1) & ~(size_t)1);      // [64]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(tab + 64);          // [3]
+  double *VG = tab + 64;                            // [8][T]      K[row of (j,b,u)][i] of up to 8 steps
+  uint64_t *bar = reinterpret_cast<uint64_t *>(VG + 8 * T);            // [3]
   unsigned short *ptab = reinterpret_cast<unsigned short *>(bar + 4);  // [D] d -> (lo | hi << 8)
 
   const bool full = a.fill == KREG_FILL_FULL;
@@ -1340,11 +944,13 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int n
 
   const int tid = threadIdx.x;
   const int64_t ld = a.ldk;
-  const int cols = npair * G3;
-  const bool okc = tid < cols;
+  const bool okc = tid < npair * G3;
   const int r = okc ? tid : 0;
-  const int jl = r / G3, cc = r - jl * G3, b = cc / 3;
+  const int jl = r / G3, cc = r - jl * G3, b = cc / 3, u = cc - 3 * b;
   const int64_t j = jb + jl;
+  const int64_t row2 = a.nv + j * G3 + cc;
+  const bool w2 = okc && a.nv > 0 && !full && row2 >= a.row_begin && row2 < a.row_end;
+  double *const dst2 = a.K + row2 * ld;
 
   if (tid == 0) {
     mbar_init(&bar[0], 1);
@@ -1352,14 +958,14 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int n
     mbar_init(&bar[2], 1);
     mbar_fence_init();
   }
-  fill_exp_table(tab, tid, blockDim.x);
+  fill_exp_table(tab, tid, T);
   __syncthreads();
   auto prefetch = [&](int n) {  // thread 0 only: operands of step n (geometry i_lo + n)
     const int64_t i = i_lo + n;
     const int buf = n & 1;
-    const unsigned be = ei_global ? 0u : (unsigned)EJ * 8, bx = (unsigned)XS * 8;
+    const unsigned be = EIG ? 0u : (unsigned)EJ * 8, bx = (unsigned)XS * 8;
     mbar_arrive_expect_tx(&bar[buf], be + bx);
-    if (!ei_global) bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
+    if (!EIG) bulk_g2s(Eib + (size_t)buf * EJ, a.E + i * a.ES, be, &bar[buf]);
     bulk_g2s(Xib + (size_t)buf * XS, a.Xc + i * XS, bx, &bar[buf]);
   };
   if (tid == 0) {
@@ -1370,17 +976,23 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int n
     prefetch(0);
   }
   __syncwarp();
-  for (int e = tid; e < D; e += blockDim.x) {
+  for (int e = tid; e < D; e += T) {
     int lo, hi;
     pair_from_index(nat, e, lo, hi);
     ptab[e] = (unsigned short)(lo | (hi << 8));
   }
-  for (int e = tid; e < TJ * nat; e += blockDim.x) Dsq[(size_t)e * NS + (e % nat)] = 0.0;  // diagonals: never rewritten
+  for (int e = tid; e < TJ * nat; e += T) Dsq[(size_t)e * NS + (e % nat)] = 0.0;  // diagonals: never rewritten
   mbar_wait(&bar[2], 0);
   const double *ej = Ejs + (size_t)jl * EJ + cc;  // E_j[c][b][u] at ej[c * G3]  (= -E_j(b,c)[u])
+  double ejr[NAT_CT > 0 ? NAT_CT : 1];
+  if constexpr (NAT_CT > 0) {
+#pragma unroll
+    for (int c = 0; c < NAT_CT; c++) ejr[c] = ej[c * G3];
+  }
   const double *dq = Dsq + (size_t)jl * nat * NS + b;
   const double *ui = Us + (size_t)jl * G3;
   const double half_c1 = -0.5 * a.c1;
+#define KREG_EJ(c) (NAT_CT > 0 ? ejr[c] : ej[(c) * G3])
 
   for (int n = 0; n < nsteps; n++) {
     __syncthreads();  // everyone left the buffer about to be refilled and the shared arrays of the previous step
@@ -1390,7 +1002,7 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int n
     mbar_wait(&bar[buf], (n >> 1) & 1);
     const int64_t i = i_lo + n;
     const double *Xi = Xib + (size_t)buf * XS;
-    for (int e = tid; e < npair * D; e += blockDim.x) {  // consecutive threads -> consecutive d: conflict-free reads
+    for (int e = tid; e < npair * D; e += T) {  // consecutive threads -> consecutive d: conflict-free reads
       const int jj = e / D, d = e - jj * D;
       const int lo = ptab[d] & 0xff, hi = ptab[d] >> 8;
       const double v = Xj[jj * XS + d] - Xi[d];
@@ -1399,24 +1011,39 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int n
       q[hi * NS + lo] = v;
     }
     __syncthreads();
-    const bool pair_wanted = okc && (full || j <= i);
-    // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t]); with t = u the same array gives this column's own u_i component
-    const double *eibase = ei_global ? a.E + i * a.ES : Eib + (size_t)buf * EJ;
-    const double *ei = eibase + 3 * b;
-    double sj = 0.0, uo = 0.0, dd = 0.0;
-    if (pair_wanted) {
-      const double *eo = eibase + cc;
-      for (int c = 0; c < nat; c++) {
-        const double dl = dq[c * NS];
-        sj = fma(ej[c * G3], dl, sj);    // -u_j[col]
-        uo = fma(-eo[c * G3], dl, uo);   // u_i^(j)[col]
-        dd = fma(dl, dl, dd);
+    const bool want = okc && (full || j <= i);
+    // E_i[c][b][t] at ei[c * G3 + t]  (= -E_i(b,c)[t])
+    const double *ei;
+    if constexpr (EIG) ei = a.E + i * a.ES + 3 * b;
+    else ei = Eib + (size_t)buf * EJ + 3 * b;
+    double sj = 0.0, uo = 0.0, dd = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    if (want) {
+      if constexpr (MFOLD) {
+#pragma unroll
+        for (int c = 0; c < nat; c++) {
+          const double dl = dq[c * NS], ejc = KREG_EJ(c);
+          const double e0 = ei[c * G3], e1 = ei[c * G3 + 1], e2 = ei[c * G3 + 2];
+          const double eu = u == 0 ? e0 : (u == 1 ? e1 : e2);
+          sj = fma(ejc, dl, sj);   // -u_j[col]
+          uo = fma(-eu, dl, uo);   // u_i^(j)[col]
+          dd = fma(dl, dl, dd);
+          m0 = fma(ejc, e0, m0);
+          m1 = fma(ejc, e1, m1);
+          m2 = fma(ejc, e2, m2);
+        }
+      } else {
+        for (int c = 0; c < nat; c++) {
+          const double dl = dq[c * NS];
+          sj = fma(KREG_EJ(c), dl, sj);
+          uo = fma(-ei[c * G3 + u], dl, uo);
+          dd = fma(dl, dl, dd);
+        }
       }
       Us[(size_t)jl * G3 + cc] = uo;
-      if (cc == 3 * b) d2p[jl * nat + b] = dd;
+      if (u == 0) d2p[jl * nat + b] = dd;
     }
     __syncthreads();
-    if (!pair_wanted) continue;
+    if (!want) continue;
     double d2 = 0.0;
     for (int c = 0; c < nat; c++) d2 += d2p[jl * nat + c];  // every thread of the pair sums in the same order
     const double kk = (j == i) ? 1.0 : exp_from_scaled(half_c1 * (0.5 * d2), tab);
@@ -1431,91 +1058,94 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(const GradArgs a, int n
         a.K[row1 * ld + j] = v;
         if (full) a.K[j * ld + row1] = v;
       }
-      const int64_t row2 = a.nv + j * G3 + cc;
-      if (!full && j != i && row2 >= a.row_begin && row2 < a.row_end) {
-        KREG_CHECK_STORE(a.K + row2 * ld + i, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-        a.K[row2 * ld + i] = kj * sj;
+      if (w2) {  // a slot per thread: no synchronisation
+        const int slot = (int)((reinterpret_cast<uintptr_t>(dst2 + i) >> 3) & 7);  // position in the 64-byte line of K
+        if (j != i) VG[slot * T + tid] = kj * sj;
+        if (slot == 7 || n == nsteps - 1) {
+          int64_t lo = i - slot;
+          if (lo < i_lo) lo = i_lo;
+          if (lo < j + 1) lo = j + 1;
+          for (int64_t ik = lo; ik <= i; ik++) {
+            KREG_CHECK_STORE(dst2 + ik, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+            dst2[ik] = VG[(slot - (int)(i - ik)) * T + tid];
+          }
+        }
       }
     }
     if (i >= a.c_i1 || rbase + G3 <= a.row_begin || rbase >= a.row_end) continue;  // pair-only step
-    const bool interior = rbase >= a.row_begin && rbase + G3 <= a.row_end;
     const double c2 = (sj * a.inv_s2) * kj;  // -(k/s^2) u_j[col] / s^2
+    m0 *= kj;
+    m1 *= kj;
+    m2 *= kj;
     double *dst = a.K + rbase * ld + a.nv + j * G3 + cc;
-    if (interior && j != i) {
-      double m0 = 0.0, m1 = 0.0, m2 = 0.0;  // sums of the J_i^T J_j products over the rows, per t
-      if (inorder) {
-        // rows strictly in order: the diagonal sums come from a pass of their own, so that no 24-byte holes are left in
-        // the row segments for later (partial 32-byte sectors cost more at the memory side than the extra reads here)
-#pragma unroll 3
-        for (int aa = 0; aa < nat; aa++) {
-          const double knej = __dmul_rn(kj, ej[aa * G3]);
-          m0 = __dadd_rn(m0, __dmul_rn(knej, -ei[aa * G3 + 0]));
-          m1 = __dadd_rn(m1, __dmul_rn(knej, -ei[aa * G3 + 1]));
-          m2 = __dadd_rn(m2, __dmul_rn(knej, -ei[aa * G3 + 2]));
-        }
-#pragma unroll 3
-        for (int aa = 0; aa < nat; aa++) {
-          const double knej = __dmul_rn(kj, ej[aa * G3]);
-          double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
-                 p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
-          if (aa == b) {
-            p0 = -m0;
-            p1 = -m1;
-            p2 = -m2;
-          }
-          double *d3 = dst + (int64_t)(3 * aa) * ld;
-          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          d3[0] = fma(ui[3 * aa + 0], c2, p0);
-          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
-          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
-        }
-        continue;
-      }
+    if (rbase >= a.row_begin && rbase + G3 <= a.row_end && j != i) {
+#pragma unroll
       for (int aa = 0; aa < nat; aa++) {
-        // explicit roundings (no FMA contraction of p into m): the boundary path below forms the same numbers, so a
-        // block comes out bit-identical whether it is written whole or clipped to a row slab (sharded assembly)
-        const double knej = __dmul_rn(kj, ej[aa * G3]);
-        const double p0 = __dmul_rn(knej, -ei[aa * G3 + 0]), p1 = __dmul_rn(knej, -ei[aa * G3 + 1]),
-                     p2 = __dmul_rn(knej, -ei[aa * G3 + 2]);
-        m0 = __dadd_rn(m0, p0);
-        m1 = __dadd_rn(m1, p1);
-        m2 = __dadd_rn(m2, p2);
-        if (aa != b) {  // the three a == b rows are completed after the loop
-          double *d3 = dst + (int64_t)(3 * aa) * ld;
-          KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          d3[0] = fma(ui[3 * aa + 0], c2, p0);
-          d3[ld] = fma(ui[3 * aa + 1], c2, p1);
-          d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
+        const double knej = -(kj * KREG_EJ(aa));
+        double p0 = __dmul_rn(knej, ei[aa * G3 + 0]), p1 = __dmul_rn(knej, ei[aa * G3 + 1]),
+               p2 = __dmul_rn(knej, ei[aa * G3 + 2]);
+        if constexpr (MFOLD) {
+          if (aa == b) {
+            p0 = m0;
+            p1 = m1;
+            p2 = m2;
+          }
+        } else {
+          m0 = __dadd_rn(m0, p0);
+          m1 = __dadd_rn(m1, p1);
+          m2 = __dadd_rn(m2, p2);
+          if (aa == b) continue;  // the three a == b rows are completed after the loop
         }
+        double *d3 = dst + (int64_t)(3 * aa) * ld;
+        KREG_CHECK_STORE(d3 + 2 * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+        d3[0] = fma(ui[3 * aa + 0], c2, p0);
+        d3[ld] = fma(ui[3 * aa + 1], c2, p1);
+        d3[2 * ld] = fma(ui[3 * aa + 2], c2, p2);
       }
-      double *dg = a.K + (rbase + 3 * b) * ld + a.nv + j * G3 + cc;
-      dg[0] = fma(ui[3 * b + 0], c2, -m0);
-      dg[ld] = fma(ui[3 * b + 1], c2, -m1);
-      dg[2 * ld] = fma(ui[3 * b + 2], c2, -m2);
+      if constexpr (!MFOLD) {
+        double *dg = dst + (int64_t)(3 * b) * ld;
+        dg[0] = fma(ui[3 * b + 0], c2, -m0);
+        dg[ld] = fma(ui[3 * b + 1], c2, -m1);
+        dg[2 * ld] = fma(ui[3 * b + 2], c2, -m2);
+      }
     } else {
-      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal
-      double m[3] = {0.0, 0.0, 0.0};
-      for (int aa = 0; aa < nat; aa++)
-        for (int t = 0; t < 3; t++) m[t] = __dadd_rn(m[t], __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
-      for (int q = 0; q < G3; q++) {
-        const int aa = q / 3, t = q - aa * 3;
-        double val = fma(ui[q], c2, aa == b ? -(t == 0 ? m[0] : t == 1 ? m[1] : m[2])
-                                            : __dmul_rn(__dmul_rn(kj, ej[aa * G3]), -ei[aa * G3 + t]));
-        if (j == i && q == cc) val += a.lambdag;
-        const int64_t rr = rbase + q;
-        if (rr >= a.row_begin && rr < a.row_end) {
-          KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
-          dst[(int64_t)q * ld] = val;
+      // boundary (rare): rows clipped to [row_begin, row_end), lambda on the matrix diagonal; the same numbers as above
+      double mm[3] = {m0, m1, m2};
+      if constexpr (!MFOLD) {
+        for (int aa = 0; aa < nat; aa++) {
+          const double knej = -(kj * KREG_EJ(aa));
+          for (int t = 0; t < 3; t++) mm[t] = __dadd_rn(mm[t], __dmul_rn(knej, ei[aa * G3 + t]));
+        }
+        for (int t = 0; t < 3; t++) mm[t] = -mm[t];
+      }
+#pragma unroll
+      for (int aa = 0; aa < nat; aa++) {
+        const double knej = -(kj * KREG_EJ(aa));
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          double pt = __dmul_rn(knej, ei[aa * G3 + t]);
+          if (aa == b) pt = t == 0 ? mm[0] : (t == 1 ? mm[1] : mm[2]);
+          double val = fma(ui[3 * aa + t], c2, pt);
+          const int q = 3 * aa + t;
+          if (j == i && q == cc) val += a.lambdag;
+          const int64_t rr = rbase + q;
+          if (rr >= a.row_begin && rr < a.row_end) {
+            KREG_CHECK_STORE(dst + (int64_t)q * ld, a.K + a.row_begin * ld, (a.row_end - a.row_begin) * ld);
+            dst[(int64_t)q * ld] = val;
+          }
         }
       }
     }
   }
+#undef KREG_EJ
 }
 
 static size_t fused_smem_doubles(int nat, int XS, int EJ, int tj, int ei_global) {
   const int G3 = 3 * nat, D = descr_size(nat), NS = nat | 1;
+  const size_t threads = (size_t)((tj * G3 + 31) / 32) * 32;
   size_t n = (size_t)tj * ((size_t)EJ + XS) + 2 * ((ei_global ? 0 : (size_t)EJ) + XS) + (((size_t)tj * nat * NS + 1) & ~(size_t)1) +
              (((size_t)tj * G3 + 1) & ~(size_t)1) + (((size_t)tj * nat + 1) & ~(size_t)1) + 64;
+  n += 8 * threads;  // staged value-gradient entries
   n += 4 + (D + 3) / 4;  // barriers, pair table (unsigned short)
   return n;
 }
@@ -1523,158 +1153,118 @@ static size_t fused_smem_doubles(int nat, int XS, int EJ, int tj, int ei_global)
 #ifndef KREG_EMIT_TEMPLATE_MAX
 #define KREG_EMIT_TEMPLATE_MAX 10  // largest molecule emitted by the register-resident grad_emit_kernel<NAT>
 #endif
-#ifndef KREG_EMIT_INORDER_MAX
-#define KREG_EMIT_INORDER_MAX 28   // up to here grad_emit_rt_kernel writes the rows strictly in order (see the kernel)
-#endif
-
-// launch plan of the run-time kernels (KREG_RT_* environment variables override, for tuning runs)
-struct RtPlan {
-  int JT, TJ, NIB, threads, ei_global;
-  size_t pair_smem, emit_smem;
-};
-
 static int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
 }
 
-static size_t emit_smem_doubles(int nat, int XS, int EJ, int tj, int ei_global = 0) {
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, NS = nat | 1;
-  size_t n = (size_t)tj * ((size_t)EJ + XS) + 2 * ((ei_global ? 0 : (size_t)EJ) + XS + (size_t)tj * PW) +
-             (((size_t)tj * nat * NS + 1) & ~(size_t)1);
-  n += 4 + (D + 3) / 4;  // barriers, pair table (unsigned short)
-  return n;
-}
+// molecules above the register-resident emit kernel's range: pair terms formed inside the emit kernel (grad_fused_kernel)
+static bool grad_fused(int nat) { return nat > KREG_EMIT_TEMPLATE_MAX; }
 
-static RtPlan rt_plan(int nat, const GradArgs &a) {
-  RtPlan p;
-  const int G3 = 3 * nat, D = descr_size(nat), PW = (G3 + 3) & ~1, PWS = PW | 1, DP = D | 1, EJ = a.ES, XS = a.XS;
-  // pair terms: as many j per CTA as ~100 KB allow (two CTAs per SM), at most 64
-  const size_t fixed = (size_t)EJ + ((D + 1) & ~1) + 64 + 4;
-  const size_t per_j = (size_t)DP + PWS + 1;
-  long jt = ((long)(100 * 1024 / 8) - (long)fixed) / (long)per_j;
-  if (jt < 4) jt = ((long)(220 * 1024 / 8) - (long)fixed) / (long)per_j;  // large molecules: one CTA per SM
-  if (jt > 64) jt = 64;
-  if (jt < 1) jt = 1;
-  p.JT = env_int("KREG_RT_JT", (int)jt);
-  p.pair_smem = (fixed + (((size_t)p.JT * DP + 1) & ~(size_t)1) + (((size_t)p.JT * PWS + 1) & ~(size_t)1)) * sizeof(double);
-  // emit: one column per thread, up to 256 columns per j-block; two CTAs per SM when the resident block allows it
-  int tj = 256 / G3;
-  if (tj < 1) tj = 1;
-  if (tj > 16) tj = 16;
-  const size_t two_ctas = 112 * 1024 / 8, one_cta = 224 * 1024 / 8;
-  int t2 = tj;
-  while (t2 > 1 && emit_smem_doubles(nat, XS, EJ, t2) > two_ctas) t2--;
-  if (emit_smem_doubles(nat, XS, EJ, t2) <= two_ctas && 2 * t2 >= tj) {
-    tj = t2;
-  } else {
-    while (tj > 1 && emit_smem_doubles(nat, XS, EJ, tj) > one_cta) tj--;
-  }
-  p.ei_global = env_int("KREG_RT_EIG", emit_smem_doubles(nat, XS, EJ, tj) > one_cta ? 1 : 0);
-  p.TJ = env_int("KREG_RT_TJ", tj);
-  if (p.TJ < 1) p.TJ = 1;
-  p.NIB = env_int("KREG_RT_NIB", 16);
-  if (p.NIB < 1) p.NIB = 1;
-  p.threads = ((p.TJ * G3 + 31) / 32) * 32;
-  p.emit_smem = emit_smem_doubles(nat, XS, EJ, p.TJ, p.ei_global) * sizeof(double);
-  return p;
-}
-
-static int launch_grad_rt(int nat, const GradArgs &a, bool pair_terms, bool emit, cudaStream_t st) {
-  const RtPlan p = rt_plan(nat, a);
+// (KREG_RT_H / KREG_RT_NIB / KREG_RT_EIG override the launch plan, for tuning runs)
+static int launch_grad_fused(int nat, const GradArgs &a, cudaStream_t st) {
   if (a.c_i1 <= a.c_i0) return KREG_OK;
-  if (pair_terms) {
-    if (p.pair_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
-    KREG_CUDA_TRY(cudaFuncSetAttribute(pair_terms_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.pair_smem));
-    dim3 grid((unsigned)((a.ntr + p.JT - 1) / p.JT), (unsigned)(a.c_i1 - a.c_i0));
-    pair_terms_rt_kernel<<<grid, 256, p.pair_smem, st>>>(a, nat, p.JT);
-    KREG_LAUNCH_CHECK();
+  const int G3 = 3 * nat, XS = a.XS, EJ = a.ES;
+  // geometries j per CTA: as many thread groups of 3 Nat columns as 256 threads hold; two CTAs per SM when the resident
+  // block allows it.  (Two geometries per thread -- half the E_i loads per output -- was measured and dropped: the 2 Nat
+  // registers of E_j columns halve the resident warps, 4.19 against 4.38 TB/s at 21 atoms, 3.95 against 5.07 at 12.)
+  int h = 256 / G3;
+  if (h < 1) h = 1;
+  if (h > 16) h = 16;
+  const size_t two_ctas = 112 * 1024 / 8, one_cta = 224 * 1024 / 8;
+  auto need = [&](int hh, int eig) { return fused_smem_doubles(nat, XS, EJ, hh, eig); };
+  int h2 = h;
+  while (h2 > 1 && need(h2, 0) > two_ctas) h2--;
+  if (need(h2, 0) <= two_ctas && 2 * h2 >= h) {
+    h = h2;
+  } else {
+    while (h > 1 && need(h, 0) > one_cta) h--;
   }
-  if (!emit) return KREG_OK;
-  if (p.threads > 256 || p.emit_smem > 227 * 1024) return KREG_E_UNSUPPORTED;
-  dim3 grid((unsigned)((a.ntr + p.TJ - 1) / p.TJ), (unsigned)((a.c_i1 - a.c_i0 + p.NIB - 1) / p.NIB));
-  KREG_CUDA_TRY(cudaFuncSetAttribute(grad_emit_rt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.emit_smem));
-  grad_emit_rt_kernel<0><<<grid, p.threads, p.emit_smem, st>>>(a, nat, p.TJ, p.NIB, p.ei_global,
-                                                               env_int("KREG_RT_INORDER", nat <= KREG_EMIT_INORDER_MAX ? 1 : 0));
+  h = env_int("KREG_RT_H", h);
+  if (h < 1) h = 1;
+  const int eig = env_int("KREG_RT_EIG", need(h, 0) > one_cta ? 1 : 0);
+  const int tj = h;
+  int nib = env_int("KREG_RT_NIB", 16);
+  if (nib < 1) nib = 1;
+  const int threads = ((h * G3 + 31) / 32) * 32;
+  const size_t smem = need(h, eig) * sizeof(double);
+  if (threads > 256 || smem > 227 * 1024) return KREG_E_UNSUPPORTED;
+  // a row slab of a matrix with value rows also owns K[its gradient rows][i] for every LATER geometry i (pair-only steps)
+  const bool full = a.fill == KREG_FILL_FULL;
+  const int64_t i_end = (!full && a.nv > 0) ? a.ntr : a.c_i1;
+  dim3 grid((unsigned)((a.ntr + tj - 1) / tj), (unsigned)((i_end - a.c_i0 + nib - 1) / nib));
+#define KREG_LAUNCH_FUSED(KERN, NRT)                                                                             \
+  do {                                                                                                           \
+    KREG_CUDA_TRY(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    KERN<<<grid, threads, smem, st>>>(a, NRT, tj, nib, i_end);                                                   \
+  } while (0)
+  if (nat <= KREG_FUSED_MAX_NATOMS && !eig) {
+    switch (nat) {
+#define KREG_CASE(N)                                      \
+  case N:                                                 \
+    KREG_LAUNCH_FUSED((grad_fused_kernel<N, false>), N);  \
+    break;
+      KREG_CASE(11) KREG_CASE(12) KREG_CASE(13) KREG_CASE(14) KREG_CASE(15) KREG_CASE(16) KREG_CASE(17) KREG_CASE(18)
+      KREG_CASE(19) KREG_CASE(20) KREG_CASE(21) KREG_CASE(22) KREG_CASE(23) KREG_CASE(24)
+#undef KREG_CASE
+      default:
+        return KREG_E_UNSUPPORTED;
+    }
+  } else if (eig) {
+    KREG_LAUNCH_FUSED((grad_fused_kernel<0, true>), nat);
+  } else {
+    KREG_LAUNCH_FUSED((grad_fused_kernel<0, false>), nat);
+  }
+#undef KREG_LAUNCH_FUSED
   KREG_LAUNCH_CHECK();
   return KREG_OK;
 }
 
+// up to KREG_EMIT_TEMPLATE_MAX atoms: pair terms (+ value-gradient rows) into the workspace, then the register-resident emit
 template <int NAT>
-static int launch_grad_nat(const GradArgs &a, cudaStream_t st, bool do_pair, bool do_emit) {
+static int launch_grad_nat(const GradArgs &a, cudaStream_t st) {
   using C = GradCfg<NAT>;
-  if (!do_pair) {
-  } else if constexpr (C::D <= 45) {
-    using SM = PairSmall<NAT>;
+  using SM = PairSmall<NAT>;
+  {
     auto kern = pair_terms_small_kernel<NAT>;
     const size_t smem = (size_t)SM::DOUBLES * sizeof(double);
     KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((a.ntr + SM::JT - 1) / SM::JT), (unsigned)(a.c_i1 - a.c_i0));
     kern<<<grid, SM::JT, smem, st>>>(a);
     KREG_LAUNCH_CHECK();
-  } else {
-    auto kern = pair_terms_kernel<NAT>;
-    const size_t smem = (size_t)PairSmem<NAT>::doubles(a.XS) * sizeof(double);
-    KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((a.ntr + C::JT - 1) / C::JT), (unsigned)(a.c_i1 - a.c_i0));
-    kern<<<grid, 256, smem, st>>>(a);
-    KREG_LAUNCH_CHECK();
   }
-  if (!do_emit) return KREG_OK;
-  if constexpr (NAT <= KREG_EMIT_TEMPLATE_MAX) {
-    dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)(a.c_i1 - a.c_i0));
-    auto emit = grad_emit_kernel<NAT>;
-    const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
-    KREG_CUDA_TRY(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-    emit<<<grid, C::THREADS, esmem, st>>>(a);
-    KREG_LAUNCH_CHECK();
-    return KREG_OK;
-  } else {
-    return KREG_E_UNSUPPORTED;  // no register-resident emit kernel is built for this size
-  }
+  dim3 grid((unsigned)((a.ntr + C::NJB * C::TJ - 1) / (C::NJB * C::TJ)), (unsigned)(a.c_i1 - a.c_i0));
+  auto emit = grad_emit_kernel<NAT>;
+  const size_t esmem = (size_t)EmitSmem<NAT>::DOUBLES * sizeof(double);
+  KREG_CUDA_TRY(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+  emit<<<grid, C::THREADS, esmem, st>>>(a);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
 }
 
-// Which kernels run, by molecule size (measured on B200; KREG_PAIR_RT = 1 and KREG_EMIT_RT = 0/1 override
-// for A/B runs):
-//   pair terms : templated kernels up to 24 atoms, the run-time kernel above
-//   emit       : <= 10 atoms  grad_emit_kernel<NAT> (operands in registers: 5.1 TB/s at 9 atoms)
-//                >= 11        grad_emit_rt_kernel (operands in shared memory, j-block resident: 4.3 TB/s at 12, 3.6 at 21
-//                             and 24 atoms; the register version spills from 11 atoms up and stays at 3.2)
-// stage 1 = pair terms (+ value-gradient rows), stage 2 = emit, for the geometries [a.c_i0, a.c_i1)
-static int launch_grad(int nat, const GradArgs &a, int stage, cudaStream_t st) {
-  const bool emit_rt = nat > KREG_EMIT_TEMPLATE_MAX || env_int("KREG_EMIT_RT", 0) != 0;
-  const bool pair_rt = nat > KREG_FUSED_MAX_NATOMS || env_int("KREG_PAIR_RT", 0) != 0;
-  const bool do_pair = stage == 1, do_emit = stage == 2;
-  if (do_pair && pair_rt) return launch_grad_rt(nat, a, true, false, st);
-  if (do_emit && emit_rt) return launch_grad_rt(nat, a, false, true, st);
-  switch (nat) {
-#define KREG_CASE(N) \
-  case N:            \
-    return launch_grad_nat<N>(a, st, do_pair, do_emit);
-#ifdef KREG_ONLY_NAT9  /* experiment builds (tools/ab_kbuild.sh): one instantiation, seconds to compile */
-    KREG_CASE(9)
-#else
-    KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9)
-    KREG_CASE(10) KREG_CASE(11) KREG_CASE(12) KREG_CASE(13) KREG_CASE(14) KREG_CASE(15) KREG_CASE(16) KREG_CASE(17)
-    KREG_CASE(18) KREG_CASE(19) KREG_CASE(20) KREG_CASE(21) KREG_CASE(22) KREG_CASE(23) KREG_CASE(24)
-#endif
-#undef KREG_CASE
-    default:
-      return KREG_E_UNSUPPORTED;
-  }
-}
-
-// Gradient blocks of the geometries [g.p_i0, g.p_i1): pair terms, then emit, on the caller's stream.  (Pipelining the two over
-// chunks of geometries on two side streams -- the pair-terms kernel of chunk c+1 under the emit kernel of chunk c -- was
-// measured and dropped: 3.57 -> 3.44 / 3.20 / 2.78 TB/s with 4 / 8 / 16 chunks at 21 atoms, 5.14 -> 5.02 / 4.89 / 4.70 at 9:
-// the emit kernel already fills every SM, so the second kernel only takes CTA slots away from it.)
+// Gradient blocks of the geometries [g.p_i0, g.p_i1) on the caller's stream.  Which kernels run, by molecule size (measured on
+// B200):
+//   <= 10 atoms  pair_terms_small_kernel<NAT> + grad_emit_kernel<NAT> (operands in registers: 5.1 TB/s at 9 atoms; the
+//                register version spills from 11 atoms up and stays at 3.2)
+//   >= 11        grad_fused_kernel (j-block resident in shared memory, pair terms formed in the emit step: 4.4-4.9 TB/s
+//                from 11 to 24 atoms, 3.2 at 32, 1.8 at 64)
+// (Pipelining the two kernels of the small path over chunks of geometries on two side streams was measured and dropped:
+// 5.14 -> 5.02 / 4.89 / 4.70 TB/s with 4 / 8 / 16 chunks at 9 atoms -- the emit kernel already fills every SM, so the second
+// kernel only takes CTA slots away from it.)
 static int launch_grad_stages(int nat, GradArgs g, cudaStream_t st) {
   if (g.p_i1 <= g.p_i0) return KREG_OK;
   g.c_i0 = g.p_i0;
   g.c_i1 = g.p_i1;
-  int rc = launch_grad(nat, g, 1, st);
-  if (rc) return rc;
-  return launch_grad(nat, g, 2, st);
+  if (grad_fused(nat)) return launch_grad_fused(nat, g, st);
+  switch (nat) {
+#define KREG_CASE(N) \
+  case N:            \
+    return launch_grad_nat<N>(g, st);
+    KREG_CASE(2) KREG_CASE(3) KREG_CASE(4) KREG_CASE(5) KREG_CASE(6) KREG_CASE(7) KREG_CASE(8) KREG_CASE(9) KREG_CASE(10)
+#undef KREG_CASE
+    default:
+      return KREG_E_UNSUPPORTED;
+  }
 }
 
 // workspace carve-up helpers ---------------------------------------------------------------
@@ -1714,7 +1304,7 @@ static BuildWs build_ws(int nat, int64_t n, bool with_grad, int64_t pair_rows = 
   w.off_bias = take((size_t)n);
   w.off_biasc = take((size_t)n);
   w.off_E = with_grad ? take((size_t)n * ((nat * nat * 3 + 1) & ~1)) : off;
-  w.off_P = with_grad ? take((size_t)pair_rows * n * ((3 * nat + 3) & ~1)) : off;
+  w.off_P = (with_grad && !grad_fused(nat)) ? take((size_t)pair_rows * n * ((3 * nat + 3) & ~1)) : off;
   w.total = off;
   return w;
 }

@@ -72,9 +72,18 @@ def sub_slabs(slab: Tuple[int, int], pieces: int, align: int = 1, offset: int = 
 
 def piece_width(b: int, m: int) -> int:
     """Stored row length of a piece that ends at row b: only columns j < b of the lower triangle are defined, so a piece
-    travels as a (rows x b) trapezoid instead of full M-wide rows (half the NVLink bytes on average); even, so that the
-    assembly kernels keep their 16-byte stores."""
-    return min(m + (m & 1), b + (b & 1))
+    travels as a (rows x b) trapezoid instead of full M-wide rows (half the NVLink bytes on average); a multiple of 16
+    doubles, so that with `piece_buffer`'s base shift the row segments the assembly kernels write start on 128-byte lines
+    (engine.empty_kernel_matrix has the measurement)."""
+    up = lambda x: (x + 15) // 16 * 16
+    return min(up(m), up(b))
+
+
+def piece_buffer(rows: int, width: int, offset: int, device) -> torch.Tensor:
+    """Contiguous (rows x width) send buffer whose column `offset` (NtrVal of a gradient matrix) is 128-byte aligned."""
+    shift = (16 - offset % 16) % 16
+    flat = torch.empty(rows * width + shift, dtype=torch.float64, device=device)
+    return flat[shift:].view(rows, width)
 
 
 def gather_row_slabs(k_full: Optional[torch.Tensor], slab: torch.Tensor, slabs: Sequence[Tuple[int, int]],
@@ -116,7 +125,12 @@ def build_kernel_matrix_sharded(build_rows: Callable[[int, int, torch.Tensor, in
     slabs = triangle_row_slabs(m, ws, align, offset)
     plans = [sub_slabs(slabs[r], pieces, align, offset) for r in range(ws)]
     if rank == root:
-        k = torch.empty((m, m), dtype=torch.float64, device=device)
+        if device.type == "cuda":
+            from . import engine
+
+            k = engine.empty_kernel_matrix(m, offset, device)  # sector-aligned row segments (engine.empty_kernel_matrix)
+        else:
+            k = torch.empty((m, m), dtype=torch.float64, device=device)
         stages, reqs = [], []
         for r in range(ws):  # post every receive first: the senders' pieces arrive while the root assembles its own slab
             if r == root:
@@ -138,7 +152,7 @@ def build_kernel_matrix_sharded(build_rows: Callable[[int, int, torch.Tensor, in
         return k
     reqs, keep = [], []
     for (a, b) in plans[rank]:
-        buf = torch.empty((b - a, piece_width(b, m)), dtype=torch.float64, device=device)
+        buf = piece_buffer(b - a, piece_width(b, m), offset, device)
         build_rows(a, b, buf, a)
         reqs.append(dist.isend(buf, root))
         keep.append(buf)

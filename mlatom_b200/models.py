@@ -531,8 +531,12 @@ class _FusedHoldout:
         self.g_val = np.asarray(val_db.get_xyz_vectorial_properties(g_learn)) if g_learn is not None else None
         m = self.nv + self.ng
         dev = self.xyz.device
-        self.k0 = torch.empty((m, m), dtype=torch.float64, device=dev)
-        self.work = torch.empty_like(self.k0)
+        if self.xyz.is_cuda:
+            self.k0 = engine.empty_kernel_matrix(m, self.nv if self.ng else 0, dev)
+            self.work = engine.empty_kernel_matrix(m, self.nv if self.ng else 0, dev)
+        else:
+            self.k0 = torch.empty((m, m), dtype=torch.float64, device=dev)
+            self.work = torch.empty_like(self.k0)
         self.diag = torch.arange(m, device=dev)
         self.sigma = None
         self.fallbacks = 0  # grid points solved by the symmetric-indefinite route

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--lam", type=float, default=1e-6)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--plain", action="store_true", help="K as a dense torch.empty((M, M)) instead of the engine's layout")
+    ap.add_argument("--ldk", type=int, default=0, help="row stride of K in doubles (default M): alignment experiments")
+    ap.add_argument("--shift", type=int, default=0, help="offset of K's first element from a 256-byte boundary, doubles")
     args = ap.parse_args()
 
     ws = int(os.environ.get("WORLD_SIZE", "1"))
@@ -66,7 +69,14 @@ def main():
 
     r0, r1 = slabs[rank]
     if rank == 0:
-        k = torch.empty((m, m), dtype=torch.float64, device=dev)
+        if args.ldk or args.shift:
+            ldk = max(args.ldk, m)
+            flat = torch.empty(m * ldk + args.shift, dtype=torch.float64, device=dev)
+            k = flat[args.shift:].view(m, ldk)[:, :m]
+        elif args.plain or ws > 1:  # gather_row_slabs receives into row ranges of K: dense rows
+            k = torch.empty((m, m), dtype=torch.float64, device=dev)
+        else:
+            k = engine.empty_kernel_matrix(m, nv if args.grads else 0, dev)  # what the engine allocates for itself
         target, off = k, 0
     else:
         k = None
