@@ -142,6 +142,41 @@ int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double 
                          const double *xeq, double sigma, int symmetric, double lambda, double *Kout, int64_t ldk,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* Permutationally invariant kernel (values-trained models) --------------------------------------------------------
+ * MLatomF `molDescrType=permuted permInvKernel` (A_KRR_kernel.f90:773-804 kernelFunction; descriptor calcX,
+ * molDescr.f90:128-160 with permuteAtoms :197-220):
+ *     k(M_i, M_j) = S_ij / (sqrt(S_ii) sqrt(S_jj)),   S_ij = sum_P exp(-|X_i - X_j^P|^2 / (2 sigma^2)),
+ * X^P = RE descriptor of the geometry with its atoms permuted by the P-th permutation (and the equilibrium distances
+ * permuted alike).  X^P is an entry permutation of X: X^P[d] = X[pidx[P][d]], pidx[P][d(a,c)] = d(p_P(a), p_P(c)) with
+ * p_P the full 0-based atom map (mod_permInds, A_KRR_kernel.f90:944-950); pidx_inv is the table of the inverse maps.
+ * pidx / pidx_inv: DEVICE int32 [nperm][D]; row 0 must be the identity (the reference pairs block 1 with every block). */
+
+/* Replaces calcX for the permuted descriptor: X[p][P][d] (the reference's X(:,p), Nperm blocks of D). */
+int kreg_perm_descriptors(int natoms, int64_t npoints, const double *xyz, const double *xeq, int nperm,
+                          const int32_t *pidx, double *X, void *stream);
+/* S[p] = S_pp (KMiMi, A_KRR_kernel.f90:425-430) and, when dS != NULL, dS[p][a][t] = dS_pp / d xyz[p][a][t]
+ * (dKMiMidMiat_part, :432-451). */
+int kreg_perm_self_terms(int natoms, int64_t npoints, const double *xyz, const double *xeq, int nperm,
+                         const int32_t *pidx, const int32_t *pidx_inv, double sigma, double *S, double *dS, void *stream);
+/* Replaces calcKernel's value block / calc_Kvalidate with this kernel function (A_KRR_kernel.f90:149-159, 208-216):
+ * Kout[i][j] = k(M_a[i], M_b[j]), row-major na x ldk, both triangles; symmetric != 0 (same set on both sides) puts
+ * exactly 1 + lambda on the diagonal, i.e. the matrix kreg_solve factorises.  The S_ij^P terms run on the FP64 tensor-core
+ * tile kernel in row slabs of at most 256 MB. */
+size_t kreg_perm_kernel_block_workspace_bytes(int natoms, int64_t na, int64_t nb, int nperm);
+int kreg_perm_kernel_block(int natoms, int64_t na, const double *xyz_a, int64_t nb, const double *xyz_b,
+                           const double *xeq, int nperm, const int32_t *pidx, double sigma, int symmetric, double lambda,
+                           double *Kout, int64_t ldk, void *workspace, size_t workspace_bytes, void *stream);
+/* Prediction (Yest_KRR :225-245, YgradXYZest_KRR permInvKernel branch :414-503) runs through kreg_pack_model_x /
+ * kreg_predict on the EXPANDED training set: the ntrain * nperm rows of kreg_perm_descriptors with the coefficients
+ * alpha_expanded[j * nperm + P] = alpha[j] / sqrt(S_jj) written by kreg_perm_scale_alpha, prior 0, giving
+ * E' = sum_j alpha_j S_ij / sqrt(S_jj) and G' = dE'/dxyz; kreg_perm_finish_prediction then forms, in place,
+ *     E = prior + E' / sqrt(S_ii),    G = G' / sqrt(S_ii) - E' dS_ii / (2 S_ii^(3/2))        (:500-502).
+ * E must hold E' also when only G is wanted; G may be NULL. */
+int kreg_perm_scale_alpha(int64_t ntrain, int nperm, const double *alpha, const double *S, double *alpha_expanded,
+                          void *stream);
+int kreg_perm_finish_prediction(int natoms, int64_t npoints, const double *S, const double *dS, double prior, double *E,
+                                double *G, void *stream);
+
 /* Linear solve ------------------------------------------------------------------------------ */
 
 /* Device / pinned-host scratch needed by kreg_solve for an m x m system. */

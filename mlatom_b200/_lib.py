@@ -59,6 +59,17 @@ PROTOTYPES = {
         [c_int, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_int, c_double, c_void_p,
          c_int64, c_void_p, c_size_t, c_void_p],
     ),
+    "kreg_perm_descriptors": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "kreg_perm_self_terms": (
+        c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "kreg_perm_kernel_block_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int]),
+    "kreg_perm_kernel_block": (
+        c_int,
+        [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_double, c_int, c_double, c_void_p,
+         c_int64, c_void_p, c_size_t, c_void_p],
+    ),
+    "kreg_perm_scale_alpha": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kreg_perm_finish_prediction": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "kreg_solve_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t), POINTER(c_size_t)]),
     "kreg_solve": (c_int, [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "kreg_solve_indefinite_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t)]),

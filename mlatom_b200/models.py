@@ -77,9 +77,15 @@ class kreg:
                 self.model_file += ".npz"
             if os.path.exists(self.model_file):
                 self.kreg_api = KREG_API(device)
-                if self._unf:
+                if self._unf and self.model_file[-4:] != ".npz":
                     self.kreg_api.load_unf(self.model_file)
                 else:
+                    with np.load(self.model_file) as header:
+                        permuted = "pmap" in header.files
+                    if permuted:  # a permutationally invariant model (perminv.PermInvKREG.save_model)
+                        from .perminv import PermInvKREG
+
+                        self.kreg_api = PermInvKREG(device=device)
                     self.kreg_api.load_model(self.model_file)
         self.hyperparameters = type(self).hyperparameters.copy()
         self.hyperparameters.update(hyperparameters)
@@ -194,6 +200,21 @@ class kreg:
             prior = self.hyperparameters["prior"].value
         return lam, lam_g, prior
 
+    def _perm_inv_groups(self):
+        """Atom groups of MLatomF's ``permInvKernel`` request in ``additional_mlatomf_args`` (None: not requested)."""
+        args = [str(a) for a in self.__dict__.get("additional_mlatomf_args", None) or []]
+        if not any(a.casefold() == "perminvkernel" for a in args):
+            return None
+        from .perminv import parse_perm_inv_nuclei
+
+        for a in args:
+            if a.casefold().startswith("perminvgroups="):
+                raise NotImplementedError("permInvGroups (permuting whole groups of atoms) is not built; use permInvNuclei")
+        for a in args:
+            if a.casefold().startswith("perminvnuclei="):
+                return parse_perm_inv_nuclei(a.split("=", 1)[1])
+        raise ValueError("permInvKernel needs permInvNuclei=<atoms separated by '-', groups by '.'>")
+
     def train(self, molecular_database=None, property_to_learn=None, xyz_derivative_property_to_learn=None,
               save_model=True, invert_matrix=False, matrix_decomposition=None, prior=None,
               hyperparameters: Union[Dict[str, Any], "hyperparameters"] = {}):
@@ -203,7 +224,17 @@ class kreg:
                 self.model_file = f"kreg_{uuid.uuid4()}" + (".unf" if self._unf else ".npz")
             elif not self._unf and self.model_file[-4:] != ".npz":
                 self.model_file += ".npz"
-        self.kreg_api = KREG_API(self.device)
+        groups = self._perm_inv_groups()
+        if groups is not None:
+            # MLatomF's permutationally invariant kernel (additional_mlatomf_args=['permInvKernel', 'permInvNuclei=..',
+            # 'molDescrType=permuted'], models.py:494-495): same device path with the expanded training set, .npz model file
+            from .perminv import PermInvKREG
+
+            self.kreg_api = PermInvKREG(groups=groups, device=self.device)
+            if save_model and self.model_file[-4:] != ".npz":
+                self.model_file += ".npz"
+        else:
+            self.kreg_api = KREG_API(self.device)
         self.kreg_api.nthreads = self.nthreads
         if self.equilibrium_molecule is None:
             self.equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=molecular_database)
@@ -212,7 +243,7 @@ class kreg:
                             self.equilibrium_molecule, property_to_learn=property_to_learn,
                             xyz_derivative_property_to_learn=xyz_derivative_property_to_learn, prior=prior)
         if save_model:
-            if self._unf:
+            if self._unf and groups is None:
                 self.kreg_api.save_unf(self.model_file, atomic_numbers=np.asarray(self.equilibrium_molecule.atomic_numbers))
             else:
                 self.kreg_api.save_model(self.model_file)

@@ -573,6 +573,135 @@ void kro_kernel_block_generic(int kind, int nn, int D, long na, const double *Xa
     for (long j = 0; j < nb; j++) K[i * nb + j] = mlatomf_kfunk(kind, nn, D, Xa + i * D, Xb + j * D, sigma);
 }
 
+/* ---- permutationally invariant kernel on the permuted RE descriptor ------------------------
+ * MLatomF with molDescrType=permuted permInvKernel: the descriptor of a geometry is the concatenation of the RE
+ * descriptors of its Nperm atom-permuted copies (calcX, molDescr.f90:128-160; permuteAtoms :197-220: permutedXYZ(:,ii) =
+ * xyz(:,perm(ii)); the equilibrium distances are permuted the same way, :82-100), and
+ *     k(M_i, M_j) = sum_P Kfunk(X_i[block 1], X_j[block P]) / sqrt(sum_P Kfunk(X_i[1], X_i[P]) sum_P Kfunk(X_j[1], X_j[P]))
+ * (kernelFunction, A_KRR_kernel.f90:773-804).  PARITY UNPINNED: the MLatomF binary is absent, KREG.so has no such path.
+ * pmap[P][ii] is the full 0-based atom map of permutation P (mod_permInds, A_KRR_kernel.f90:944-950). */
+void kro_perm_descriptors(int nat, long np, const double *xyz, const double *req, int nperm, const int *pmap,
+                          double *X /* [np][nperm * D] */) {
+  const int D = nat * (nat - 1) / 2;
+#pragma omp parallel for schedule(static)
+  for (long p = 0; p < np; p++) {
+    double *pxyz = (double *)malloc(sizeof(double) * 3 * nat), *peq = (double *)malloc(sizeof(double) * 3 * nat);
+    double *reqd = (double *)malloc(sizeof(double) * D);
+    for (int P = 0; P < nperm; P++) {
+      for (int ii = 0; ii < nat; ii++) /* permuteAtoms, molDescr.f90:210-218 */
+        for (int t = 0; t < 3; t++) {
+          pxyz[3 * ii + t] = xyz[((size_t)p * nat + pmap[P * nat + ii]) * 3 + t];
+          peq[3 * ii + t] = req[3 * pmap[P * nat + ii] + t];
+        }
+      kro_xeq(nat, peq, reqd);                                             /* getReq on the permuted eq. geometry */
+      kro_descriptors(nat, 1, pxyz, reqd, X + ((size_t)p * nperm + P) * D); /* calcMolDescr with ReqMod = that block */
+    }
+    free(pxyz);
+    free(peq);
+    free(reqd);
+  }
+}
+
+/* kernelFunction, permInvKernel branch (A_KRR_kernel.f90:783-795); Xi, Xj are whole permuted descriptors */
+static double perm_kernel_function(int Xsize, int nperm, const double *Xi, const double *Xj, double sigma) {
+  double KMiMj = 0.0, KMiMi = 0.0, KMjMj = 0.0;
+  for (int PP = 0; PP < nperm; PP++) {
+    KMiMj = KMiMj + kernel(Xsize, Xi, Xj + (size_t)Xsize * PP, sigma);
+    KMiMi = KMiMi + kernel(Xsize, Xi, Xi + (size_t)Xsize * PP, sigma);
+    KMjMj = KMjMj + kernel(Xsize, Xj, Xj + (size_t)Xsize * PP, sigma);
+  }
+  return KMiMj / (sqrt(KMiMi) * sqrt(KMjMj));
+}
+
+/* calcKernel values block / calc_Kvalidate with that kernel function (A_KRR_kernel.f90:149-159, 208-216) */
+void kro_perm_kernel_block(int Xsize, int nperm, long na, const double *Xa, long nb, const double *Xb, double sigma,
+                           double *K) {
+  const size_t XV = (size_t)Xsize * nperm;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < na; i++)
+    for (long j = 0; j < nb; j++) K[i * nb + j] = perm_kernel_function(Xsize, nperm, Xa + i * XV, Xb + j * XV, sigma);
+}
+
+/* Yest_KRR (A_KRR_kernel.f90:225-245, values part) and the first-order part of YgradXYZest_KRR's permInvKernel branch
+ * (:414-503) for a values-trained model.  inv_pmap[P][a] = mod_inversePermInds(a,P).  E gets prior added
+ * (A_KRR.f90:1006).  Loop structure and association of the reference kept. */
+void kro_perm_predict(int nat, int nperm, const int *inv_pmap, long ntr, const double *X_tr /* [ntr][nperm*D] */,
+                      const double *alpha, double sigma, double prior, long np, const double *xyz_te,
+                      const double *X_te /* [np][nperm*D] */, int calc_grad, double *E, double *G /* [np][nat][3] */) {
+  const int Xsize = nat * (nat - 1) / 2;
+  const size_t XV = (size_t)Xsize * nperm;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < np; i++) {
+    const double *Xi = X_te + i * XV, *xyz = xyz_te + (size_t)i * nat * 3;
+    double y = 0.0;
+    for (long jj = 0; jj < ntr; jj++) y = y + alpha[jj] * perm_kernel_function(Xsize, nperm, Xi, X_tr + jj * XV, sigma);
+    E[i] = y + prior;
+    if (!calc_grad) continue;
+    double *tmp = (double *)calloc((size_t)3 * nat * 4, sizeof(double));
+    double *temp_Array1 = tmp, *in1 = tmp + 3 * nat, *dKMiMi = tmp + 6 * nat, *dKMiMj = tmp + 9 * nat;
+    double KMiMi = 0.0;
+    for (int PP = 0; PP < nperm; PP++) KMiMi = KMiMi + kernel(Xsize, Xi, Xi + (size_t)Xsize * PP, sigma);
+    /* dKMiMidMiat_part (:432-451) */
+    for (int PP = 0; PP < nperm; PP++) {
+      const size_t lb = (size_t)Xsize * PP;
+      const double cmf = kernel(Xsize, Xi, Xi + lb, sigma);
+      for (int a = 0; a < nat - 1; a++)
+        for (int cc = a + 1; cc < nat; cc++) {
+          const int dd = pair_index(nat, a, cc);
+          const int Pdd = pair_index(nat, inv_pmap[PP * nat + a], inv_pmap[PP * nat + cc]);
+          const double R = rij(xyz + 3 * a, xyz + 3 * cc);
+          const double temp1 = (Xi[lb + dd] + Xi[Pdd] - Xi[dd] * 2) * Xi[dd] / (R * R);
+          for (int tt = 0; tt < 3; tt++) {
+            const double temp2 = xyz[3 * cc + tt] - xyz[3 * a + tt];
+            in1[3 * a + tt] = in1[3 * a + tt] + temp1 * temp2;
+            in1[3 * cc + tt] = in1[3 * cc + tt] - temp1 * temp2;
+          }
+        }
+      for (int k = 0; k < 3 * nat; k++) {
+        dKMiMi[k] = dKMiMi[k] + cmf * in1[k];
+        in1[k] = 0.0;
+      }
+    }
+    for (int k = 0; k < 3 * nat; k++) dKMiMi[k] = dKMiMi[k] / (sigma * sigma);
+    /* loop over the training points (:454-503) */
+    for (long jj = 0; jj < ntr; jj++) {
+      const double *Xj = X_tr + jj * XV;
+      double KMiMj = 0.0, KMjMj = 0.0;
+      for (int PP = 0; PP < nperm; PP++) {
+        KMiMj = KMiMj + kernel(Xsize, Xi, Xj + (size_t)Xsize * PP, sigma);
+        KMjMj = KMjMj + kernel(Xsize, Xj, Xj + (size_t)Xsize * PP, sigma);
+      }
+      for (int k = 0; k < 3 * nat; k++) dKMiMj[k] = 0.0;
+      const double cmf = alpha[jj] / sqrt(KMiMi * KMjMj);
+      for (int PP = 0; PP < nperm; PP++) {
+        const size_t lb = (size_t)Xsize * PP;
+        const double cmf1 = kernel(Xsize, Xi, Xj + lb, sigma);
+        for (int a = 0; a < nat - 1; a++)
+          for (int cc = a + 1; cc < nat; cc++) {
+            const int dd = pair_index(nat, a, cc);
+            const double R = rij(xyz + 3 * a, xyz + 3 * cc);
+            const double temp1 = (Xj[lb + dd] - Xi[dd]) * Xi[dd] / (R * R);
+            for (int tt = 0; tt < 3; tt++) {
+              const double temp2 = xyz[3 * cc + tt] - xyz[3 * a + tt];
+              in1[3 * a + tt] = in1[3 * a + tt] + temp1 * temp2;
+              in1[3 * cc + tt] = in1[3 * cc + tt] - temp1 * temp2;
+            }
+          }
+        for (int k = 0; k < 3 * nat; k++) {
+          dKMiMj[k] = dKMiMj[k] + cmf1 * in1[k];
+          in1[k] = 0.0;
+        }
+      }
+      for (int k = 0; k < 3 * nat; k++) {
+        dKMiMj[k] = dKMiMj[k] / (sigma * sigma);
+        temp_Array1[k] = temp_Array1[k] + cmf * (dKMiMj[k] - dKMiMi[k] * KMiMj / KMiMi / 2.0);
+      }
+    }
+    for (int k = 0; k < 3 * nat; k++) G[(size_t)i * nat * 3 + k] = temp_Array1[k];
+    free(tmp);
+  }
+}
+
 int kro_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -186,3 +186,65 @@ def kernel_block_generic(kind: str, x_a, x_b, sigma: float, nn: int = 2) -> np.n
     load().kro_kernel_block_generic(c_int(KERNEL_KINDS[kind.lower()]), c_int(nn), c_int(x_a.shape[1]), c_long(x_a.shape[0]),
                                     _d(x_a), c_long(x_b.shape[0]), _d(x_b), c_double(sigma), _d(out))
     return out
+
+
+# ---- permutationally invariant kernel (MLatomF molDescrType=permuted permInvKernel) -- PARITY UNPINNED ----------------
+def perm_atom_maps(natoms: int, groups) -> np.ndarray:
+    """Full 0-based atom maps of every permutation of the atoms inside each group (MLatomF ``permInvNuclei=1-2.5-6``:
+    groups separated by '.', atoms by '-'; Nperm = prod (group size)!, dataset.f90:1952-1977).  A map follows
+    permuteAtoms / getPermIatoms (molDescr.f90:197-220): walking the atoms in order, the k-th atom that belongs to the
+    permuted set takes the k-th entry of the permuted index list.  Row 0 is the identity."""
+    import itertools
+
+    groups = [sorted(int(a) for a in g) for g in groups]
+    maps = []
+    for combo in itertools.product(*[itertools.permutations(g) for g in groups]):
+        perm_list = [a for g in combo for a in g]          # permIatomsNucl(iperm): the groups' permuted atoms in sequence
+        members = set(perm_list)
+        m, icount = list(range(natoms)), 0
+        for ii in range(natoms):
+            if ii in members:
+                m[ii] = perm_list[icount]
+                icount += 1
+        maps.append(m)
+    return np.asarray(maps, dtype=np.int32)
+
+
+def inverse_atom_maps(pmap: np.ndarray) -> np.ndarray:
+    """mod_inversePermInds (A_KRR_kernel.f90:944-950)."""
+    inv = np.empty_like(pmap)
+    for p in range(pmap.shape[0]):
+        inv[p, pmap[p]] = np.arange(pmap.shape[1], dtype=pmap.dtype)
+    return inv
+
+
+def perm_descriptors(xyz: np.ndarray, req: np.ndarray, pmap: np.ndarray) -> np.ndarray:
+    """Permuted RE descriptor (calcX, molDescr.f90:128-160): (N, Nperm * D), block P = RE descriptor of permutation P."""
+    xyz, req = _c(xyz), _c(req)
+    pmap = np.ascontiguousarray(pmap, dtype=np.int32)
+    n, nat, _ = xyz.shape
+    out = np.zeros((n, pmap.shape[0] * nat * (nat - 1) // 2))
+    load().kro_perm_descriptors(c_int(nat), c_long(n), _d(xyz), _d(req), c_int(pmap.shape[0]),
+                                pmap.ctypes.data_as(ctypes.c_void_p), _d(out))
+    return out
+
+
+def perm_kernel_block(x_a: np.ndarray, x_b: np.ndarray, nperm: int, sigma: float) -> np.ndarray:
+    """Normalised permutationally invariant Gaussian kernel (kernelFunction, A_KRR_kernel.f90:773-804)."""
+    x_a, x_b = _c(x_a), _c(x_b)
+    out = np.zeros((x_a.shape[0], x_b.shape[0]))
+    load().kro_perm_kernel_block(c_int(x_a.shape[1] // nperm), c_int(nperm), c_long(x_a.shape[0]), _d(x_a),
+                                 c_long(x_b.shape[0]), _d(x_b), c_double(sigma), _d(out))
+    return out
+
+
+def perm_predict(x_tr, alpha, sigma, prior, xyz_te, x_te, pmap, calc_grad=True):
+    """Yest_KRR and the permInvKernel branch of YgradXYZest_KRR (A_KRR_kernel.f90:225-245, 414-503), values-trained."""
+    x_tr, x_te, xyz_te, a = _c(x_tr), _c(x_te), _c(xyz_te), _c(alpha).reshape(-1)
+    inv = np.ascontiguousarray(inverse_atom_maps(np.asarray(pmap)), dtype=np.int32)
+    npred, nat, _ = xyz_te.shape
+    e, g = np.zeros(npred), np.zeros((npred, nat, 3))
+    load().kro_perm_predict(c_int(nat), c_int(inv.shape[0]), inv.ctypes.data_as(ctypes.c_void_p), c_long(x_tr.shape[0]),
+                            _d(x_tr), _d(a), c_double(sigma), c_double(prior), c_long(npred), _d(xyz_te), _d(x_te),
+                            c_int(1 if calc_grad else 0), _d(e), _d(g))
+    return e, (g if calc_grad else None)

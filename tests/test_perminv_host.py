@@ -1,0 +1,73 @@
+"""Permutationally invariant kernel, CPU side: the host logic of mlatom_b200/perminv.py (option parsing, atom maps,
+descriptor-index tables) against the oracle's literal permute-then-describe restatement (molDescr.f90:128-160, 197-220),
+and the oracle's own consistency (the restated first-order derivative branch, A_KRR_kernel.f90:414-503, against finite
+differences of the restated energy; invariance of the kernel on a symmetric molecule).  No GPU, no compute calls into the
+CUDA library.  Parity UNPINNED for this path (no MLatomF binary in the reference checkout)."""
+import numpy as np
+import pytest
+
+from mlatom_b200 import perminv
+from mlatom_b200 import synthetic as S
+
+
+def test_option_string_and_atom_maps():
+    groups = perminv.parse_perm_inv_nuclei("4-5.6-7-8")
+    assert groups == [[3, 4], [5, 6, 7]]
+    pmap = perminv.atom_maps(9, groups)
+    assert pmap.shape == (12, 9) and np.array_equal(pmap[0], np.arange(9))
+    assert len({tuple(r) for r in pmap.tolist()}) == 12  # all distinct
+    for r in pmap:  # atoms outside the groups never move; members stay inside their group
+        assert np.array_equal(r[:3], [0, 1, 2]) and r[8] == 8
+        assert sorted(r[3:5]) == [3, 4] and sorted(r[5:8]) == [5, 6, 7]
+    with pytest.raises(ValueError):
+        perminv.atom_maps(9, [[1, 2], [2, 3]])
+    with pytest.raises(ValueError):
+        perminv.atom_maps(4, [[3, 4]])
+
+
+@pytest.mark.parametrize("nat,spec", [(9, "4-5.6-7-8"), (5, "2-3-4-5"), (21, "20-21"), (3, "1-2-3")])
+def test_descriptor_index_tables_reproduce_the_permuted_descriptor(oracle, nat, spec):
+    """Block P of the reference's permuted descriptor (atoms AND equilibrium distances permuted, then described) is the
+    plain descriptor with its entries taken through pidx[P] -- bit for bit; pinv undoes it."""
+    eq = S.equilibrium(nat)
+    pmap = perminv.atom_maps(nat, perminv.parse_perm_inv_nuclei(spec))
+    assert np.array_equal(pmap, oracle.perm_atom_maps(nat, perminv.parse_perm_inv_nuclei(spec)))
+    pidx, pinv = perminv.descriptor_permutations(pmap)
+    d = nat * (nat - 1) // 2
+    x = S.geometries(eq, 6, 4, 0.1)
+    xp = oracle.perm_descriptors(x, eq, pmap).reshape(6, pmap.shape[0], d)
+    plain = oracle.descriptors(x, oracle.xeq(eq))
+    assert np.array_equal(xp[:, 0], plain)
+    for p in range(pmap.shape[0]):
+        assert np.array_equal(xp[:, p], plain[:, pidx[p]])
+        assert np.array_equal(plain[:, pinv[p]][:, pidx[p]], plain)
+
+
+def test_oracle_gradient_branch_against_finite_differences(oracle):
+    nat, sigma = 9, 1.1
+    eq = S.equilibrium(nat)
+    pmap = perminv.atom_maps(nat, [[3, 4], [5, 6, 7]])
+    xtr, xte = S.geometries(eq, 25, 1, 0.1), S.geometries(eq, 4, 2, 0.1)
+    xptr = oracle.perm_descriptors(xtr, eq, pmap)
+    alpha = np.random.default_rng(0).standard_normal(25)
+    e, g = oracle.perm_predict(xptr, alpha, sigma, 0.3, xte, oracle.perm_descriptors(xte, eq, pmap), pmap)
+    h = 1e-5
+    for a, t in [(0, 0), (3, 1), (6, 2), (8, 0)]:
+        xp, xm = xte.copy(), xte.copy()
+        xp[:, a, t] += h
+        xm[:, a, t] -= h
+        ep, _ = oracle.perm_predict(xptr, alpha, sigma, 0.3, xp, oracle.perm_descriptors(xp, eq, pmap), pmap, False)
+        em, _ = oracle.perm_predict(xptr, alpha, sigma, 0.3, xm, oracle.perm_descriptors(xm, eq, pmap), pmap, False)
+        assert np.abs((ep - em) / (2 * h) - g[:, a, t]).max() <= 1e-8
+
+
+def test_oracle_kernel_is_invariant_on_a_symmetric_molecule(oracle):
+    eq = np.array([[0, 0, 0], [1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], dtype=np.float64) * 0.63
+    pmap = perminv.atom_maps(5, [[1, 2, 3, 4]])
+    xa, xb = S.geometries(eq, 8, 1, 0.1), S.geometries(eq, 5, 2, 0.1)
+    k = oracle.perm_kernel_block(oracle.perm_descriptors(xa, eq, pmap), oracle.perm_descriptors(xb, eq, pmap), 24, 0.9)
+    ks = oracle.perm_kernel_block(oracle.perm_descriptors(xa[:, pmap[7]], eq, pmap), oracle.perm_descriptors(xb, eq, pmap),
+                                  24, 0.9)
+    assert np.abs(k - ks).max() <= 1e-14
+    kd = oracle.perm_kernel_block(oracle.perm_descriptors(xa, eq, pmap), oracle.perm_descriptors(xa, eq, pmap), 24, 0.9)
+    assert np.abs(np.diag(kd) - 1.0).max() <= 4e-16 and np.abs(kd - kd.T).max() <= 1e-15
