@@ -142,6 +142,30 @@ int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double 
                          const double *xeq, double sigma, int symmetric, double lambda, double *Kout, int64_t ldk,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* Models on those kernel functions (values-trained; MLatomF `kernel=exponential|Matern|Laplacian`, reached in the reference
+ * through kreg(ml_program='MLatomF') + additional_mlatomf_args, models.py:494-495).  Training = kreg_kernel_block_ex
+ * (symmetric, lambda) + kreg_solve.  Prediction of energies AND gradients for the three kernels of the Euclidean distance
+ * runs on the tensor-core skeleton of the large-molecule path, any molecule size:
+ *   E[i] = prior + sum_j alpha_j k(r_ij)                                   (Yest_KRR, A_KRR_kernel.f90:225-245)
+ *   G[i] = J_i^T sum_j alpha_j phi(r_ij) (X_j - X_i),  phi = -k'(r) / r     (YgradXYZest_KRR :731-744 -> dKdMiat_unpermuted
+ *          :1407-1447 -> dKdXid :1178-1233)
+ * Matern of order nn >= 1: the reference's analytic derivative; exponential (and Matern nn = 0): the reference takes a
+ * central difference of Kfunk in descriptor space (:1222-1230), here the analytic phi = k / (sigma r), 0 at r = 0;
+ * KREG_KERNEL_GAUSSIAN is accepted too (the same numbers as kreg_predict through this path).  The Laplacian kernel
+ * (L1 distance, no GEMM form) predicts energies through kreg_kernel_block_ex + kreg_block_dot. */
+size_t kreg_radial_packed_model_bytes(int natoms, int64_t ntrain);
+/* Packs centred descriptor rows, column terms, alpha and the transposed rows (the values-only layout of the large-molecule
+ * path; the kernel width does not enter).  `packed` must be 256-byte aligned; center[D] is written. */
+int kreg_pack_model_radial(int natoms, int64_t ntrain, const double *xyz_train, const double *xeq,
+                           const double *alpha_val, double *center, void *packed, size_t packed_bytes, void *stream);
+size_t kreg_predict_radial_workspace_bytes(int natoms, int64_t ntrain, int64_t npoints);
+int kreg_predict_radial(int kind, int nn, int natoms, int64_t ntrain, const void *packed, const double *center,
+                        const double *xeq, double sigma, double prior, int64_t npoints, const double *xyz, int flags,
+                        double *E, double *G, void *workspace, size_t workspace_bytes, void *stream);
+/* E[i] = prior + sum_j K[i][j] alpha[j] for a materialised kernel block (row-major na x ldk): deterministic. */
+int kreg_block_dot(int64_t na, int64_t nb, const double *K, int64_t ldk, const double *alpha, double prior, double *E,
+                   void *stream);
+
 /* Permutationally invariant kernel (values-trained models) --------------------------------------------------------
  * MLatomF `molDescrType=permuted permInvKernel` (A_KRR_kernel.f90:773-804 kernelFunction; descriptor calcX,
  * molDescr.f90:128-160 with permuteAtoms :197-220):

@@ -59,6 +59,15 @@ PROTOTYPES = {
         [c_int, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_double, c_int, c_double, c_void_p,
          c_int64, c_void_p, c_size_t, c_void_p],
     ),
+    "kreg_radial_packed_model_bytes": (c_size_t, [c_int, c_int64]),
+    "kreg_pack_model_radial": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kreg_predict_radial_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64]),
+    "kreg_predict_radial": (
+        c_int,
+        [c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_int,
+         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "kreg_block_dot": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p]),
     "kreg_perm_descriptors": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "kreg_perm_self_terms": (
         c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),

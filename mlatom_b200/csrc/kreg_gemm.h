@@ -41,6 +41,10 @@ struct ValuesArgs {
   int nn;              // Matern order n (nu = n + 1/2)
   double inv_sigma;
   double mat_c[12];    // Matern polynomial coefficients in (2 r / sigma)^m, m = 0..nn
+  // EPI_WR (prediction with the radial kernels, kreg_predict_big.cu): phi(r) = -k'(r) / r, the factor of (X_j - X_i) in
+  // dk/dX_i (dKdXid, A_KRR_kernel.f90:1178-1233); Matern: exp(-r/sigma) sum_m mat_d[m] (2 r / sigma)^m, m = 0..nn-1
+  double mat_d[12];
+  double inv_s2;
 };
 
 constexpr int kGemmKC = 9;  // k-steps per chunk of the GEMM modes (chunk width 36 doubles, conflict-free stride 36)
@@ -51,8 +55,10 @@ constexpr int EPI_W = 1;    // prediction GEMM1: exp * column scale -> chunk-maj
 constexpr int EPI_WV = 2;   // prediction GEMM1, gradient models: exp * Cin -> chunk-major W and K
 constexpr int EPI_LIN = 3;  // plain GEMM: C = A B^T + column term (row-major)
 constexpr int EPI_KR = 4;   // radial kernels of the Euclidean distance: exponential, Matern
+constexpr int EPI_WR = 5;   // prediction GEMM1 for the radial kernels: phi(r) * column scale -> chunk-major W, k(r) * column scale -> K
 
 // kreg_kbuild.cu
+void set_matern_coefficients(ValuesArgs &a, int nn, double sigma);
 int launch_gemm_epi(const ValuesArgs &a, int epi, cudaStream_t st);
 // centred, zero-padded descriptor rows Xc[n][XS] of the geometries xyz[n][nat][3]; bias[p] = -c1 |Xc_p|^2 / 2 and
 // (optionally) bias_col[p] = -|Xc_p|^2 / 2

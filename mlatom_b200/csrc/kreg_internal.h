@@ -21,6 +21,11 @@ int big_predict(int nat, int64_t ntr, const void *packed, const double *center, 
                 double prior, bool has_v, int64_t npoints, const double *xyz, double *E, double *G, void *workspace,
                 size_t workspace_bytes, int sms, cudaStream_t st);
 
+size_t big_predict_radial_workspace_bytes(int nat, int64_t ntr, int64_t npoints, int sms);
+int big_predict_radial(int kind, int nn, int nat, int64_t ntr, const void *packed, const double *center, const double *xeq,
+                       double sigma, double prior, int64_t npoints, const double *xyz, double *E, double *G,
+                       void *workspace, size_t workspace_bytes, int sms, cudaStream_t st);
+
 // Shapes of the tensor-core formulation for a molecule with NAT atoms.
 //   GEMM1  S  = Xtest (rows x D) . Xtrain^T        : K dimension D, padded to 4*KS
 //   GEMM2  A += W (rows x 8) . [Xtrain | 1] (8 x N) : N = D + 1 (ones column -> energy), padded to 8*NT

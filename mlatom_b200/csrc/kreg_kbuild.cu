@@ -198,6 +198,59 @@ __device__ __forceinline__ void radial_tile_epilogue(const ValuesArgs &a, double
   }
 }
 
+// Prediction GEMM1 epilogue for the radial kernels (kreg_predict_big.cu, radial models): from r^2 = -2 (s + b_i) both
+//   w_ij = alpha_j phi(r_ij),  phi = -k'(r) / r   (the factor of X_j - X_i in dk/dX_i: dKdXid, A_KRR_kernel.f90:1178-1233)
+//   e_ij = alpha_j k(r_ij)                         (Yest_KRR, A_KRR_kernel.f90:225-245)
+// go out chunk-major, the A operands of the two second GEMMs.  kind: Gaussian (phi = k / s^2; exercises this path against
+// the fused kernels), exponential (phi = k / (sigma r), 0 at r = 0 like the reference's central difference of exp(-|x|)),
+// Matern of order nn >= 1 (the reference's analytic form, :1205-1219: a polynomial in r, regular at 0).
+__device__ __forceinline__ void radial_pair_values(const ValuesArgs &a, double s_plus_bi, double &k, double &phi) {
+  const double r2 = fmax(-2.0 * s_plus_bi, 0.0);
+  if (a.kind == KREG_KERNEL_GAUSSIAN) {
+    k = exp(-0.5 * r2 * a.inv_s2);
+    phi = k * a.inv_s2;
+    return;
+  }
+  const double r = sqrt(r2), x = r * a.inv_sigma, ex = exp(-x);
+  if (a.kind == KREG_KERNEL_MATERN && a.nn >= 1) {
+    const double y = 2.0 * x;
+    double p = a.mat_c[a.nn], d = a.mat_d[a.nn - 1];
+    for (int m = a.nn - 1; m >= 0; m--) p = fma(p, y, a.mat_c[m]);
+    for (int m = a.nn - 2; m >= 0; m--) d = fma(d, y, a.mat_d[m]);
+    k = ex * p;
+    phi = ex * d;
+    return;
+  }
+  k = ex;
+  phi = r > 0.0 ? ex * a.inv_sigma / r : 0.0;
+}
+
+__device__ __forceinline__ void wr_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
+                                                 const double *bA, int wi, int wj, int g, int q) {
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const int ri = wi * 32 + mt * 8 + g;
+    const int64_t i = i0 + ri;
+    const bool row_ok = i < a.na;
+    const double bi = bA[ri];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
+      if (!row_ok || j >= a.nb) continue;
+      double k0, k1, p0, p1;
+      radial_pair_values(a, S[mt][nt][0] + bi, k0, p0);
+      radial_pair_values(a, S[mt][nt][1] + bi, k1, p1);
+      const bool has1 = j + 1 < a.nb;
+      const double c0 = __ldg(a.colscale + j), c1 = has1 ? __ldg(a.colscale + j + 1) : 0.0;  // padding column: exact zeros
+      const int64_t ch = j / a.wkc;
+      const int64_t off = (ch * a.na + i) * a.wkc + (j - ch * a.wkc);
+      KREG_CHECK(off >= 0 && off + 1 < (int64_t)((a.nb + a.wkc - 1) / a.wkc) * a.na * a.wkc && (off & 1) == 0, 3);
+      *reinterpret_cast<double2 *>(a.Wch + off) = make_double2(p0 * c0, has1 ? p1 * c1 : 0.0);
+      *reinterpret_cast<double2 *>(a.Kfch + off) = make_double2(k0 * c0, has1 ? k1 * c1 : 0.0);
+    }
+  }
+}
+
 // Plain GEMM epilogue: C[i][j] = accumulator (A_i . B_j + column term), row-major.
 __device__ __forceinline__ void lin_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
                                                   int wi, int wj, int g, int q) {
@@ -334,6 +387,8 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
       lin_tile_epilogue(a, S, i0, j0, wi, wj, g, q);
     else if (EPI == EPI_KR)
       radial_tile_epilogue(a, S, i0, j0, bA, wi, wj, g, q);
+    else if (EPI == EPI_WR)
+      wr_tile_epilogue(a, S, i0, j0, bA, wi, wj, g, q);
     else
       w_tile_epilogue<EPI>(a, S, i0, j0, bA, tab, wi, wj, g, q);
   };
@@ -425,6 +480,7 @@ static int launch_values_kc(ValuesArgs a, cudaStream_t st) {
   constexpr int XSP = KC * 4 + ((KC * 4) % 8 == 4 ? 0 : 4);
   const bool multi = a.nchunks > 1 || EPI != EPI_K;  // the GEMM modes always stream chunk-major operands
   if (multi ? (a.XSC != XSP || !a.XAch || !a.XBch) : (a.XS != XSP)) return KREG_E_BADARG;  // workspace layout contract
+  if (!a.biasA || !a.biasB) return KREG_E_BADARG;  // both are staged by bulk copies in every mode (EPI_LIN ignores the row terms)
   const int64_t r1 = a.row_end < a.na ? a.row_end : a.na;
   if (r1 <= a.row_begin) return KREG_OK;
   const int64_t ti0 = a.row_begin / kTileI, ti1 = (r1 - 1) / kTileI;
@@ -464,6 +520,8 @@ int launch_gemm_epi(const ValuesArgs &a, int epi, cudaStream_t st) {
       return launch_values_kc<kGemmKC, EPI_LIN>(a, st);
     case EPI_KR:
       return launch_values_kc<kGemmKC, EPI_KR>(a, st);
+    case EPI_WR:
+      return launch_values_kc<kGemmKC, EPI_WR>(a, st);
     case EPI_K:
       return launch_values_kc<kGemmKC, EPI_K>(a, st);
     default:
@@ -1351,6 +1409,42 @@ __global__ void __launch_bounds__(256) laplacian_block_kernel(int D, int64_t na,
   }
 }
 
+// Matern kernel of order nn as polynomials in y = 2 r / sigma times exp(-r / sigma):
+//   k   = sum_m mat_c[m] y^m, m = 0..nn     (Kfunk, A_KRR_kernel.f90:837-849; MLatomF's summation index kk = nn - m)
+//   phi = sum_m mat_d[m] y^m, m = 0..nn-1   (dKdXid, :1205-1219 = mod_MaternConsts(:,1), :966-977; kk = nn - 1 - m)
+void set_matern_coefficients(ValuesArgs &a, int nn, double sigma) {
+  auto fact = [](int n) {
+    double f = 1.0;
+    for (int i = 1; i <= n; i++) f *= i;
+    return f;
+  };
+  for (int m = 0; m < 12; m++) a.mat_c[m] = a.mat_d[m] = 0.0;
+  for (int m = 0; m <= nn; m++) {
+    const int kk = nn - m;
+    a.mat_c[m] = fact(nn) / fact(2 * nn) * (fact(nn + kk) / fact(kk) / fact(nn - kk));
+  }
+  for (int m = 0; m < nn; m++) {
+    const int kk = nn - 1 - m;
+    a.mat_d[m] = fact(nn) / fact(2 * nn) / (sigma * sigma) * 2.0 * (fact(nn + kk - 1) / fact(kk) / fact(nn - kk) * (nn - kk));
+  }
+}
+
+// E[i] = prior + sum_j K[i][j] alpha[j] (Yest_KRR, A_KRR_kernel.f90:225-245, from a materialised kernel block): one warp
+// per row, lanes stride the row, fixed-order shuffle tree -- run-to-run deterministic.
+__global__ void __launch_bounds__(256) block_dot_kernel(int64_t na, int64_t nb, const double *__restrict__ K, int64_t ldk,
+                                                        const double *__restrict__ alpha, double prior,
+                                                        double *__restrict__ E) {
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= na) return;
+  const int lane = threadIdx.x & 31;
+  const double *row = K + i * ldk;
+  double s = 0.0;
+  for (int64_t j = lane; j < nb; j += 32) s = fma(row[j], alpha[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) E[i] = prior + s;
+}
+
 struct ExWs {
   int XS, nchD;
   size_t off_center, off_XA, off_XAch, off_bA, off_bAc, off_XB, off_XBch, off_bB, off_bBc, total;
@@ -1454,20 +1548,20 @@ extern "C" int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, co
   a.kind = kind;
   a.nn = nn;
   a.inv_sigma = 1.0 / sigma;
-  if (kind == KREG_KERNEL_MATERN) {
-    auto fact = [](int n) {
-      double f = 1.0;
-      for (int i = 1; i <= n; i++) f *= i;
-      return f;
-    };
-    for (int m = 0; m <= nn; m++) {
-      const int kk = nn - m;  // MLatomF's summation index (A_KRR_kernel.f90:839-844)
-      a.mat_c[m] = fact(nn) / fact(2 * nn) * (fact(nn + kk) / fact(kk) / fact(nn - kk));
-    }
-  }
+  if (kind == KREG_KERNEL_MATERN) set_matern_coefficients(a, nn, sigma);
   rc = launch_gemm_epi(a, EPI_KR, st);
   if (rc || !symmetric) return rc;
   return launch_set_diagonal(na, Kout, ldk, 1.0 + lambda, st);
+}
+
+extern "C" int kreg_block_dot(int64_t na, int64_t nb, const double *K, int64_t ldk, const double *alpha, double prior,
+                              double *E, void *stream) {
+  if (na < 0 || nb < 0 || ldk < nb) return KREG_E_BADARG;
+  if (na == 0) return KREG_OK;
+  if (!K || !alpha || !E) return KREG_E_BADARG;
+  block_dot_kernel<<<(unsigned)((na + 7) / 8), 256, 0, as_stream(stream)>>>(na, nb, K, ldk, alpha, prior, E);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
 }
 
 extern "C" size_t kreg_build_workspace_bytes_rows(int natoms, int64_t ntrain, int64_t ntrgr, int64_t row_begin,

@@ -338,3 +338,53 @@ extern "C" int kreg_predict(int natoms, int64_t ntrain, const void *packed, cons
   return launch_predict(natoms, a, has_gradient_terms != 0, sms, workspace, workspace_bytes, false, &need,
                         as_stream(stream));
 }
+
+// ---- models on MLatomF's other radial kernel functions (values-trained) --------------------------------------------------
+extern "C" size_t kreg_radial_packed_model_bytes(int natoms, int64_t ntrain) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0) return 0;
+  return big_packed_model_bytes(natoms, ntrain, false);
+}
+
+extern "C" int kreg_pack_model_radial(int natoms, int64_t ntrain, const double *xyz_train, const double *xeq,
+                                      const double *alpha_val, double *center, void *packed, size_t packed_bytes,
+                                      void *stream) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  if (ntrain <= 0 || !xyz_train || !xeq || !alpha_val || !center || !packed) return KREG_E_BADARG;
+  if (packed_bytes < big_packed_model_bytes(natoms, ntrain, false)) return KREG_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(packed) & 255) != 0) return KREG_E_BADARG;
+  cudaStream_t st = as_stream(stream);
+  int rc = launch_descriptor_mean(natoms, ntrain, xyz_train, xeq, center, st);
+  if (rc) return rc;
+  // the kernel width does not enter the packed arrays (centred rows, -n_j/2, alpha_j, transposed rows)
+  return big_pack_model(natoms, ntrain, xyz_train, nullptr, xeq, alpha_val, nullptr, 1.0, center, packed, packed_bytes, st);
+}
+
+extern "C" size_t kreg_predict_radial_workspace_bytes(int natoms, int64_t ntrain, int64_t npoints) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0 || npoints <= 0) return 0;
+  int sms = 0;
+  if (device_sm_count(&sms) != KREG_OK) return 0;
+  return big_predict_radial_workspace_bytes(natoms, ntrain, npoints, sms);
+}
+
+extern "C" int kreg_predict_radial(int kind, int nn, int natoms, int64_t ntrain, const void *packed, const double *center,
+                                   const double *xeq, double sigma, double prior, int64_t npoints, const double *xyz,
+                                   int flags, double *E, double *G, void *workspace, size_t workspace_bytes, void *stream) {
+  if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
+  if (kind != KREG_KERNEL_GAUSSIAN && kind != KREG_KERNEL_EXPONENTIAL && kind != KREG_KERNEL_MATERN)
+    return KREG_E_UNSUPPORTED;  // the Laplacian's L1 distance has no GEMM form: kreg_kernel_block_ex + kreg_block_dot
+  if (kind == KREG_KERNEL_MATERN && (nn < 0 || nn > 10)) return KREG_E_UNSUPPORTED;
+  if (ntrain <= 0 || npoints < 0 || !packed || !center || !xeq || !(sigma > 0.0)) return KREG_E_BADARG;
+  if (!(flags & (KREG_PREDICT_ENERGY | KREG_PREDICT_GRADIENT))) return KREG_E_BADARG;
+  if (npoints == 0) return KREG_OK;
+  if (!xyz) return KREG_E_BADARG;
+  if ((flags & KREG_PREDICT_ENERGY) && !E) return KREG_E_BADARG;
+  if ((flags & KREG_PREDICT_GRADIENT) && !G) return KREG_E_BADARG;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  // Matern of order 0 is the exponential kernel (Kfunk :837-849 with nn = 0); the reference differentiates it numerically
+  if (kind == KREG_KERNEL_MATERN && nn == 0) kind = KREG_KERNEL_EXPONENTIAL;
+  return big_predict_radial(kind, nn, natoms, ntrain, packed, center, xeq, sigma, prior, npoints, xyz,
+                            (flags & KREG_PREDICT_ENERGY) ? E : nullptr, (flags & KREG_PREDICT_GRADIENT) ? G : nullptr,
+                            workspace, workspace_bytes, sms, as_stream(stream));
+}

@@ -56,17 +56,17 @@ struct BigWs {  // byte offsets inside the per-call scratch, sized for tiles of 
   int64_t TN;
   int NPAD;
   int64_t ldc;
-  size_t off_Xc, off_Xch, off_bias, off_zero, off_C2, off_W, off_acc, total;
+  size_t off_Xc, off_Xch, off_bias, off_bias2, off_zero, off_C2, off_W, off_acc, off_accE, total;
 };
 
-static BigWs big_ws(const BigModel &m, int64_t ntr, bool has_v, int64_t npoints, int sms) {
+static BigWs big_ws(const BigModel &m, int64_t ntr, bool has_v, int64_t npoints, int sms, bool radial = false) {
   BigWs w;
   // GEMM2 runs (TN / 128) x ceil((D + 1) / 64) CTA tiles, two per SM: take whole waves of them, as many as keep the
   // chunk-major W (and K) under ~1.5 GB; small batches take what they need
   const int64_t ncol = (m.nbT + 63) / 64;
   int64_t row_tiles = (2 * (int64_t)sms) / ncol;
   if (row_tiles < 1) row_tiles = 1;
-  const size_t w_row_bytes = (size_t)m.nchW * kCW * sizeof(double) * (has_v ? 3 : 1);  // W (+ K + C2) per test row
+  const size_t w_row_bytes = (size_t)m.nchW * kCW * sizeof(double) * (has_v ? 3 : radial ? 2 : 1);  // W (+ K + C2) per test row
   int64_t waves = (int64_t)((size_t)1536 << 20) / (int64_t)(w_row_bytes * 128 * row_tiles);
   if (waves < 1) {
     waves = 1;
@@ -90,10 +90,12 @@ static BigWs big_ws(const BigModel &m, int64_t ntr, bool has_v, int64_t npoints,
   w.off_Xc = take((size_t)TN * m.XS);
   w.off_Xch = take((size_t)m.nchD * TN * kCW);
   w.off_bias = take((size_t)TN + 2);
+  w.off_bias2 = radial ? take((size_t)TN + 2) : off;
   w.off_zero = take((size_t)m.nbT + 66);
   w.off_C2 = has_v ? take((size_t)TN * w.ldc) : off;
-  w.off_W = take((size_t)m.nchW * (has_v ? 2 : 1) * TN * kCW);
+  w.off_W = take((size_t)m.nchW * ((has_v || radial) ? 2 : 1) * TN * kCW);
   w.off_acc = take((size_t)TN * w.NPAD);
+  w.off_accE = radial ? take((size_t)TN * 2) : off;
   w.total = off;
   return w;
 }
@@ -156,14 +158,17 @@ __global__ void __launch_bounds__(256) big_epilogue_kernel(int nat, int64_t n, c
                                                            const double *__restrict__ Xc, int XS,
                                                            const double *__restrict__ acc, int ldacc, int ecol,
                                                            double inv_s2, double prior, double *__restrict__ E,
-                                                           double *__restrict__ G) {
+                                                           double *__restrict__ G,
+                                                           const double *__restrict__ accE = nullptr, int ldaccE = 0) {
   const int lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (p >= n) return;
   const double *y = acc + p * ldacc;
-  const double esum = y[ecol];
-  if (lane == 0 && E) E[p] = prior + esum;
+  // Gaussian: the weights of the energy and of the gradient are the same numbers (w = alpha k); the radial kernels carry
+  // the energy sums in an array of their own (accE) and the sum of the gradient weights in column `ecol`
+  if (lane == 0 && E) E[p] = prior + (accE ? accE[p * ldaccE] : y[ecol]);
   if (!G) return;
+  const double esum = y[ecol];
   const double *m = xyz + p * nat * 3;
   const double *xc = Xc + p * XS;
   for (int a = lane; a < nat; a += 32) {
@@ -242,6 +247,115 @@ int big_pack_model(int nat, int64_t ntr, const double *xyz_train, const double *
 
 size_t big_predict_workspace_bytes(int nat, int64_t ntr, bool has_v, int64_t npoints, int sms) {
   return big_ws(big_model(nat, ntr, has_v), ntr, has_v, npoints, sms).total;
+}
+
+size_t big_predict_radial_workspace_bytes(int nat, int64_t ntr, int64_t npoints, int sms) {
+  return big_ws(big_model(nat, ntr, false), ntr, false, npoints, sms, true).total;
+}
+
+// Prediction with MLatomF's radial kernel functions (Gaussian / exponential / Matern; Kfunk A_KRR_kernel.f90:806-851, first
+// derivatives dKdXid :1178-1233 inside dKdMiat_unpermuted :1407-1447) for a values-trained model, any molecule size, on
+// the same three-kernel skeleton:
+//   GEMM1   S = X'te . X'tr^T - n_j/2, epilogue (EPI_WR): r_ij from S, then w_ij = alpha_j phi(r_ij) and e_ij = alpha_j k(r_ij)
+//   GEMM2   A = W . [X'tr | 1]   (gradient weights; skipped for energies only)      GEMM2'  e = E . 1
+//   epilogue per geometry: E = prior + e, g = A[:D] - X'_i A[D], dE/dM = J_i^T g
+// The packed model is the values-only layout of big_pack_model (sigma does not enter it).
+int big_predict_radial(int kind, int nn, int nat, int64_t ntr, const void *packed, const double *center, const double *xeq,
+                       double sigma, double prior, int64_t npoints, const double *xyz, double *E, double *G,
+                       void *workspace, size_t workspace_bytes, int sms, cudaStream_t st) {
+  const BigModel m = big_model(nat, ntr, false);
+  const BigWs w = big_ws(m, ntr, false, npoints, sms, true);
+  if (!workspace || workspace_bytes < w.total) return KREG_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || (reinterpret_cast<uintptr_t>(packed) & 255) != 0)
+    return KREG_E_BADARG;
+  const char *mb = static_cast<const char *>(packed);
+  const double *Xch = reinterpret_cast<const double *>(mb + m.off_Xch);
+  const double *bcol = reinterpret_cast<const double *>(mb + m.off_bcol);
+  const double *scale = reinterpret_cast<const double *>(mb + m.off_scale);
+  const double *XT = reinterpret_cast<const double *>(mb + m.off_XT);
+  char *wb = static_cast<char *>(workspace);
+  double *XcA = reinterpret_cast<double *>(wb + w.off_Xc), *XAch = reinterpret_cast<double *>(wb + w.off_Xch);
+  double *biasS = reinterpret_cast<double *>(wb + w.off_bias), *biasU = reinterpret_cast<double *>(wb + w.off_bias2);
+  double *zeros = reinterpret_cast<double *>(wb + w.off_zero), *Wch = reinterpret_cast<double *>(wb + w.off_W);
+  double *acc = reinterpret_cast<double *>(wb + w.off_acc), *accE = reinterpret_cast<double *>(wb + w.off_accE);
+  KREG_CUDA_TRY(cudaMemsetAsync(zeros, 0, (size_t)(m.nbT + 66) * sizeof(double), st));
+  const bool want_g = G != nullptr;
+
+  for (int64_t n0 = 0; n0 < npoints; n0 += w.TN) {
+    const int64_t tn = npoints - n0 < w.TN ? npoints - n0 : w.TN;
+    const double *x = xyz + n0 * nat * 3;
+    // the radial epilogue wants the UNSCALED row term -n_i/2 (biasU); the scaled one (biasS) is a by-product
+    int rc = launch_prep_rows(nat, tn, x, xeq, center, m.XS, 1.0, XcA, biasS, biasU, st);
+    if (rc) return rc;
+    rc = launch_chunk_rows(tn, m.XS, kGemmKC, m.nchD, kCW, XcA, XAch, st);
+    if (rc) return rc;
+    ValuesArgs a = {};
+    a.XSC = kCW;
+    a.XS = m.XS;
+    a.all_cols = 1;
+    a.row_begin = 0;
+    a.row_end = tn;
+    a.na = tn;
+    a.strideA = tn;
+    a.wkc = kCW;
+    a.biasA = biasU;  // every mode of the tile kernel stages the row terms (the plain-GEMM mode does not use them)
+    double *Efch = Wch + (size_t)m.nchW * tn * kCW;
+    KREG_CUDA_TRY(cudaMemsetAsync(Wch + (size_t)(m.nchW - 1) * tn * kCW, 0, (size_t)tn * kCW * sizeof(double), st));
+    KREG_CUDA_TRY(cudaMemsetAsync(Efch + (size_t)(m.nchW - 1) * tn * kCW, 0, (size_t)tn * kCW * sizeof(double), st));
+    {
+      ValuesArgs g1 = a;
+      g1.XAch = XAch;
+      g1.XBch = Xch;
+      g1.nb = ntr;
+      g1.strideB = ntr;
+      g1.nchunks = m.nchD;
+      g1.biasB = bcol;
+      g1.colscale = scale;
+      g1.Wch = Wch;
+      g1.Kfch = Efch;
+      g1.kind = kind;
+      g1.nn = nn;
+      g1.inv_sigma = 1.0 / sigma;
+      g1.inv_s2 = 1.0 / (sigma * sigma);
+      if (kind == KREG_KERNEL_MATERN) set_matern_coefficients(g1, nn, sigma);
+      rc = launch_gemm_epi(g1, EPI_WR, st);
+      if (rc) return rc;
+    }
+    if (want_g) {
+      ValuesArgs g2 = a;
+      g2.XAch = Wch;
+      g2.XBch = XT;
+      g2.nb = m.nbT;
+      g2.strideB = m.nbT;
+      g2.nchunks = m.nchW;
+      g2.biasB = zeros;
+      g2.K = acc;
+      g2.ldk = w.NPAD;
+      g2.njt = 1;
+      rc = launch_gemm_epi(g2, EPI_LIN, st);
+      if (rc) return rc;
+    }
+    {
+      ValuesArgs g3 = a;  // energies: the ones row of the B operand alone (one column tile)
+      g3.XAch = Efch;
+      g3.XBch = XT + (size_t)m.D * kCW;
+      g3.nb = 1;
+      g3.strideB = m.nbT;
+      g3.nchunks = m.nchW;
+      g3.biasB = zeros;
+      g3.K = accE;
+      g3.ldk = 2;
+      g3.njt = 1;
+      rc = launch_gemm_epi(g3, EPI_LIN, st);
+      if (rc) return rc;
+    }
+    big_epilogue_kernel<<<(unsigned)((tn + 7) / 8), 256, 0, st>>>(nat, tn, x, xeq, XcA, m.XS, want_g ? acc : accE,
+                                                                  want_g ? w.NPAD : 2, want_g ? m.D : 0, 1.0, prior,
+                                                                  E ? E + n0 : nullptr, G ? G + n0 * nat * 3 : nullptr,
+                                                                  accE, 2);
+    KREG_LAUNCH_CHECK();
+  }
+  return KREG_OK;
 }
 
 int big_predict(int nat, int64_t ntr, const void *packed, const double *center, const double *xeq, double sigma,

@@ -81,11 +81,15 @@ class kreg:
                     self.kreg_api.load_unf(self.model_file)
                 else:
                     with np.load(self.model_file) as header:
-                        permuted = "pmap" in header.files
+                        permuted, other = "pmap" in header.files, "kernel" in header.files
                     if permuted:  # a permutationally invariant model (perminv.PermInvKREG.save_model)
                         from .perminv import PermInvKREG
 
                         self.kreg_api = PermInvKREG(device=device)
+                    elif other:   # a model on another kernel function (kernels.RadialKREG.save_model)
+                        from .kernels import RadialKREG
+
+                        self.kreg_api = RadialKREG(device=device)
                     self.kreg_api.load_model(self.model_file)
         self.hyperparameters = type(self).hyperparameters.copy()
         self.hyperparameters.update(hyperparameters)
@@ -200,6 +204,21 @@ class kreg:
             prior = self.hyperparameters["prior"].value
         return lam, lam_g, prior
 
+    def _other_kernel(self):
+        """(kernel, nn) of an MLatomF ``kernel=`` request other than Gaussian in ``additional_mlatomf_args`` (else None)."""
+        kernel, nn = None, 2  # MLatomF's default order of the Matern kernel (optionsModule.f90:105)
+        for a in [str(a) for a in self.__dict__.get("additional_mlatomf_args", None) or []]:
+            key, _, val = a.partition("=")
+            if key.casefold() == "kernel":
+                kernel = val
+            elif key.casefold() == "nn":
+                nn = int(val)
+        if kernel is None or kernel.casefold() == "gaussian":
+            return None
+        if kernel.casefold() not in ("exponential", "matern", "laplacian"):
+            raise NotImplementedError(f"kernel={kernel} is not built (Gaussian, exponential, Matern, Laplacian are)")
+        return kernel, nn
+
     def _perm_inv_groups(self):
         """Atom groups of MLatomF's ``permInvKernel`` request in ``additional_mlatomf_args`` (None: not requested)."""
         args = [str(a) for a in self.__dict__.get("additional_mlatomf_args", None) or []]
@@ -225,7 +244,18 @@ class kreg:
             elif not self._unf and self.model_file[-4:] != ".npz":
                 self.model_file += ".npz"
         groups = self._perm_inv_groups()
-        if groups is not None:
+        other = self._other_kernel()
+        if other is not None:
+            # MLatomF's other kernel functions (additional_mlatomf_args=['kernel=Matern', 'nn=2'], models.py:494-495)
+            from .kernels import RadialKREG
+
+            if groups is not None:
+                raise NotImplementedError("permInvKernel is built for the Gaussian kernel only")
+            self.kreg_api = RadialKREG(kernel=other[0], nn=other[1], device=self.device)
+            if save_model and self.model_file[-4:] != ".npz":
+                self.model_file += ".npz"
+            groups = ()  # not a .unf model either
+        elif groups is not None:
             # MLatomF's permutationally invariant kernel (additional_mlatomf_args=['permInvKernel', 'permInvNuclei=..',
             # 'molDescrType=permuted'], models.py:494-495): same device path with the expanded training set, .npz model file
             from .perminv import PermInvKREG
@@ -391,7 +421,10 @@ class kreg:
             self.model_file = os.path.join(tmp, os.path.basename(saved_name or "kreg_tmp.npz"))
             if algo in ("grid", "brute"):
                 slices = self._grid(names, optimization_algorithm_kwargs.get("grid_size", 9))
-                can_fuse = (fused and set(names) <= {"lambda", "sigma"} and validation_loss_function is None
+                # the fused path assembles the plain Gaussian KREG kernel: models on another kernel function or on the
+                # permutationally invariant kernel take the pointwise route (train + predict per grid point)
+                gaussian_kreg = self._other_kernel() is None and self._perm_inv_groups() is None
+                can_fuse = (fused and gaussian_kreg and set(names) <= {"lambda", "sigma"} and validation_loss_function is None
                             and cv_splits_molecular_databases is None and not any(v for v in unsupported.values()))
                 if can_fuse:
                     table = self._fused_grid_losses(names, slices, training_kwargs, prediction_kwargs,
@@ -405,6 +438,8 @@ class kreg:
                 # Python class, available here because the fused path makes it cheap
                 if not set(names) <= {"lambda", "sigma"}:
                     raise NotImplementedError("log2grid optimises 'sigma' and/or 'lambda'")
+                if self._other_kernel() is not None or self._perm_inv_groups() is not None:
+                    raise NotImplementedError("log2grid runs on the fused Gaussian KREG path only; use 'grid'")
                 best, _, self.grid_trace = self._log2_grid_search(names, optimization_algorithm_kwargs, training_kwargs,
                                                                   prediction_kwargs, subtraining_molecular_database,
                                                                   validation_molecular_database)

@@ -573,6 +573,83 @@ void kro_kernel_block_generic(int kind, int nn, int D, long na, const double *Xa
     for (long j = 0; j < nb; j++) K[i * nb + j] = mlatomf_kfunk(kind, nn, D, Xa + i * D, Xb + j * D, sigma);
 }
 
+/* dKdXid (A_KRR_kernel.f90:1178-1233): Gaussian and Matern (nn > 0) analytic, everything else a central difference of
+ * Kfunk with h = sqrt(epsilon) * Xi(dd). */
+static double mlatomf_dKdXid(int kind, int nn, int D, const double *Xi, const double *Xj, int dd, double sigma) {
+  if (kind == 0) return mlatomf_kfunk(0, nn, D, Xi, Xj, sigma) * (Xj[dd] - Xi[dd]) / (sigma * sigma);
+  if (kind == 2 && nn > 0) {
+    const double dist = mlatomf_distance(kind, D, Xi, Xj);
+    double v = 0.0;
+    for (int kk = 0; kk <= nn - 1; kk++)
+      v = v + factorial_rprec(nn + kk - 1) / factorial_rprec(kk) / factorial_rprec(nn - kk) * (nn - kk) *
+                  pow(2.0 * dist / sigma, nn - kk - 1) * (Xj[dd] - Xi[dd]);
+    return v * exp(-1.0 * dist / sigma) * factorial_rprec(nn) / factorial_rprec(2 * nn) / (sigma * sigma) * 2.0;
+  }
+  const double eps = 2.220446049250313e-16; /* epsilon(Xi(dd)) */
+  double h = sqrt(eps);
+  if (fabs(Xi[dd]) > 0.0 + 2.0 * eps) h = h * Xi[dd];
+  double *Xph = (double *)malloc(sizeof(double) * 2 * D), *Xmh = Xph + D;
+  memcpy(Xph, Xi, sizeof(double) * D);
+  memcpy(Xmh, Xi, sizeof(double) * D);
+  Xph[dd] = Xph[dd] + h;
+  Xmh[dd] = Xmh[dd] - h;
+  const double fxph = mlatomf_kfunk(kind, nn, D, Xph, Xj, sigma), fxmh = mlatomf_kfunk(kind, nn, D, Xmh, Xj, sigma);
+  free(Xph);
+  return (fxph - fxmh) / (2.0 * h);
+}
+
+/* dKdMiat_unpermuted, RE branch (A_KRR_kernel.f90:1407-1447) with dKdXid_changing / _const2 / _const1 (:1235-1301) */
+static double mlatomf_dKdMiat(int kind, int nn, int nat, int D, const double *Xi, const double *Xj, const double *xyzi,
+                              int a, int tt, double sigma) {
+  const int analytic = (kind == 0) || (kind == 2 && nn > 0);
+  double v = 0.0;
+  for (int bb = 0; bb < nat; bb++) {
+    if (a != bb) {
+      const int dd = pair_index(nat, a, bb);
+      const double changing = analytic ? Xj[dd] - Xi[dd] : mlatomf_dKdXid(kind, nn, D, Xi, Xj, dd, sigma);
+      const double R = rij(xyzi + 3 * a, xyzi + 3 * bb);
+      v = v + changing * Xi[dd] * (xyzi[3 * bb + tt] - xyzi[3 * a + tt]) / (R * R);
+    }
+  }
+  double const2 = 1.0, const1 = 1.0;
+  if (kind == 0) {
+    const2 = mlatomf_kfunk(0, nn, D, Xi, Xj, sigma);
+    const1 = 1.0 / (sigma * sigma);
+  } else if (kind == 2 && nn > 0) {
+    const double dist = mlatomf_distance(kind, D, Xi, Xj);
+    const double cst = factorial_rprec(nn) / factorial_rprec(2 * nn) / (sigma * sigma) * 2.0; /* mod_MaternConsts(:,1), :966-977 */
+    const2 = 0.0;
+    for (int kk = 0; kk <= nn - 1; kk++)
+      const2 = const2 + factorial_rprec(nn + kk - 1) / factorial_rprec(kk) / factorial_rprec(nn - kk) * (nn - kk) *
+                            pow(2.0 / sigma, nn - kk - 1) * cst * pow(dist, nn - kk - 1);
+    const2 = const2 * exp(-1.0 * dist / sigma);
+  }
+  return v * const2 * const1;
+}
+
+/* Yest_KRR (A_KRR_kernel.f90:225-245) and the generic branch of YgradXYZest_KRR (:731-744) for a values-trained model on
+ * any of the kernel functions; prior added as calcEst_KRR does (A_KRR.f90:1006). */
+void kro_predict_generic(int kind, int nn, int nat, long ntr, const double *X_tr, const double *alpha, double sigma,
+                         double prior, long np, const double *xyz_te, const double *X_te, int calc_grad, double *E,
+                         double *G) {
+  const int D = nat * (nat - 1) / 2;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < np; i++) {
+    const double *Xi = X_te + i * D, *xyzi = xyz_te + (size_t)i * nat * 3;
+    double y = 0.0;
+    for (long jj = 0; jj < ntr; jj++) y = y + alpha[jj] * mlatomf_kfunk(kind, nn, D, Xi, X_tr + jj * D, sigma);
+    E[i] = y + prior;
+    if (!calc_grad) continue;
+    for (int a = 0; a < nat; a++)
+      for (int tt = 0; tt < 3; tt++) {
+        double g = 0.0;
+        for (long jj = 0; jj < ntr; jj++)
+          g = g + alpha[jj] * mlatomf_dKdMiat(kind, nn, nat, D, Xi, X_tr + jj * D, xyzi, a, tt, sigma);
+        G[((size_t)i * nat + a) * 3 + tt] = g;
+      }
+  }
+}
+
 /* ---- permutationally invariant kernel on the permuted RE descriptor ------------------------
  * MLatomF with molDescrType=permuted permInvKernel: the descriptor of a geometry is the concatenation of the RE
  * descriptors of its Nperm atom-permuted copies (calcX, molDescr.f90:128-160; permuteAtoms :197-220: permutedXYZ(:,ii) =

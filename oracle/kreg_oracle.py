@@ -248,3 +248,16 @@ def perm_predict(x_tr, alpha, sigma, prior, xyz_te, x_te, pmap, calc_grad=True):
                             _d(x_tr), _d(a), c_double(sigma), c_double(prior), c_long(npred), _d(xyz_te), _d(x_te),
                             c_int(1 if calc_grad else 0), _d(e), _d(g))
     return e, (g if calc_grad else None)
+
+
+def predict_generic(kind: str, x_tr, alpha, sigma, prior, xyz_te, x_te, nn: int = 2, calc_grad=True):
+    """Values-trained model on any of MLatomF's kernel functions: Yest_KRR (A_KRR_kernel.f90:225-245) and the generic
+    branch of YgradXYZest_KRR (:731-744 -> dKdMiat_unpermuted :1407-1447 -> dKdXid :1178-1233; exponential and Laplacian
+    derivatives by central differences, as the reference does).  Parity unpinned (no executable MLatomF here)."""
+    x_tr, x_te, xyz_te, a = _c(x_tr), _c(x_te), _c(xyz_te), _c(alpha).reshape(-1)
+    npred, nat, _ = xyz_te.shape
+    e, g = np.zeros(npred), np.zeros((npred, nat, 3))
+    load().kro_predict_generic(c_int(KERNEL_KINDS[kind.lower()]), c_int(nn), c_int(nat), c_long(x_tr.shape[0]), _d(x_tr),
+                               _d(a), c_double(sigma), c_double(prior), c_long(npred), _d(xyz_te), _d(x_te),
+                               c_int(1 if calc_grad else 0), _d(e), _d(g))
+    return e, (g if calc_grad else None)

@@ -69,3 +69,115 @@ def test_values_trained_model_on_each_kernel(eng, oracle, kind, nn):
     cond = np.linalg.cond(ref + lam * np.eye(ntr))
     assert np.abs(e - e_ref).max() <= max(1e-10, 50 * cond * np.finfo(float).eps) * np.abs(e_ref).max()
     assert np.sqrt(np.mean((e - ete) ** 2)) < np.std(ete)  # and the model has learned something
+
+
+# ---- prediction (energies AND gradients) with these kernels: kreg_pack_model_radial / kreg_predict_radial ----------------
+# Matern of order >= 1 and Gaussian are analytic in the reference (dKdXid, A_KRR_kernel.f90:1202-1219): 1e-10 / 1e-8.
+# The exponential kernel is differentiated NUMERICALLY there (central difference of Kfunk, h = sqrt(eps) X_d, :1222-1230),
+# analytically here: the two agree to the truncation + rounding error of that difference, ~1e-7 relative.
+PRED_CASES = [("gaussian", 0, 1.3, 1e-8), ("matern", 1, 2.0, 1e-8), ("matern", 2, 1.1, 1e-8), ("matern", 5, 0.9, 1e-8),
+              ("exponential", 0, 1.5, 2e-6), ("matern", 0, 1.5, 2e-6)]
+
+
+@pytest.mark.parametrize("nat,ntr,nte", [(9, 150, 333), (5, 64, 70), (21, 130, 65), (30, 37, 129), (2, 9, 9)])
+@pytest.mark.parametrize("kind,nn,sigma,gtol", PRED_CASES)
+def test_radial_prediction_with_fixed_alpha_vs_oracle(eng, oracle, nat, ntr, nte, kind, nn, sigma, gtol):
+    from mlatom_b200 import kernels
+
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
+    xeq = oracle.xeq(eq)
+    alpha = np.random.default_rng(4).standard_normal(ntr)
+    prior = -100.0
+    model = kernels.RadialModel(kind, nn, dev(xtr), dev(xeq), dev(alpha), sigma, prior)
+    e, g = model.predict(dev(xte))
+    e, g = e.cpu().numpy(), g.cpu().numpy()
+    okind = "exponential" if (kind == "matern" and nn == 0) else kind
+    e_ref, g_ref = oracle.predict_generic(okind, oracle.descriptors(xtr, xeq), alpha, sigma, prior, xte,
+                                          oracle.descriptors(xte, xeq), nn=nn)
+    assert np.abs(e - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
+    assert np.abs(g - g_ref).max() <= gtol * max(1.0, np.abs(g_ref).max()), float(np.abs(g - g_ref).max())
+    e2, g2 = model.predict(dev(xte), energy=True, gradient=False)
+    assert g2 is None and np.abs(e2.cpu().numpy() - e).max() <= 1e-12 * np.abs(e).max()
+    e3, g3 = model.predict(dev(xte), energy=False, gradient=True)
+    assert e3 is None and np.array_equal(g3.cpu().numpy(), g)
+
+
+def test_radial_gaussian_path_equals_the_fused_kernels(eng):
+    """The same Gaussian model through the radial three-kernel path and through kreg_predict: two formulations of the
+    same sums (table exp in registers against libm exp on r^2 from the GEMM)."""
+    from mlatom_b200 import kernels
+
+    nat, ntr, nte, sigma = 9, 2000, 5000, 1.0
+    eq = S.equilibrium(nat)
+    xtr, xte = dev(S.geometries(eq, ntr, 1)), dev(S.geometries(eq, nte, 2))
+    xeq = eng.xeq(dev(eq))
+    alpha = torch.randn(ntr, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    e1, g1 = eng.PackedModel.from_training_set(xtr, xeq, alpha, sigma, 0.0, ntr, 0).predict(xte)
+    e2, g2 = kernels.RadialModel("gaussian", 0, xtr, xeq, alpha, sigma, 0.0).predict(xte)
+    scale = float(alpha.abs().sum())
+    assert float((e1 - e2).abs().max()) <= 1e-13 * scale and float((g1 - g2).abs().max()) <= 1e-12 * scale
+
+
+def test_laplacian_model_predicts_energies_only(eng, oracle):
+    from mlatom_b200 import kernels
+
+    nat, ntr, nte, sigma = 9, 120, 77, 3.0
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
+    xeq = oracle.xeq(eq)
+    alpha = np.random.default_rng(6).standard_normal(ntr)
+    model = kernels.RadialModel("laplacian", 0, dev(xtr), dev(xeq), dev(alpha), sigma, 7.0)
+    e, g = model.predict(dev(xte), True, False)
+    e_ref, _ = oracle.predict_generic("laplacian", oracle.descriptors(xtr, xeq), alpha, sigma, 7.0, xte,
+                                      oracle.descriptors(xte, xeq), calc_grad=False)
+    assert g is None and np.abs(e.cpu().numpy() - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
+    with pytest.raises(NotImplementedError):
+        model.predict(dev(xte), True, True)
+
+
+def test_model_class_routes_kernel_arguments(eng, oracle, tmp_path):
+    """kreg(ml_program='MLatomF') + additional_mlatomf_args=['kernel=Matern', 'nn=3'] (mlatom/models.py:494-495): train,
+    predict into molecules, model-file round trip, grid search through the pointwise route; against LAPACK on the
+    oracle's matrix through predictions."""
+    from mlatom_b200 import data, models
+
+    nat, ntr, sigma, lam, nn = 9, 300, 2.0, 1e-8, 3
+    eq = S.equilibrium(nat)
+    z = S.atomic_numbers(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, 50, 2)
+    etr, _ = S.pair_potential(xtr, eq)
+    ete, gte = S.pair_potential(xte, eq)
+    m = models.kreg(model_file=str(tmp_path / "matern"), ml_program="MLatomF", equilibrium_molecule=data.molecule.from_arrays(z, eq),
+                    hyperparameters={"sigma": sigma, "lambda": lam})
+    m.additional_mlatomf_args = ["kernel=Matern", f"nn={nn}"]
+    m.train(molecular_database=data.molecular_database.from_arrays(z, xtr, energy=etr), property_to_learn="energy", prior="mean")
+    assert type(m.kreg_api).__name__ == "RadialKREG" and m.kreg_api.kernel == "Matern" and m.kreg_api.nn == nn
+    tdb = data.molecular_database.from_arrays(z, xte)
+    m.predict(molecular_database=tdb, calculate_energy=True, calculate_energy_gradients=True)
+    e = tdb.get_properties("energy")
+    g = tdb.get_xyz_vectorial_properties("energy_gradients")
+    from scipy.linalg import cho_factor, cho_solve
+
+    xeq = oracle.xeq(eq)
+    X, Xte = oracle.descriptors(xtr, xeq), oracle.descriptors(xte, xeq)
+    kref = oracle.kernel_block_generic("matern", X, X, sigma, nn=nn) + lam * np.eye(ntr)
+    prior = float(etr.mean())
+    a_ref = cho_solve(cho_factor(kref), etr - prior)
+    e_ref, g_ref = oracle.predict_generic("matern", X, a_ref, sigma, prior, xte, Xte, nn=nn)
+    bound = max(1e-10, 50 * np.linalg.cond(kref) * np.finfo(float).eps)
+    assert np.abs(e - e_ref).max() <= bound * np.abs(e_ref).max()
+    assert np.abs(g - g_ref).max() <= max(1e-8, bound * np.abs(a_ref).sum())
+    assert np.sqrt(np.mean((e - ete) ** 2)) < 0.5 * np.std(ete)
+    m2 = models.kreg(model_file=m.model_file, ml_program="MLatomF")
+    assert type(m2.kreg_api).__name__ == "RadialKREG" and m2.kreg_api.nn == nn
+    e2, g2 = m2.predict_xyz(xte)
+    assert np.array_equal(e2, e) and np.array_equal(g2, g)
+    # hyper-parameter grid on this kernel: the pointwise route (the fused path is the Gaussian kernel's)
+    sub = data.molecular_database.from_arrays(z, xtr[:240], energy=etr[:240])
+    val = data.molecular_database.from_arrays(z, xtr[240:], energy=etr[240:])
+    m.optimize_hyperparameters(hyperparameters=["sigma"], training_kwargs={"property_to_learn": "energy", "prior": "mean"},
+                               prediction_kwargs={"property_to_predict": "estimated_energy"},
+                               subtraining_molecular_database=sub, validation_molecular_database=val,
+                               optimization_algorithm="grid", optimization_algorithm_kwargs={"grid_size": 4})
+    assert np.isfinite(m.validation_loss) and 2 ** -5 <= m.hyperparameters["sigma"].value <= 2 ** 9

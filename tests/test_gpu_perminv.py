@@ -59,15 +59,17 @@ def test_descriptors_and_kernel_block_vs_oracle(pm, oracle, nat, spec, na, nb, s
     assert np.abs(ks - ks.T).max() <= 1e-15
 
 
-def test_kernel_block_in_row_slabs(pm, oracle):
-    """More rows than one 256 MB slab of S_ij^P terms holds (5 atoms, 24 permutations, 3000 x 3000)."""
-    nat, n, sigma = 5, 3000, 0.9
+@pytest.mark.parametrize("nat,spec,n", [(5, "2-3-4-5", 3000), (12, "10-11-12", 2600)])
+def test_kernel_block_in_row_slabs(pm, oracle, nat, spec, n):
+    """More rows than one 256 MB slab of S_ij^P terms holds: 5 atoms with 24 permutations (single-chunk descriptor) and
+    12 atoms with 6 (D = 66: two chunks, the chunk-major operand copies are addressed by row sub-range)."""
+    sigma = 0.9
     eq = S.equilibrium(nat)
-    pmap = pm.atom_maps(nat, pm.parse_perm_inv_nuclei("2-3-4-5"))
+    pmap = pm.atom_maps(nat, pm.parse_perm_inv_nuclei(spec))
     perms = pm.Permutations(pmap, torch.device("cuda"))
     x = S.geometries(eq, n, 8, 0.1)
     k = pm.kernel_block(dev(x), dev(x), dev(oracle.xeq(eq)), perms, sigma).cpu().numpy()
-    rows = np.r_[0:5, 1400:1405, n - 5:n]  # rows of the first, a middle and the last slab
+    rows = np.r_[0:5, n // 2:n // 2 + 5, n - 5:n]  # rows of the first, a middle and the last slab
     xp = oracle.perm_descriptors(x, eq, pmap)
     ref = oracle.perm_kernel_block(xp[rows], xp, perms.nperm, sigma)
     assert np.abs(k[rows] - ref).max() <= K_TOL

@@ -71,3 +71,29 @@ def test_oracle_kernel_is_invariant_on_a_symmetric_molecule(oracle):
     assert np.abs(k - ks).max() <= 1e-14
     kd = oracle.perm_kernel_block(oracle.perm_descriptors(xa, eq, pmap), oracle.perm_descriptors(xa, eq, pmap), 24, 0.9)
     assert np.abs(np.diag(kd) - 1.0).max() <= 4e-16 and np.abs(kd - kd.T).max() <= 1e-15
+
+
+@pytest.mark.parametrize("kind,nn,tol", [("gaussian", 0, 1e-8), ("matern", 1, 1e-8), ("matern", 3, 1e-8),
+                                         ("exponential", 0, 1e-6), ("laplacian", 0, 1e-6)])
+def test_oracle_generic_kernel_prediction_is_self_consistent(oracle, kind, nn, tol):
+    """The restated generic prediction path (Yest_KRR + YgradXYZest_KRR's generic branch with dKdMiat_unpermuted /
+    dKdXid, A_KRR_kernel.f90:731-744, 1407-1447, 1178-1233): its gradient against central differences of its own energy,
+    and for the Gaussian kernel against the KREG.so-pinned MLatomF path."""
+    nat, sigma = 9, 1.3
+    eq = S.equilibrium(nat)
+    xeq = oracle.xeq(eq)
+    xtr, xte = S.geometries(eq, 30, 1, 0.1), S.geometries(eq, 4, 2, 0.1)
+    xdtr, xdte = oracle.descriptors(xtr, xeq), oracle.descriptors(xte, xeq)
+    alpha = np.random.default_rng(0).standard_normal(30)
+    e, g = oracle.predict_generic(kind, xdtr, alpha, sigma, 0.5, xte, xdte, nn=nn)
+    if kind == "gaussian":
+        e1, g1 = oracle.predict_mlatomf(xtr, xdtr, alpha, sigma, 0.5, 30, 0, xte, xdte, True, True)
+        assert np.abs(e - e1).max() <= 1e-14 and np.abs(g - g1).max() <= 1e-13
+    h = 1e-5
+    for a, t in [(0, 0), (4, 1), (8, 2)]:
+        xp, xm = xte.copy(), xte.copy()
+        xp[:, a, t] += h
+        xm[:, a, t] -= h
+        ep, _ = oracle.predict_generic(kind, xdtr, alpha, sigma, 0.5, xp, oracle.descriptors(xp, xeq), nn=nn, calc_grad=False)
+        em, _ = oracle.predict_generic(kind, xdtr, alpha, sigma, 0.5, xm, oracle.descriptors(xm, xeq), nn=nn, calc_grad=False)
+        assert np.abs((ep - em) / (2 * h) - g[:, a, t]).max() <= tol

@@ -3,7 +3,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 export KREG_LIB=$PWD/mlatom_b200/libkreg_b200_dbg.so
-timeout 2400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_large_molecules.py tests/test_gpu_other_kernels.py tests/test_gpu_api.py -m gpu -q -p no:cacheprovider > gpurun_out/r02_debug_bounds_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_debug_bounds_tests.log
+timeout 2400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_large_molecules.py tests/test_gpu_other_kernels.py tests/test_gpu_api.py tests/test_gpu_perminv.py -m gpu -q -p no:cacheprovider > gpurun_out/r02_debug_bounds_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_debug_bounds_tests.log
 tail -5 gpurun_out/r02_debug_bounds_tests.log
 python - <<'PY' | tee gpurun_out/r02_debug_bounds.txt
 import ctypes, sys, os
