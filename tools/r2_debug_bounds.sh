@@ -28,6 +28,12 @@ for nat, ntr in ((9, 333), (5, 129), (12, 77), (21, 45), (26, 23), (40, 9)):
     model.predict(dev(S.geometries(eq, 301, 2)))
     for kind in ("exponential", "matern", "laplacian"):
         eng.kernel_block_ex(kind, xyz, dev(S.geometries(eq, 57, 3)), xeq, 1.1)
+    from mlatom_b200 import kernels, perminv
+    for kind in ("matern", "exponential"):
+        kernels.RadialModel(kind, 2, xyz, xeq, a[:ntr].contiguous(), 1.1, 0.0).predict(dev(S.geometries(eq, 301, 2)))
+    perms = perminv.Permutations(perminv.atom_maps(nat, [[0, 1], [2, 3, 4]] if nat >= 5 else [[0, 1]]), torch.device("cuda"))
+    perminv.kernel_block(xyz, dev(S.geometries(eq, 57, 3)), xeq, perms, 1.1)
+    perminv.PermInvModel(xyz, xeq, a[:ntr].contiguous(), 1.1, 0.0, perms).predict(dev(S.geometries(eq, 301, 2)))
 code, line = ctypes.c_int(0), ctypes.c_int(0)
 n = lib.kreg_debug_bounds_failures(ctypes.byref(code), ctypes.byref(line))
 print(f"kreg_debug_bounds_failures = {n} (first code {code.value}, line {line.value}); library = {_lib.LIB_PATH}")
