@@ -616,7 +616,7 @@ def run_ours(args):
     # would find it (the gradient-block kernels above 10 atoms are SM-bound and read 5-10 % lower after seconds of
     # full-power FP64 tensor work); clocks sampled over this region too ----
     kb_cfgs = None
-    if world == 1 and args.workload == "cfg2" and not args.no_extra:
+    if world == 1 and args.workload == "cfg2":
         hbm_peak0 = 6650.0
         try:
             hbm_peak0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

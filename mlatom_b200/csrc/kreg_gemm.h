@@ -67,6 +67,8 @@ int launch_prep_rows(int nat, int64_t n, const double *xyz, const double *xeq, c
 // the two bias arrays alone, for rows Xc that are already in place
 int launch_prep_bias(int nat, int64_t n, int XS, double c1, const double *Xc, double *bias, double *bias_col,
                      cudaStream_t st);
+// out[i * ldo] = sum of row i of a chunk-major array W[nch][n][wkc] (deterministic)
+int launch_chunk_rowsum(int64_t n, int nch, int wkc, const double *W, double *out, int ldo, cudaStream_t st);
 // chunk-major copy Xch[ch][p][XSC] = Xc[p][ch * 4 KC + (0 .. 4 KC)), zero padded
 int launch_chunk_rows(int64_t n, int XS, int KC, int nchunks, int XSC, const double *Xc, double *Xch, cudaStream_t st);
 

@@ -204,15 +204,39 @@ __device__ __forceinline__ void radial_tile_epilogue(const ValuesArgs &a, double
 // go out chunk-major, the A operands of the two second GEMMs.  kind: Gaussian (phi = k / s^2; exercises this path against
 // the fused kernels), exponential (phi = k / (sigma r), 0 at r = 0 like the reference's central difference of exp(-|x|)),
 // Matern of order nn >= 1 (the reference's analytic form, :1205-1219: a polynomial in r, regular at 0).
-__device__ __forceinline__ void radial_pair_values(const ValuesArgs &a, double s_plus_bi, double &k, double &phi) {
+// exp(-x) through the table exponential of the Gaussian kernels (11 FP64-pipe instructions against ~30 for libm's exp).
+template <int NN>
+__device__ __forceinline__ void matern_pair_values(const ValuesArgs &a, double x, double ex, double &k, double &phi) {
+  const double y = 2.0 * x;
+  double p = a.mat_c[NN], d = a.mat_d[NN - 1];
+#pragma unroll
+  for (int m = NN - 1; m >= 0; m--) p = fma(p, y, a.mat_c[m]);
+#pragma unroll
+  for (int m = NN - 2; m >= 0; m--) d = fma(d, y, a.mat_d[m]);
+  k = ex * p;
+  phi = ex * d;
+}
+
+__device__ __forceinline__ void radial_pair_values(const ValuesArgs &a, double s_plus_bi, const double *tab, double &k,
+                                                   double &phi) {
   const double r2 = fmax(-2.0 * s_plus_bi, 0.0);
   if (a.kind == KREG_KERNEL_GAUSSIAN) {
-    k = exp(-0.5 * r2 * a.inv_s2);
+    k = exp_from_scaled(-0.5 * kExpScale * a.inv_s2 * r2, tab);
     phi = k * a.inv_s2;
     return;
   }
-  const double r = sqrt(r2), x = r * a.inv_sigma, ex = exp(-x);
+  const double r = sqrt(r2), x = r * a.inv_sigma, ex = exp_from_scaled(-kExpScale * x, tab);
   if (a.kind == KREG_KERNEL_MATERN && a.nn >= 1) {
+    switch (a.nn) {  // the orders in use get straight-line polynomials; the rest a loop
+      case 1:
+        return matern_pair_values<1>(a, x, ex, k, phi);
+      case 2:
+        return matern_pair_values<2>(a, x, ex, k, phi);
+      case 3:
+        return matern_pair_values<3>(a, x, ex, k, phi);
+      default:
+        break;
+    }
     const double y = 2.0 * x;
     double p = a.mat_c[a.nn], d = a.mat_d[a.nn - 1];
     for (int m = a.nn - 1; m >= 0; m--) p = fma(p, y, a.mat_c[m]);
@@ -226,27 +250,37 @@ __device__ __forceinline__ void radial_pair_values(const ValuesArgs &a, double s
 }
 
 __device__ __forceinline__ void wr_tile_epilogue(const ValuesArgs &a, double (&S)[4][4][2], int64_t i0, int64_t j0,
-                                                 const double *bA, int wi, int wj, int g, int q) {
+                                                 const double *bA, const double *tab, int wi, int wj, int g, int q) {
+  // the chunk-major position of a column does not depend on the row: four integer divisions per tile, not one per element
+  int64_t coloff[4];
+  double c0[4], c1[4];
+  bool ok0[4], ok1[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; nt++) {
+    const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
+    const int64_t ch = j / a.wkc;
+    coloff[nt] = ch * a.na * a.wkc + (j - ch * a.wkc);
+    ok0[nt] = j < a.nb;
+    ok1[nt] = j + 1 < a.nb;
+    c0[nt] = ok0[nt] ? __ldg(a.colscale + j) : 0.0;
+    c1[nt] = ok1[nt] ? __ldg(a.colscale + j + 1) : 0.0;  // padding column of the last chunk: exact zeros for the second GEMM
+  }
 #pragma unroll
   for (int mt = 0; mt < 4; mt++) {
     const int ri = wi * 32 + mt * 8 + g;
     const int64_t i = i0 + ri;
-    const bool row_ok = i < a.na;
+    if (i >= a.na) continue;
     const double bi = bA[ri];
 #pragma unroll
     for (int nt = 0; nt < 4; nt++) {
-      const int64_t j = j0 + wj * 32 + nt * 8 + 2 * q;
-      if (!row_ok || j >= a.nb) continue;
+      if (!ok0[nt]) continue;
       double k0, k1, p0, p1;
-      radial_pair_values(a, S[mt][nt][0] + bi, k0, p0);
-      radial_pair_values(a, S[mt][nt][1] + bi, k1, p1);
-      const bool has1 = j + 1 < a.nb;
-      const double c0 = __ldg(a.colscale + j), c1 = has1 ? __ldg(a.colscale + j + 1) : 0.0;  // padding column: exact zeros
-      const int64_t ch = j / a.wkc;
-      const int64_t off = (ch * a.na + i) * a.wkc + (j - ch * a.wkc);
+      radial_pair_values(a, S[mt][nt][0] + bi, tab, k0, p0);
+      radial_pair_values(a, S[mt][nt][1] + bi, tab, k1, p1);
+      const int64_t off = coloff[nt] + i * a.wkc;
       KREG_CHECK(off >= 0 && off + 1 < (int64_t)((a.nb + a.wkc - 1) / a.wkc) * a.na * a.wkc && (off & 1) == 0, 3);
-      *reinterpret_cast<double2 *>(a.Wch + off) = make_double2(p0 * c0, has1 ? p1 * c1 : 0.0);
-      *reinterpret_cast<double2 *>(a.Kfch + off) = make_double2(k0 * c0, has1 ? k1 * c1 : 0.0);
+      *reinterpret_cast<double2 *>(a.Wch + off) = make_double2(p0 * c0[nt], ok1[nt] ? p1 * c1[nt] : 0.0);
+      *reinterpret_cast<double2 *>(a.Kfch + off) = make_double2(k0 * c0[nt], ok1[nt] ? k1 * c1[nt] : 0.0);
     }
   }
 }
@@ -388,7 +422,7 @@ __global__ void __launch_bounds__(256, 2) values_ring_kernel(const ValuesArgs a)
     else if (EPI == EPI_KR)
       radial_tile_epilogue(a, S, i0, j0, bA, wi, wj, g, q);
     else if (EPI == EPI_WR)
-      wr_tile_epilogue(a, S, i0, j0, bA, wi, wj, g, q);
+      wr_tile_epilogue(a, S, i0, j0, bA, tab, wi, wj, g, q);
     else
       w_tile_epilogue<EPI>(a, S, i0, j0, bA, tab, wi, wj, g, q);
   };
@@ -1443,6 +1477,31 @@ __global__ void __launch_bounds__(256) block_dot_kernel(int64_t na, int64_t nb, 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) E[i] = prior + s;
+}
+
+// out[i * ldo] = sum over all chunks and columns of a chunk-major array W[ch][i][wkc]: the energies of the radial models
+// (E_i = sum_j alpha_j k_ij) without a second GEMM whose single useful column would waste 63/64 of a tile.  One warp per
+// row, chunks in order, fixed shuffle tree: deterministic.
+__global__ void __launch_bounds__(256) chunk_rowsum_kernel(int64_t n, int nch, int wkc, const double *__restrict__ W,
+                                                           double *__restrict__ out, int ldo) {
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int ch = 0; ch < nch; ch++) {
+    const double *row = W + ((int64_t)ch * n + i) * wkc;
+    for (int jj = lane; jj < wkc; jj += 32) s += row[jj];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i * ldo] = s;
+}
+
+int launch_chunk_rowsum(int64_t n, int nch, int wkc, const double *W, double *out, int ldo, cudaStream_t st) {
+  if (n <= 0) return KREG_OK;
+  chunk_rowsum_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(n, nch, wkc, W, out, ldo);
+  KREG_LAUNCH_CHECK();
+  return KREG_OK;
 }
 
 struct ExWs {

@@ -257,7 +257,7 @@ size_t big_predict_radial_workspace_bytes(int nat, int64_t ntr, int64_t npoints,
 // derivatives dKdXid :1178-1233 inside dKdMiat_unpermuted :1407-1447) for a values-trained model, any molecule size, on
 // the same three-kernel skeleton:
 //   GEMM1   S = X'te . X'tr^T - n_j/2, epilogue (EPI_WR): r_ij from S, then w_ij = alpha_j phi(r_ij) and e_ij = alpha_j k(r_ij)
-//   GEMM2   A = W . [X'tr | 1]   (gradient weights; skipped for energies only)      GEMM2'  e = E . 1
+//   GEMM2   A = W . [X'tr | 1]   (gradient weights; skipped for energies only);    e_i = row sums of E (chunk_rowsum_kernel)
 //   epilogue per geometry: E = prior + e, g = A[:D] - X'_i A[D], dE/dM = J_i^T g
 // The packed model is the values-only layout of big_pack_model (sigma does not enter it).
 int big_predict_radial(int kind, int nn, int nat, int64_t ntr, const void *packed, const double *center, const double *xeq,
@@ -335,20 +335,9 @@ int big_predict_radial(int kind, int nn, int nat, int64_t ntr, const void *packe
       rc = launch_gemm_epi(g2, EPI_LIN, st);
       if (rc) return rc;
     }
-    {
-      ValuesArgs g3 = a;  // energies: the ones row of the B operand alone (one column tile)
-      g3.XAch = Efch;
-      g3.XBch = XT + (size_t)m.D * kCW;
-      g3.nb = 1;
-      g3.strideB = m.nbT;
-      g3.nchunks = m.nchW;
-      g3.biasB = zeros;
-      g3.K = accE;
-      g3.ldk = 2;
-      g3.njt = 1;
-      rc = launch_gemm_epi(g3, EPI_LIN, st);
-      if (rc) return rc;
-    }
+    // energies: row sums of the chunk-major alpha_j k_ij (a GEMM with the ones row would waste 63/64 of its tile)
+    rc = launch_chunk_rowsum(tn, m.nchW, kCW, Efch, accE, 2, st);
+    if (rc) return rc;
     big_epilogue_kernel<<<(unsigned)((tn + 7) / 8), 256, 0, st>>>(nat, tn, x, xeq, XcA, m.XS, want_g ? acc : accE,
                                                                   want_g ? w.NPAD : 2, want_g ? m.D : 0, 1.0, prior,
                                                                   E ? E + n0 : nullptr, G ? G + n0 * nat * 3 : nullptr,
