@@ -220,9 +220,19 @@ class kreg:
         return kernel, nn
 
     def _perm_inv_groups(self):
-        """Atom groups of MLatomF's ``permInvKernel`` request in ``additional_mlatomf_args`` (None: not requested)."""
+        """Atom groups of MLatomF's ``permInvKernel`` request in ``additional_mlatomf_args`` (None: not requested).
+        Arguments that would select a model this package does not build raise instead of being dropped silently."""
         args = [str(a) for a in self.__dict__.get("additional_mlatomf_args", None) or []]
+        for a in args:
+            key, _, val = a.casefold().partition("=")
+            if (key == "moldescriptor" and val != "re") or (key == "moldescrtype" and val not in ("unsorted", "permuted")) \
+                    or key in ("selectperm", "periodkernel", "decaykernel", "usepermind"):
+                raise NotImplementedError(f"MLatomF argument {a!r} selects a model outside this package (RE descriptor, "
+                                          "Gaussian / exponential / Matern / Laplacian kernels, permInvKernel with permInvNuclei)")
         if not any(a.casefold() == "perminvkernel" for a in args):
+            if any(a.casefold() == "moldescrtype=permuted" for a in args):
+                raise NotImplementedError("molDescrType=permuted without permInvKernel (the plain kernel on the concatenated "
+                                          "permuted descriptor) is not built")
             return None
         from .perminv import parse_perm_inv_nuclei
 

@@ -97,3 +97,35 @@ def test_oracle_generic_kernel_prediction_is_self_consistent(oracle, kind, nn, t
         ep, _ = oracle.predict_generic(kind, xdtr, alpha, sigma, 0.5, xp, oracle.descriptors(xp, xeq), nn=nn, calc_grad=False)
         em, _ = oracle.predict_generic(kind, xdtr, alpha, sigma, 0.5, xm, oracle.descriptors(xm, xeq), nn=nn, calc_grad=False)
         assert np.abs((ep - em) / (2 * h) - g[:, a, t]).max() <= tol
+
+
+def test_model_class_reads_the_mlatomf_arguments():
+    """`additional_mlatomf_args` (mlatom/models.py:494-495) select the kernel function / the permutationally invariant
+    kernel exactly as MLatomF's command line would (no compute: the decision logic only)."""
+    from mlatom_b200 import models
+
+    m = models.kreg(ml_program="MLatomF")
+    assert m._other_kernel() is None and m._perm_inv_groups() is None
+    m.additional_mlatomf_args = ["kernel=Matern"]
+    assert m._other_kernel() == ("Matern", 2)  # MLatomF's default order (optionsModule.f90:105)
+    m.additional_mlatomf_args = ["nn=4", "kernel=matern"]
+    assert m._other_kernel() == ("matern", 4)
+    m.additional_mlatomf_args = ["kernel=Gaussian"]
+    assert m._other_kernel() is None
+    m.additional_mlatomf_args = ["kernel=polynomial"]
+    with pytest.raises(NotImplementedError):
+        m._other_kernel()
+    m.additional_mlatomf_args = ["permInvKernel", "permInvNuclei=4-5.6-7-8", "molDescrType=permuted"]
+    assert m._perm_inv_groups() == [[3, 4], [5, 6, 7]]
+    m.additional_mlatomf_args = ["permInvKernel"]
+    with pytest.raises(ValueError):
+        m._perm_inv_groups()
+    m.additional_mlatomf_args = ["permInvKernel", "permInvGroups=1,2-3,4"]
+    with pytest.raises(NotImplementedError):
+        m._perm_inv_groups()
+    for unsupported in (["molDescrType=permuted", "permInvNuclei=1-2"], ["molDescriptor=CM"], ["selectPerm"]):
+        m.additional_mlatomf_args = unsupported  # models this package does not build must not be dropped silently
+        with pytest.raises(NotImplementedError):
+            m._perm_inv_groups()
+    m.additional_mlatomf_args = ["molDescriptor=RE", "molDescrType=unsorted", "benchmark"]
+    assert m._perm_inv_groups() is None and m._other_kernel() is None
