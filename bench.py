@@ -732,7 +732,9 @@ def run_ours(args):
                           "hbm_peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback",
                           "frac_of_hbm": kb["gb_per_s"] / (hbm_peak if hbm_peak else 6650.0),
                           "fp64_bound_ms": fp64_ms, "frac_of_fp64_bound": fp64_ms / kb["ms"],
-                          "note": f"values-only K at D={D} is FP64-issue-bound, not HBM-bound (SURVEY.md App. D)",
+                          "note": f"values-only K at D={D} is FP64-issue-bound, not HBM-bound (SURVEY.md App. D); this block is the "
+                                  "model of the headline run (Ntrain=10k: 2.7 waves of tiles + three preparation kernels inside "
+                                  "0.22 ms) -- the BASELINE sizes (cfg3 50k values, cfg5 56k gradient-augmented) are in kbuild_configs",
                           "potrf_potrs_ms_timed_separately": extra.get("solve_ms")}
     if world == 1 and args.workload == "cfg2":
         if kb_cfgs is not None:
