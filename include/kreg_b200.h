@@ -173,7 +173,9 @@ int kreg_block_dot(int64_t na, int64_t nb, const double *K, int64_t ldk, const d
  * X^P = RE descriptor of the geometry with its atoms permuted by the P-th permutation (and the equilibrium distances
  * permuted alike).  X^P is an entry permutation of X: X^P[d] = X[pidx[P][d]], pidx[P][d(a,c)] = d(p_P(a), p_P(c)) with
  * p_P the full 0-based atom map (mod_permInds, A_KRR_kernel.f90:944-950); pidx_inv is the table of the inverse maps.
- * pidx / pidx_inv: DEVICE int32 [nperm][D]; row 0 must be the identity (the reference pairs block 1 with every block). */
+ * pidx / pidx_inv: DEVICE int32 [nperm][D]; row 0 must be the identity (the reference pairs block 1 with every block).
+ * nperm is limited by the shared memory of the self-term kernel, (2 D + nperm) doubles <= 200 KB (about 20 000 permutations
+ * at 21 atoms); larger sets return KREG_E_UNSUPPORTED. */
 
 /* Replaces calcX for the permuted descriptor: X[p][P][d] (the reference's X(:,p), Nperm blocks of D). */
 int kreg_perm_descriptors(int natoms, int64_t npoints, const double *xyz, const double *xeq, int nperm,
