@@ -248,6 +248,11 @@ class KREG_API:
     def load_model(self, filename):
         """kreg_api.py:152-156; files written by the reference load here and vice versa."""
         with np.load(filename) as model:
+            # model files of the other model kinds carry extra keys; read as a plain KREG model they would silently
+            # predict with the wrong kernel
+            if type(self) is KREG_API and ("pmap" in model.files or "kernel" in model.files):
+                kind = "perminv.PermInvKREG" if "pmap" in model.files else "kernels.RadialKREG"
+                raise ValueError(f"{filename} is a {kind} model file: load it with that class (mlatom_b200.models.kreg does)")
             for key in model.files:
                 self.__dict__[key] = model[key]
         self._model = None
