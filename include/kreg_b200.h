@@ -145,7 +145,8 @@ int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double 
 /* Models on those kernel functions (values-trained; MLatomF `kernel=exponential|Matern|Laplacian`, reached in the reference
  * through kreg(ml_program='MLatomF') + additional_mlatomf_args, models.py:494-495).  Training = kreg_kernel_block_ex
  * (symmetric, lambda) + kreg_solve.  Prediction of energies AND gradients for the three kernels of the Euclidean distance
- * runs on the tensor-core skeleton of the large-molecule path, any molecule size:
+ * runs on the fused two-GEMM tensor-core kernels up to KREG_FUSED_MAX_NATOMS atoms (the Gaussian model's kernels with a
+ * different elementwise step) and on the tiled three-kernel path above:
  *   E[i] = prior + sum_j alpha_j k(r_ij)                                   (Yest_KRR, A_KRR_kernel.f90:225-245)
  *   G[i] = J_i^T sum_j alpha_j phi(r_ij) (X_j - X_i),  phi = -k'(r) / r     (YgradXYZest_KRR :731-744 -> dKdMiat_unpermuted
  *          :1407-1447 -> dKdXid :1178-1233)
@@ -154,8 +155,8 @@ int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double 
  * KREG_KERNEL_GAUSSIAN is accepted too (the same numbers as kreg_predict through this path).  The Laplacian kernel
  * (L1 distance, no GEMM form) predicts energies through kreg_kernel_block_ex + kreg_block_dot. */
 size_t kreg_radial_packed_model_bytes(int natoms, int64_t ntrain);
-/* Packs centred descriptor rows, column terms, alpha and the transposed rows (the values-only layout of the large-molecule
- * path; the kernel width does not enter).  `packed` must be 256-byte aligned; center[D] is written. */
+/* Packs the model in the layout kreg_predict_radial streams for this molecule size (the kernel width does not enter):
+ * `packed` must be 256-byte aligned, kreg_radial_packed_model_bytes long; center[D] is written. */
 int kreg_pack_model_radial(int natoms, int64_t ntrain, const double *xyz_train, const double *xeq,
                            const double *alpha_val, double *center, void *packed, size_t packed_bytes, void *stream);
 size_t kreg_predict_radial_workspace_bytes(int natoms, int64_t ntrain, int64_t npoints);

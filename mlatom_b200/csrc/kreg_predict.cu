@@ -15,6 +15,7 @@
 // through a TMA bulk-copy ring in shared memory.  Energies and gradients come out of ONE pass (the
 // reference makes two and recomputes k_ij 3*Nat+1 times).
 #include "kreg_common.cuh"
+#include "kreg_gemm.h"
 #include "kreg_internal.h"
 #include "kreg_predict_args.h"
 
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(32) pack_model_kernel(int nat, int64_t ntrain,
                                                         const double *__restrict__ alpha,
                                                         const double *__restrict__ V, double c1, double inv_s2,
                                                         double *__restrict__ packed,
-                                                        const double *__restrict__ Xin /* optional [ntrain][D] */) {
+                                                        const double *__restrict__ Xin /* optional [ntrain][D] */,
+                                                        int raw_alpha = 0 /* radial-kernel models: alpha_j as it is */) {
   extern __shared__ double sm[];
   const TcShape sh(nat);
   const int TS = sh.NT * 8 > sh.KS * 4 ? sh.NT * 8 : sh.KS * 4;
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(32) pack_model_kernel(int nat, int64_t ntrain,
     double x, sj = -0.5 * nj[lane];
     if (HAS_V) {
       x = (j < ntrain) ? a - xv[lane] * inv_s2 : 0.0;
+    } else if (raw_alpha) {
+      x = (j < ntrain) ? a : 0.0;  // radial kernels: the weight multiplies k and phi after the fact; s_j = -n_j/2
     } else {
       x = (a < 0.0) ? -0.0 : 0.0;
       sj = (a != 0.0) ? sj + log(fabs(a)) / inv_s2 : -1e300;
@@ -342,6 +346,7 @@ extern "C" int kreg_predict(int natoms, int64_t ntrain, const void *packed, cons
 // ---- models on MLatomF's other radial kernel functions (values-trained) --------------------------------------------------
 extern "C" size_t kreg_radial_packed_model_bytes(int natoms, int64_t ntrain) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0) return 0;
+  if (natoms <= KREG_FUSED_MAX_NATOMS) return kreg_packed_model_bytes(natoms, ntrain, 0);  // the fused kernels' chunks
   return big_packed_model_bytes(natoms, ntrain, false);
 }
 
@@ -350,17 +355,29 @@ extern "C" int kreg_pack_model_radial(int natoms, int64_t ntrain, const double *
                                       void *stream) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS) return KREG_E_UNSUPPORTED;
   if (ntrain <= 0 || !xyz_train || !xeq || !alpha_val || !center || !packed) return KREG_E_BADARG;
-  if (packed_bytes < big_packed_model_bytes(natoms, ntrain, false)) return KREG_E_WORKSPACE;
+  if (packed_bytes < kreg_radial_packed_model_bytes(natoms, ntrain)) return KREG_E_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(packed) & 255) != 0) return KREG_E_BADARG;
   cudaStream_t st = as_stream(stream);
   int rc = launch_descriptor_mean(natoms, ntrain, xyz_train, xeq, center, st);
   if (rc) return rc;
+  if (natoms <= KREG_FUSED_MAX_NATOMS) {
+    // the fused kernels' fragment-ordered chunks with alpha_j itself and s_j = -n_j/2 in the scalar slots
+    const TcShape sh(natoms);
+    const int TS = sh.NT * 8 > sh.KS * 4 ? sh.NT * 8 : sh.KS * 4;
+    const size_t smem = (size_t)(16 * TS + 16) * sizeof(double);
+    pack_model_kernel<false><<<(unsigned)((ntrain + 7) / 8), 32, smem, st>>>(natoms, ntrain, xyz_train, xeq, center, alpha_val,
+                                                                         nullptr, 1.0, 1.0, static_cast<double *>(packed),
+                                                                         nullptr, 1);
+    KREG_LAUNCH_CHECK();
+    return KREG_OK;
+  }
   // the kernel width does not enter the packed arrays (centred rows, -n_j/2, alpha_j, transposed rows)
   return big_pack_model(natoms, ntrain, xyz_train, nullptr, xeq, alpha_val, nullptr, 1.0, center, packed, packed_bytes, st);
 }
 
 extern "C" size_t kreg_predict_radial_workspace_bytes(int natoms, int64_t ntrain, int64_t npoints) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0 || npoints <= 0) return 0;
+  if (natoms <= KREG_FUSED_MAX_NATOMS) return 0;  // the fused kernels need no scratch (radial models never run split)
   int sms = 0;
   if (device_sm_count(&sms) != KREG_OK) return 0;
   return big_predict_radial_workspace_bytes(natoms, ntrain, npoints, sms);
@@ -384,6 +401,36 @@ extern "C" int kreg_predict_radial(int kind, int nn, int natoms, int64_t ntrain,
   if (rc) return rc;
   // Matern of order 0 is the exponential kernel (Kfunk :837-849 with nn = 0); the reference differentiates it numerically
   if (kind == KREG_KERNEL_MATERN && nn == 0) kind = KREG_KERNEL_EXPONENTIAL;
+  if (natoms <= KREG_FUSED_MAX_NATOMS) {
+    // the fused two-GEMM kernels (predict_kernel<..., KIND = 1>): same operand ring and fragments as the Gaussian model
+    PredictArgs a = {};
+    a.xyz = xyz;
+    a.npoints = npoints;
+    a.xeq = xeq;
+    a.center = center;
+    a.packed = static_cast<const double *>(packed);
+    a.ngroups = (int)((ntrain + 7) / 8);
+    a.c1 = 1.0;      // row term -n_i/2, unscaled
+    a.inv_s2 = 1.0;  // phi carries every factor of the gradient
+    a.prior = prior;
+    a.E = (flags & KREG_PREDICT_ENERGY) ? E : nullptr;
+    a.G = (flags & KREG_PREDICT_GRADIENT) ? G : nullptr;
+    a.radial = 1;
+    a.kind = kind;
+    a.nn = nn;
+    a.inv_sigma = 1.0 / sigma;
+    a.rinv_s2 = 1.0 / (sigma * sigma);
+    if (kind == KREG_KERNEL_MATERN) {
+      ValuesArgs coef = {};
+      set_matern_coefficients(coef, nn, sigma);
+      for (int m = 0; m < 12; m++) {
+        a.mat_c[m] = coef.mat_c[m];
+        a.mat_d[m] = coef.mat_d[m];
+      }
+    }
+    size_t need = 0;
+    return launch_predict(natoms, a, false, sms, nullptr, 0, false, &need, as_stream(stream));
+  }
   return big_predict_radial(kind, nn, natoms, ntrain, packed, center, xeq, sigma, prior, npoints, xyz,
                             (flags & KREG_PREDICT_ENERGY) ? E : nullptr, (flags & KREG_PREDICT_GRADIENT) ? G : nullptr,
                             workspace, workspace_bytes, sms, as_stream(stream));

@@ -22,6 +22,15 @@ struct PredictArgs {
   int nslices;
   int stages_per_slice;
   double *partial;
+  // models on MLatomF's radial kernel functions (predict_kernel<..., KIND = 1>; kreg_predict_radial): the packed model
+  // then carries alpha_j itself and the plain column term -n_j/2, c1 is 1 (row term -n_i/2) and inv_s2 is 1
+  int radial;         // 1: radial-kernel model (0: the Gaussian KREG model, everything below unused)
+  int kind;           // KREG_KERNEL_GAUSSIAN / _EXPONENTIAL / _MATERN
+  int nn;             // Matern order
+  double inv_sigma;   // 1 / sigma
+  double rinv_s2;     // 1 / sigma^2 (Gaussian through the radial path)
+  double mat_c[12];   // k   = exp(-r/sigma) sum_m mat_c[m] (2r/sigma)^m
+  double mat_d[12];   // phi = exp(-r/sigma) sum_m mat_d[m] (2r/sigma)^m
 };
 
 }  // namespace kreg

@@ -37,11 +37,14 @@ struct PredictCfg {
 };
 
 // Per-geometry epilogue: E = prior + A[D];  g = (A[:D] - X'_i A[D]) / s^2;  dE/dM = J_i^T g  (KREG.f90:121 Jacobian)
+// (Radial kernels: the energy sum, sum_j alpha_j k_ij, is not the sum of the gradient weights, sum_j alpha_j phi_ij, that
+// the ones column accumulates; it arrives through `esep`.)
 template <int NAT, bool WANT_G>
-__device__ __forceinline__ void predict_row_epilogue(const PredictArgs &args, const double *y, int64_t p) {
+__device__ __forceinline__ void predict_row_epilogue(const PredictArgs &args, const double *y, int64_t p,
+                                                     const double *esep = nullptr) {
   constexpr int D = NAT * (NAT - 1) / 2;
   const double esum = y[D];
-  if (args.E) args.E[p] = args.prior + esum;
+  if (args.E) args.E[p] = args.prior + (esep ? *esep : esum);
   if (WANT_G && args.G) {
     const double *m = args.xyz + p * (NAT * 3);
     double mm[NAT * 3], gr[NAT * 3];
@@ -151,8 +154,14 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
 
 // SPLIT = small-batch (latency) mode: the training set is divided over gridDim.y slices and the raw accumulators go to
 // predict_finish_kernel.  A separate instantiation, so that none of its code perturbs the throughput kernel.
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps, bool SPLIT = false>
+// KIND = 1: values-trained model on one of MLatomF's radial kernel functions (Gaussian / exponential / Matern chosen at
+// run time, args.kind): the elementwise step takes r_ij from the GEMM1 accumulator and forms the gradient weight
+// alpha_j phi(r_ij) (phi = -k'(r)/r; dKdXid, A_KRR_kernel.f90:1178-1233) for GEMM2 and the energy term alpha_j k(r_ij),
+// summed per thread like the energy-only pass does.  Everything else -- operand ring, fragments, GEMMs -- is shared.
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps, bool SPLIT = false,
+          int KIND = 0>
 __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
+  static_assert(KIND == 0 || (!HAS_V && !SPLIT), "radial kernels: values-trained models, unsplit launches");
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
   constexpr int kWarps = NW, kThreads = NW * 32;  // shadow the defaults: this kernel's own CTA shape
   constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
   double afrag[A_IN_SMEM ? 1 : MT][A_IN_SMEM ? 1 : KS];
   double bi[MT];
   double acc[WANT_G ? MT : 1][WANT_G ? NT : 1][2];  // GEMM2 accumulators (energy + gradient passes)
-  double esum[WANT_G ? 1 : MT];                      // energy-only passes: per-thread partial row sums of W
+  double esum[(WANT_G && KIND == 0) ? 1 : MT];       // energy-only passes (and radial kernels): per-thread partial row sums
   const double *arow[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) {
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
     } else {
       esum[WANT_G ? 0 : mt] = 0.0;
     }
+    if (WANT_G && KIND != 0) esum[(WANT_G && KIND == 0) ? 0 : mt] = 0.0;
   }
   const double c1 = args.c1;
 
@@ -322,6 +332,38 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
       // elementwise: k = exp(c1 S + bias_i); gradient models w = k (a'_j + S2); value models w = sign(alpha_j) k
       // (|alpha_j| is inside the exponent), so no multiply at all
       double W[MT][2], Kf[HAS_V ? MT : 1][2];
+      if constexpr (KIND != 0) {
+        // radial kernels: r^2 = -2 (S + b_i) with S = X'_i.X'_j - n_j/2 and b_i = -n_i/2 (c1 = 1); sc.x / sc.z = alpha_j
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+          double kk[2], ph[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const double r2 = fmax(-2.0 * (S[mt][e] + bi[mt]), 0.0);
+            if (args.kind == KREG_KERNEL_GAUSSIAN) {
+              kk[e] = exp_from_scaled_cvt(-0.5 * kExpScale * args.rinv_s2 * r2, tab);
+              ph[e] = kk[e] * args.rinv_s2;
+            } else {
+              const double r = sqrt(r2), x = r * args.inv_sigma, ex = exp_from_scaled_cvt(-kExpScale * x, tab);
+              if (args.kind == KREG_KERNEL_MATERN) {
+                const double y = 2.0 * x;
+                double pc = args.mat_c[args.nn], pd = args.mat_d[args.nn - 1];
+                for (int m = args.nn - 1; m >= 0; m--) pc = fma(pc, y, args.mat_c[m]);
+                for (int m = args.nn - 2; m >= 0; m--) pd = fma(pd, y, args.mat_d[m]);
+                kk[e] = ex * pc;
+                ph[e] = ex * pd;
+              } else {
+                kk[e] = ex;
+                ph[e] = r > 0.0 ? ex * args.inv_sigma / r : 0.0;
+              }
+            }
+          }
+          W[mt][0] = sc.x * ph[0];
+          W[mt][1] = sc.z * ph[1];
+          esum[(WANT_G && KIND == 0) ? 0 : mt] += sc.x * kk[0] + sc.z * kk[1];
+        }
+        if (!WANT_G) continue;
+      } else {
 #pragma unroll
       for (int mt = 0; mt < MT; mt++) {
         const double k0 = exp_from_scaled_cvt(fma(S[mt][0], c1, bi[mt]), tab);
@@ -342,6 +384,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
         for (int mt = 0; mt < MT; mt++) esum[WANT_G ? 0 : mt] += W[mt][0] + W[mt][1];
         continue;
       }
+      }  // KIND == 0
       // GEMM2: acc += W . [Xtrain | 1]  (+ K . V)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
@@ -365,6 +408,16 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
 
   // ---- epilogue: accumulators -> shared tile, then one thread per test geometry ----
   __syncthreads();
+  if (WANT_G && KIND != 0) {
+    // radial kernels: the energy sums travel beside the accumulators, in the (now dead) row-term array
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      double s = esum[(WANT_G && KIND == 0) ? 0 : mt];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0) bias[(warp * MT + mt) * 8 + g] = s;
+    }
+  }
   if (WANT_G) {
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
@@ -395,7 +448,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
   }
   for (int r = tid; r < C::ROWS; r += kThreads) {
     const int64_t p = row0 + r;
-    if (p < args.npoints) predict_row_epilogue<NAT, WANT_G>(args, tile + r * TS, p);
+    if (p < args.npoints) predict_row_epilogue<NAT, WANT_G>(args, tile + r * TS, p, (WANT_G && KIND != 0) ? bias + r : nullptr);
   }
 }
 
@@ -415,10 +468,10 @@ static void plan_slices(int ngroups, int64_t blocks, int sms, int *nslices, int 
   *nslices = (all_stages + per - 1) / per;
 }
 
-template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW, bool SPLIT = false>
+template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW, bool SPLIT = false, int KIND = 0>
 static int launch_predict_g(PredictArgs a, cudaStream_t st) {
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
-  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G, NW, SPLIT>;
+  auto kern = predict_kernel<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, WANT_G, NW, SPLIT, KIND>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   KREG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
   const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
@@ -440,6 +493,21 @@ static size_t predict_ws_cfg(int ngroups, int64_t npoints, int sms, int *nslices
   const int64_t blocks = (npoints + C::ROWS - 1) / C::ROWS;
   plan_slices<GPS>(ngroups, blocks, sms, nslices, stages_per_slice);
   return *nslices > 1 ? (size_t)*nslices * blocks * C::ROWS * C::TS * sizeof(double) : 0;
+}
+
+// the same configuration for a model on a radial kernel function (values-trained, never split: the energy sums do not
+// travel with the partial accumulators)
+template <int NAT, int MT, bool A_IN_SMEM, int GPS, int NSTAGE, int NW = kWarps>
+static int launch_predict_radial_cfg(PredictArgs a, bool query, size_t *need, cudaStream_t st) {
+  if (query) {
+    *need = 0;
+    return KREG_OK;
+  }
+  a.nslices = 1;
+  a.stages_per_slice = 0;
+  a.partial = nullptr;
+  return a.G ? launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, false, 1>(a, st)
+             : launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, false, NW, false, 1>(a, st);
 }
 
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, int NW = kWarps>
@@ -469,6 +537,12 @@ template <int NAT>
 static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *ws, size_t ws_bytes, bool query,
                               size_t *need, cudaStream_t st) {
   constexpr TcShape sh(NAT);
+  if (a.radial) {  // radial kernel functions: the value-model configuration of each size class
+    if constexpr (sh.D <= 36) return launch_predict_radial_cfg<NAT, 2, false, 3, 3>(a, query, need, st);
+    else if constexpr (sh.D <= 66) return launch_predict_radial_cfg<NAT, 2, false, 2, 4>(a, query, need, st);
+    else if constexpr (sh.D <= 210) return launch_predict_radial_cfg<NAT, 1, true, 1, 3>(a, query, need, st);
+    else return launch_predict_radial_cfg<NAT, 1, true, 1, 2>(a, query, need, st);
+  }
   if constexpr (sh.D <= 36) {
     // small molecules: test-row fragments live in registers, 2 m-tiles per warp, two CTAs per SM (16 warps hide the
     // fixed DMMA issue latency better than one CTA with 4 m-tiles per warp: 51.5 vs 53.7 ms on cfg2)
