@@ -347,9 +347,18 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
               const double r = sqrt(r2), x = r * args.inv_sigma, ex = exp_from_scaled_cvt(-kExpScale * x, tab);
               if (args.kind == KREG_KERNEL_MATERN) {
                 const double y = 2.0 * x;
-                double pc = args.mat_c[args.nn], pd = args.mat_d[args.nn - 1];
-                for (int m = args.nn - 1; m >= 0; m--) pc = fma(pc, y, args.mat_c[m]);
-                for (int m = args.nn - 2; m >= 0; m--) pd = fma(pd, y, args.mat_d[m]);
+                double pc, pd;
+                if (args.nn <= 3) {
+                  // the orders in use: fixed-length Horner forms (coefficients above the order are zero), so every
+                  // coefficient is a constant-bank operand of its FMA -- no indexed loads, no loop
+                  pc = fma(fma(fma(args.mat_c[3], y, args.mat_c[2]), y, args.mat_c[1]), y, args.mat_c[0]);
+                  pd = fma(fma(args.mat_d[2], y, args.mat_d[1]), y, args.mat_d[0]);
+                } else {
+                  pc = args.mat_c[args.nn];
+                  pd = args.mat_d[args.nn - 1];
+                  for (int m = args.nn - 1; m >= 0; m--) pc = fma(pc, y, args.mat_c[m]);
+                  for (int m = args.nn - 2; m >= 0; m--) pd = fma(pd, y, args.mat_d[m]);
+                }
                 kk[e] = ex * pc;
                 ph[e] = ex * pd;
               } else {
