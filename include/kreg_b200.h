@@ -159,6 +159,9 @@ size_t kreg_radial_packed_model_bytes(int natoms, int64_t ntrain);
  * `packed` must be 256-byte aligned, kreg_radial_packed_model_bytes long; center[D] is written. */
 int kreg_pack_model_radial(int natoms, int64_t ntrain, const double *xyz_train, const double *xeq,
                            const double *alpha_val, double *center, void *packed, size_t packed_bytes, void *stream);
+/* Scratch for this batch: the three-kernel path's tiles above KREG_FUSED_MAX_NATOMS atoms; below, the partial
+ * accumulators of the small-batch launch (the training set split over the chip, as in kreg_predict; 0 for batches
+ * large enough to fill it; there a NULL or short workspace only means the batch runs unsplit). */
 size_t kreg_predict_radial_workspace_bytes(int natoms, int64_t ntrain, int64_t npoints);
 int kreg_predict_radial(int kind, int nn, int natoms, int64_t ntrain, const void *packed, const double *center,
                         const double *xeq, double sigma, double prior, int64_t npoints, const double *xyz, int flags,

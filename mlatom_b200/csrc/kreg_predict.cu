@@ -377,9 +377,17 @@ extern "C" int kreg_pack_model_radial(int natoms, int64_t ntrain, const double *
 
 extern "C" size_t kreg_predict_radial_workspace_bytes(int natoms, int64_t ntrain, int64_t npoints) {
   if (natoms < KREG_MIN_NATOMS || natoms > KREG_MAX_NATOMS || ntrain <= 0 || npoints <= 0) return 0;
-  if (natoms <= KREG_FUSED_MAX_NATOMS) return 0;  // the fused kernels need no scratch (radial models never run split)
   int sms = 0;
   if (device_sm_count(&sms) != KREG_OK) return 0;
+  if (natoms <= KREG_FUSED_MAX_NATOMS) {  // small batches: partial accumulators of the split launch (0 otherwise)
+    PredictArgs a = {};
+    a.npoints = npoints;
+    a.ngroups = (int)((ntrain + 7) / 8);
+    a.radial = 1;
+    size_t need = 0;
+    if (launch_predict(natoms, a, false, sms, nullptr, 0, true, &need, nullptr) != KREG_OK) return 0;
+    return need;
+  }
   return big_predict_radial_workspace_bytes(natoms, ntrain, npoints, sms);
 }
 
@@ -429,7 +437,7 @@ extern "C" int kreg_predict_radial(int kind, int nn, int natoms, int64_t ntrain,
       }
     }
     size_t need = 0;
-    return launch_predict(natoms, a, false, sms, nullptr, 0, false, &need, as_stream(stream));
+    return launch_predict(natoms, a, false, sms, workspace, workspace_bytes, false, &need, as_stream(stream));
   }
   return big_predict_radial(kind, nn, natoms, ntrain, packed, center, xeq, sigma, prior, npoints, xyz,
                             (flags & KREG_PREDICT_ENERGY) ? E : nullptr, (flags & KREG_PREDICT_GRADIENT) ? G : nullptr,

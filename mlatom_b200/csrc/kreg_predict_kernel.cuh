@@ -80,10 +80,11 @@ __device__ __forceinline__ void predict_row_epilogue(const PredictArgs &args, co
 // roots and divisions).  Atom a accumulates its partners in the order c = 0..Nat-1, which is the order in which the
 // serial version reaches them, so both give bit-identical gradients.
 template <int NAT>
-__device__ __forceinline__ void predict_row_epilogue_warp(const PredictArgs &args, const double *y, int64_t p, int lane) {
+__device__ __forceinline__ void predict_row_epilogue_warp(const PredictArgs &args, const double *y, int64_t p, int lane,
+                                                          const double *esep = nullptr) {
   constexpr int D = NAT * (NAT - 1) / 2;
   const double esum = y[D];
-  if (lane == 0 && args.E) args.E[p] = args.prior + esum;
+  if (lane == 0 && args.E) args.E[p] = args.prior + (esep ? *esep : esum);
   if (!args.G || lane >= NAT) return;
   const double *m = args.xyz + p * (NAT * 3);
   const int a = lane;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
     }
   }
   __syncthreads();
-  if (tid < 32) predict_row_epilogue_warp<NAT>(args, ftile, row, tid);
+  if (tid < 32) predict_row_epilogue_warp<NAT>(args, ftile, row, tid, args.radial ? ftile + NAT * (NAT - 1) / 2 + 1 : nullptr);
 }
 
 // SPLIT = small-batch (latency) mode: the training set is divided over gridDim.y slices and the raw accumulators go to
@@ -161,7 +162,9 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
 template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool WANT_G, int NW = kWarps, bool SPLIT = false,
           int KIND = 0>
 __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
-  static_assert(KIND == 0 || (!HAS_V && !SPLIT), "radial kernels: values-trained models, unsplit launches");
+  static_assert(KIND == 0 || !HAS_V, "radial kernels: values-trained models");
+  // split launches of a radial model carry the energy sum in accumulator column D + 1, which must be a padding column
+  static_assert(KIND == 0 || !SPLIT || (NAT * (NAT - 1) / 2 + 1) % 8 != 0, "no free accumulator column for the energy sum");
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
   constexpr int kWarps = NW, kThreads = NW * 32;  // shadow the defaults: this kernel's own CTA shape
   constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
 
   // ---- epilogue: accumulators -> shared tile, then one thread per test geometry ----
   __syncthreads();
-  if (WANT_G && KIND != 0) {
+  if (WANT_G && KIND != 0 && !SPLIT) {
     // radial kernels: the energy sums travel beside the accumulators, in the (now dead) row-term array
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
@@ -435,6 +438,18 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
       for (int nt = 0; nt < NT; nt++)
         *reinterpret_cast<double2 *>(tile + r * TS + 8 * nt + 2 * q) =
             make_double2(acc[WANT_G ? mt : 0][WANT_G ? nt : 0][0], acc[WANT_G ? mt : 0][WANT_G ? nt : 0][1]);
+    }
+    if (KIND != 0 && SPLIT) {
+      // split launch of a radial model: this slice's energy sums go out with the accumulators, in the padding column D + 1
+      // (written after the accumulator store, which covers that column with an exact zero)
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        double s = esum[(WANT_G && KIND == 0) ? 0 : mt];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0) tile[((warp * MT + mt) * 8 + g) * TS + D + 1] = s;
+      }
     }
   } else {
     // the four lanes q = 0..3 of a row hold disjoint column subsets: fixed-order butterfly, lane q == 0 stores
@@ -504,17 +519,31 @@ static size_t predict_ws_cfg(int ngroups, int64_t npoints, int sms, int *nslices
   return *nslices > 1 ? (size_t)*nslices * blocks * C::ROWS * C::TS * sizeof(double) : 0;
 }
 
-// the same configuration for a model on a radial kernel function (values-trained, never split: the energy sums do not
-// travel with the partial accumulators)
+// the same configuration for a model on a radial kernel function (values-trained)
 template <int NAT, int MT, bool A_IN_SMEM, int GPS, int NSTAGE, int NW = kWarps>
-static int launch_predict_radial_cfg(PredictArgs a, bool query, size_t *need, cudaStream_t st) {
+static int launch_predict_radial_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes, bool query, size_t *need,
+                                     cudaStream_t st) {
+  // small batches split the training set over the chip like the Gaussian model does, when the accumulator row has a
+  // padding column for the slices' energy sums (every size except 6, 11 and 22 atoms, where D + 1 is a multiple of 8)
+  constexpr bool can_split = (NAT * (NAT - 1) / 2 + 1) % 8 != 0;
+  int nslices = 1, per = 0;
+  size_t bytes = 0;
+  if (can_split) bytes = predict_ws_cfg<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, NW>(a.ngroups, a.npoints, sms, &nslices, &per);
   if (query) {
-    *need = 0;
+    *need = bytes;
     return KREG_OK;
   }
   a.nslices = 1;
   a.stages_per_slice = 0;
   a.partial = nullptr;
+  if constexpr (can_split) {
+    if (nslices > 1 && ws && ws_bytes >= bytes) {
+      a.nslices = nslices;
+      a.stages_per_slice = per;
+      a.partial = static_cast<double *>(ws);
+      return launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, true, 1>(a, st);
+    }
+  }
   return a.G ? launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, false, 1>(a, st)
              : launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, false, NW, false, 1>(a, st);
 }
@@ -547,10 +576,10 @@ static int launch_predict_nat(const PredictArgs &a, bool has_v, int sms, void *w
                               size_t *need, cudaStream_t st) {
   constexpr TcShape sh(NAT);
   if (a.radial) {  // radial kernel functions: the value-model configuration of each size class
-    if constexpr (sh.D <= 36) return launch_predict_radial_cfg<NAT, 2, false, 3, 3>(a, query, need, st);
-    else if constexpr (sh.D <= 66) return launch_predict_radial_cfg<NAT, 2, false, 2, 4>(a, query, need, st);
-    else if constexpr (sh.D <= 210) return launch_predict_radial_cfg<NAT, 1, true, 1, 3>(a, query, need, st);
-    else return launch_predict_radial_cfg<NAT, 1, true, 1, 2>(a, query, need, st);
+    if constexpr (sh.D <= 36) return launch_predict_radial_cfg<NAT, 2, false, 3, 3>(a, sms, ws, ws_bytes, query, need, st);
+    else if constexpr (sh.D <= 66) return launch_predict_radial_cfg<NAT, 2, false, 2, 4>(a, sms, ws, ws_bytes, query, need, st);
+    else if constexpr (sh.D <= 210) return launch_predict_radial_cfg<NAT, 1, true, 1, 3>(a, sms, ws, ws_bytes, query, need, st);
+    else return launch_predict_radial_cfg<NAT, 1, true, 1, 2>(a, sms, ws, ws_bytes, query, need, st);
   }
   if constexpr (sh.D <= 36) {
     // small molecules: test-row fragments live in registers, 2 m-tiles per warp, two CTAs per SM (16 warps hide the

@@ -181,3 +181,30 @@ def test_model_class_routes_kernel_arguments(eng, oracle, tmp_path):
                                subtraining_molecular_database=sub, validation_molecular_database=val,
                                optimization_algorithm="grid", optimization_algorithm_kwargs={"grid_size": 4})
     assert np.isfinite(m.validation_loss) and 2 ** -5 <= m.hyperparameters["sigma"].value <= 2 ** 9
+
+
+@pytest.mark.parametrize("nat", [9, 6, 21])
+@pytest.mark.parametrize("n", [1, 3, 64])
+def test_radial_small_batches_take_the_split_path(eng, oracle, nat, n):
+    """One geometry (an MD / geometry-optimisation step) and a few dozen: the training set is split over the chip like
+    for the Gaussian model (6 atoms: no free accumulator column for the energy sums, the batch runs unsplit); the numbers
+    agree with the oracle and with the same geometries inside a large batch."""
+    from mlatom_b200 import kernels
+
+    ntr, sigma = 2000, 1.4
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, 3000, 2)
+    xeq = oracle.xeq(eq)
+    alpha = np.random.default_rng(9).standard_normal(ntr)
+    model = kernels.RadialModel("matern", 2, dev(xtr), dev(xeq), dev(alpha), sigma, -3.0)
+    e, g = model.predict(dev(xte[:n]))
+    e, g = e.cpu().numpy(), g.cpu().numpy()
+    e_ref, g_ref = oracle.predict_generic("matern", oracle.descriptors(xtr, xeq), alpha, sigma, -3.0, xte[:n],
+                                          oracle.descriptors(xte[:n], xeq), nn=2)
+    scale = np.abs(alpha).sum()
+    assert np.abs(e - e_ref).max() <= 1e-13 * scale and np.abs(g - g_ref).max() <= 1e-12 * scale
+    e_big, g_big = model.predict(dev(xte))
+    assert np.abs(e_big.cpu().numpy()[:n] - e).max() <= 1e-13 * scale
+    assert np.abs(g_big.cpu().numpy()[:n] - g).max() <= 1e-12 * scale
+    e_only, _ = model.predict(dev(xte[:n]), True, False)
+    assert np.abs(e_only.cpu().numpy() - e).max() <= 1e-13 * scale
