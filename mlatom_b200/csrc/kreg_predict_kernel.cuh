@@ -120,6 +120,7 @@ template <int NAT, int ROWS, int TS>
 __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictArgs args) {
   __shared__ __align__(16) double ftile[TS];
   __shared__ double part[kThreads];
+  __shared__ double e_sep;
   const int tid = threadIdx.x;
   const int64_t row = (int64_t)blockIdx.x * ROWS + blockIdx.y;
   if (row >= args.npoints) return;
@@ -149,8 +150,19 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
       ftile[tid] = s;
     }
   }
+  if (args.radial && tid >= kThreads - 32) {
+    // radial kernels: the slices' energy sums arrive beside the accumulators; lane k takes slices k, k + 32, ..., then a
+    // fixed-order butterfly
+    const double *es = args.partial_e + row;
+    const size_t estride = (size_t)gridDim.x * ROWS;
+    double s = 0.0;
+    for (int sl = tid & 31; sl < args.nslices; sl += 32) s += es[(size_t)sl * estride];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) e_sep = s;
+  }
   __syncthreads();
-  if (tid < 32) predict_row_epilogue_warp<NAT>(args, ftile, row, tid, args.radial ? ftile + NAT * (NAT - 1) / 2 + 1 : nullptr);
+  if (tid < 32) predict_row_epilogue_warp<NAT>(args, ftile, row, tid, args.radial ? &e_sep : nullptr);
 }
 
 // SPLIT = small-batch (latency) mode: the training set is divided over gridDim.y slices and the raw accumulators go to
@@ -163,8 +175,6 @@ template <int NAT, int MT, bool HAS_V, bool A_IN_SMEM, int GPS, int NSTAGE, bool
           int KIND = 0>
 __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ? 2 : 1) predict_kernel(const PredictArgs args) {
   static_assert(KIND == 0 || !HAS_V, "radial kernels: values-trained models");
-  // split launches of a radial model carry the energy sum in accumulator column D + 1, which must be a padding column
-  static_assert(KIND == 0 || !SPLIT || (NAT * (NAT - 1) / 2 + 1) % 8 != 0, "no free accumulator column for the energy sum");
   using C = PredictCfg<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, NW>;
   constexpr int kWarps = NW, kThreads = NW * 32;  // shadow the defaults: this kernel's own CTA shape
   constexpr int D = C::D, KS = C::KS, KS2 = C::KS2, NT = C::NT, TS = C::TS;
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
 
   // ---- epilogue: accumulators -> shared tile, then one thread per test geometry ----
   __syncthreads();
-  if (WANT_G && KIND != 0 && !SPLIT) {
+  if (WANT_G && KIND != 0) {
     // radial kernels: the energy sums travel beside the accumulators, in the (now dead) row-term array
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
@@ -439,18 +449,6 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
         *reinterpret_cast<double2 *>(tile + r * TS + 8 * nt + 2 * q) =
             make_double2(acc[WANT_G ? mt : 0][WANT_G ? nt : 0][0], acc[WANT_G ? mt : 0][WANT_G ? nt : 0][1]);
     }
-    if (KIND != 0 && SPLIT) {
-      // split launch of a radial model: this slice's energy sums go out with the accumulators, in the padding column D + 1
-      // (written after the accumulator store, which covers that column with an exact zero)
-      __syncwarp();
-#pragma unroll
-      for (int mt = 0; mt < MT; mt++) {
-        double s = esum[(WANT_G && KIND == 0) ? 0 : mt];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (q == 0) tile[((warp * MT + mt) * 8 + g) * TS + D + 1] = s;
-      }
-    }
   } else {
     // the four lanes q = 0..3 of a row hold disjoint column subsets: fixed-order butterfly, lane q == 0 stores
 #pragma unroll
@@ -468,6 +466,10 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
     const int64_t left = args.npoints - row0;
     const int nvalid = (int)(left < C::ROWS ? left : C::ROWS);
     for (int e = tid; e < nvalid * TS; e += kThreads) dst[e] = tile[e];
+    if (KIND != 0) {  // radial kernels: this slice's energy sums, [slice][geometry]
+      double *de = args.partial_e + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::ROWS;
+      for (int r = tid; r < nvalid; r += kThreads) de[r] = bias[r];
+    }
     return;
   }
   for (int r = tid; r < C::ROWS; r += kThreads) {
@@ -523,26 +525,26 @@ static size_t predict_ws_cfg(int ngroups, int64_t npoints, int sms, int *nslices
 template <int NAT, int MT, bool A_IN_SMEM, int GPS, int NSTAGE, int NW = kWarps>
 static int launch_predict_radial_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes, bool query, size_t *need,
                                      cudaStream_t st) {
-  // small batches split the training set over the chip like the Gaussian model does, when the accumulator row has a
-  // padding column for the slices' energy sums (every size except 6, 11 and 22 atoms, where D + 1 is a multiple of 8)
-  constexpr bool can_split = (NAT * (NAT - 1) / 2 + 1) % 8 != 0;
+  // small batches split the training set over the chip like the Gaussian model does; the slices' energy sums follow the
+  // partial accumulators in the workspace
+  using C = PredictCfg<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, NW>;
   int nslices = 1, per = 0;
-  size_t bytes = 0;
-  if (can_split) bytes = predict_ws_cfg<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, NW>(a.ngroups, a.npoints, sms, &nslices, &per);
+  const size_t acc_bytes = predict_ws_cfg<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, NW>(a.ngroups, a.npoints, sms, &nslices, &per);
+  const int64_t blocks = (a.npoints + C::ROWS - 1) / C::ROWS;
+  const size_t bytes = nslices > 1 ? acc_bytes + (size_t)nslices * blocks * C::ROWS * sizeof(double) : 0;
   if (query) {
     *need = bytes;
     return KREG_OK;
   }
   a.nslices = 1;
   a.stages_per_slice = 0;
-  a.partial = nullptr;
-  if constexpr (can_split) {
-    if (nslices > 1 && ws && ws_bytes >= bytes) {
-      a.nslices = nslices;
-      a.stages_per_slice = per;
-      a.partial = static_cast<double *>(ws);
-      return launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, true, 1>(a, st);
-    }
+  a.partial = a.partial_e = nullptr;
+  if (nslices > 1 && ws && ws_bytes >= bytes) {
+    a.nslices = nslices;
+    a.stages_per_slice = per;
+    a.partial = static_cast<double *>(ws);
+    a.partial_e = a.partial + acc_bytes / sizeof(double);
+    return launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, true, 1>(a, st);
   }
   return a.G ? launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, false, 1>(a, st)
              : launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, false, NW, false, 1>(a, st);

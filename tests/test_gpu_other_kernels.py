@@ -183,15 +183,16 @@ def test_model_class_routes_kernel_arguments(eng, oracle, tmp_path):
     assert np.isfinite(m.validation_loss) and 2 ** -5 <= m.hyperparameters["sigma"].value <= 2 ** 9
 
 
-@pytest.mark.parametrize("nat", [9, 6, 21])
+@pytest.mark.parametrize("nat", [9, 6, 11, 21, 22])
 @pytest.mark.parametrize("n", [1, 3, 64])
 def test_radial_small_batches_take_the_split_path(eng, oracle, nat, n):
     """One geometry (an MD / geometry-optimisation step) and a few dozen: the training set is split over the chip like
-    for the Gaussian model (6 atoms: no free accumulator column for the energy sums, the batch runs unsplit); the numbers
-    agree with the oracle and with the same geometries inside a large batch."""
-    from mlatom_b200 import kernels
+    for the Gaussian model (6, 11 and 22 atoms: the accumulator row has no padding column, which is why the slices' energy
+    sums travel in their own array); the numbers agree with the oracle and with the same geometries inside a large batch."""
+    from mlatom_b200 import _lib, kernels
 
     ntr, sigma = 2000, 1.4
+    assert _lib.load().kreg_predict_radial_workspace_bytes(nat, ntr, n) > 0  # this batch does run split
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, 3000, 2)
     xeq = oracle.xeq(eq)

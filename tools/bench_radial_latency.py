@@ -12,7 +12,7 @@ from mlatom_b200.engine import _ptr, _stream
 
 dev = torch.device("cuda")
 out = []
-for nat in (9, 21):
+for nat in (6, 9, 21, 22):
     ntr = 10000
     eq = S.equilibrium(nat)
     xtr = torch.from_numpy(S.geometries(eq, ntr, 1)).to(dev)
