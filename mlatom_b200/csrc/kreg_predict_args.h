@@ -23,6 +23,7 @@ struct PredictArgs {
   int stages_per_slice;
   double *partial;
   double *partial_e;  // radial-kernel models: the slices' energy sums, [slice][geometry] (behind `partial` in the workspace)
+  size_t partial_doubles, partial_e_doubles;  // their extents (checked by the bounds-checking build)
   // models on MLatomF's radial kernel functions (predict_kernel<..., KIND = 1>; kreg_predict_radial): the packed model
   // then carries alpha_j itself and the plain column term -n_j/2, c1 is 1 (row term -n_i/2) and inv_s2 is 1
   int radial;         // 1: radial-kernel model (0: the Gaussian KREG model, everything below unused)

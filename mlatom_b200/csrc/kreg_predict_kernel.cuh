@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
     for (int e = tid; e < TS; e += kThreads) {
       double s = 0.0;
 #pragma unroll 4
-      for (int sl = 0; sl < args.nslices; sl++) s += src[(size_t)sl * slice_stride + e];
+      for (int sl = 0; sl < args.nslices; sl++) {
+        KREG_CHECK_STORE(src + (size_t)sl * slice_stride + e, args.partial, args.partial_doubles);
+        s += src[(size_t)sl * slice_stride + e];
+      }
       ftile[e] = s;
     }
   } else {
@@ -139,7 +142,10 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
       const int e = tid % TS, k = tid / TS;
       double s = 0.0;
 #pragma unroll 4
-      for (int sl = k; sl < args.nslices; sl += P) s += src[(size_t)sl * slice_stride + e];
+      for (int sl = k; sl < args.nslices; sl += P) {
+        KREG_CHECK_STORE(src + (size_t)sl * slice_stride + e, args.partial, args.partial_doubles);
+        s += src[(size_t)sl * slice_stride + e];
+      }
       part[k * TS + e] = s;
     }
     __syncthreads();
@@ -156,7 +162,10 @@ __global__ void __launch_bounds__(kThreads) predict_finish_kernel(const PredictA
     const double *es = args.partial_e + row;
     const size_t estride = (size_t)gridDim.x * ROWS;
     double s = 0.0;
-    for (int sl = tid & 31; sl < args.nslices; sl += 32) s += es[(size_t)sl * estride];
+    for (int sl = tid & 31; sl < args.nslices; sl += 32) {
+      KREG_CHECK_STORE(es + (size_t)sl * estride, args.partial_e, args.partial_e_doubles);
+      s += es[(size_t)sl * estride];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((tid & 31) == 0) e_sep = s;
@@ -465,10 +474,16 @@ __global__ void __launch_bounds__(NW * 32, (MT <= 2 && !A_IN_SMEM && NAT <= 9) ?
     double *dst = args.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::ROWS * TS;
     const int64_t left = args.npoints - row0;
     const int nvalid = (int)(left < C::ROWS ? left : C::ROWS);
-    for (int e = tid; e < nvalid * TS; e += kThreads) dst[e] = tile[e];
+    for (int e = tid; e < nvalid * TS; e += kThreads) {
+      KREG_CHECK_STORE(dst + e, args.partial, args.partial_doubles);
+      dst[e] = tile[e];
+    }
     if (KIND != 0) {  // radial kernels: this slice's energy sums, [slice][geometry]
       double *de = args.partial_e + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::ROWS;
-      for (int r = tid; r < nvalid; r += kThreads) de[r] = bias[r];
+      for (int r = tid; r < nvalid; r += kThreads) {
+        KREG_CHECK_STORE(de + r, args.partial_e, args.partial_e_doubles);
+        de[r] = bias[r];
+      }
     }
     return;
   }
@@ -544,6 +559,8 @@ static int launch_predict_radial_cfg(PredictArgs a, int sms, void *ws, size_t ws
     a.stages_per_slice = per;
     a.partial = static_cast<double *>(ws);
     a.partial_e = a.partial + acc_bytes / sizeof(double);
+    a.partial_doubles = acc_bytes / sizeof(double);
+    a.partial_e_doubles = (bytes - acc_bytes) / sizeof(double);
     return launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, true, 1>(a, st);
   }
   return a.G ? launch_predict_g<NAT, MT, false, A_IN_SMEM, GPS, NSTAGE, true, NW, false, 1>(a, st)
@@ -566,6 +583,7 @@ static int launch_predict_cfg(PredictArgs a, int sms, void *ws, size_t ws_bytes,
     a.nslices = nslices;
     a.stages_per_slice = per;
     a.partial = static_cast<double *>(ws);
+    a.partial_doubles = bytes / sizeof(double);
   }
   // energy-only requests skip the second GEMM entirely (the split mode always carries the full accumulators)
   if (a.nslices > 1) return launch_predict_g<NAT, MT, HAS_V, A_IN_SMEM, GPS, NSTAGE, true, NW, true>(a, st);
