@@ -431,10 +431,11 @@ class kreg:
             self.model_file = os.path.join(tmp, os.path.basename(saved_name or "kreg_tmp.npz"))
             if algo in ("grid", "brute"):
                 slices = self._grid(names, optimization_algorithm_kwargs.get("grid_size", 9))
-                # the fused path assembles the plain Gaussian KREG kernel: models on another kernel function or on the
-                # permutationally invariant kernel take the pointwise route (train + predict per grid point)
-                gaussian_kreg = self._other_kernel() is None and self._perm_inv_groups() is None
-                can_fuse = (fused and gaussian_kreg and set(names) <= {"lambda", "sigma"} and validation_loss_function is None
+                # the fused path assembles the Gaussian KREG kernel or (values-trained) one of MLatomF's other kernel
+                # functions; models on the permutationally invariant kernel take the pointwise route (train + predict per
+                # grid point)
+                plain_kernel = self._perm_inv_groups() is None
+                can_fuse = (fused and plain_kernel and set(names) <= {"lambda", "sigma"} and validation_loss_function is None
                             and cv_splits_molecular_databases is None and not any(v for v in unsupported.values()))
                 if can_fuse:
                     table = self._fused_grid_losses(names, slices, training_kwargs, prediction_kwargs,
@@ -448,8 +449,9 @@ class kreg:
                 # Python class, available here because the fused path makes it cheap
                 if not set(names) <= {"lambda", "sigma"}:
                     raise NotImplementedError("log2grid optimises 'sigma' and/or 'lambda'")
-                if self._other_kernel() is not None or self._perm_inv_groups() is not None:
-                    raise NotImplementedError("log2grid runs on the fused Gaussian KREG path only; use 'grid'")
+                if self._perm_inv_groups() is not None:
+                    raise NotImplementedError("log2grid runs on the fused path, which the permutationally invariant kernel "
+                                              "does not have; use 'grid'")
                 best, _, self.grid_trace = self._log2_grid_search(names, optimization_algorithm_kwargs, training_kwargs,
                                                                   prediction_kwargs, subtraining_molecular_database,
                                                                   validation_molecular_database)
@@ -493,8 +495,11 @@ class kreg:
             self.equilibrium_molecule = self.get_equilibrium_molecule(molecular_database=sub_db)
         _, _, prior = self._lambdas_and_prior(tk.get("prior"))
         fixed_lam_g = self.hyperparameters["lambdaGradXYZ"].value if "lambdaGradXYZ" in self.hyperparameters.keys() else None
+        other = self._other_kernel()
+        if other is not None and g_learn is not None:
+            raise NotImplementedError("models on the non-Gaussian kernels are trained on values only here")
         return _FusedHoldout(t, self.equilibrium_molecule.xyz_coordinates, sub_db, val_db, p_learn, g_learn, prior,
-                             fixed_lam_g)
+                             fixed_lam_g, kernel=other)
 
     def _fused_grid_losses(self, names, slices, training_kwargs, prediction_kwargs, sub_db, val_db):
         """All (lambda, sigma) grid losses with K(sigma) built once per sigma."""
@@ -589,8 +594,9 @@ class _FusedHoldout:
     model_cls.py:577-585).  A matrix that is not positive definite at some lambda is solved by the Bunch-Kaufman
     fallback, as the reference does (mathUtils.f90:24-26)."""
 
-    def __init__(self, t, eq_xyz, sub_db, val_db, p_learn, g_learn, prior, fixed_lam_g):
+    def __init__(self, t, eq_xyz, sub_db, val_db, p_learn, g_learn, prior, fixed_lam_g, kernel=None):
         self.p_learn, self.g_learn, self.fixed_lam_g = p_learn, g_learn, fixed_lam_g
+        self.kernel = kernel  # None: the Gaussian KREG model; (name, nn): values-trained model on that kernel function
         self.xeq = engine.xeq(t(eq_xyz))
         self.xyz, self.xyz_val = t(sub_db.xyz_coordinates), t(val_db.xyz_coordinates)
         ntr, nat = int(self.xyz.shape[0]), int(self.xyz.shape[1])
@@ -607,7 +613,10 @@ class _FusedHoldout:
         self.g_val = np.asarray(val_db.get_xyz_vectorial_properties(g_learn)) if g_learn is not None else None
         m = self.nv + self.ng
         dev = self.xyz.device
-        if self.xyz.is_cuda:
+        if kernel is not None:
+            self.k0 = None  # kernel_block_ex returns K(sigma)
+            self.work = torch.empty((m, m), dtype=torch.float64, device=dev)
+        elif self.xyz.is_cuda:
             self.k0 = engine.empty_kernel_matrix(m, self.nv if self.ng else 0, dev)
             self.work = engine.empty_kernel_matrix(m, self.nv if self.ng else 0, dev)
         else:
@@ -616,11 +625,16 @@ class _FusedHoldout:
         self.diag = torch.arange(m, device=dev)
         self.sigma = None
         self.fallbacks = 0  # grid points solved by the symmetric-indefinite route
-        ws_bytes = engine.build_workspace_bytes(nat, ntr, self.ng) if self.xyz.is_cuda else 0
+        ws_bytes = engine.build_workspace_bytes(nat, ntr, self.ng) if self.xyz.is_cuda and kernel is None else 0
         self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None  # one scratch for every sigma
 
     def set_sigma(self, sigma):
         self.sigma = float(sigma)
+        if self.kernel is not None:
+            self.k0 = None  # release the previous sigma's matrix before the next one is allocated
+            self.k0 = engine.kernel_block_ex(self.kernel[0], self.xyz, self.xyz, self.xeq, self.sigma, nn=self.kernel[1],
+                                             symmetric=True, lam=0.0)
+            return
         engine.build_kernel_matrix(self.xyz, self.xeq, self.sigma, 0.0, 0.0, use_values=self.nv > 0,
                                    use_gradients=self.ng > 0, fill=FILL_LOWER, out=self.k0, workspace=self.ws)
 
@@ -647,7 +661,12 @@ class _FusedHoldout:
                     raise
                 return float("inf")  # exactly singular pivot: no solution to score
             self.fallbacks += 1
-        model = engine.PackedModel.from_training_set(self.xyz, self.xeq, alpha, self.sigma, self.prior_value, nv, self.ng)
+        if self.kernel is not None:
+            from .kernels import RadialModel
+
+            model = RadialModel(self.kernel[0], self.kernel[1], self.xyz, self.xeq, alpha, self.sigma, self.prior_value)
+        else:
+            model = engine.PackedModel.from_training_set(self.xyz, self.xeq, alpha, self.sigma, self.prior_value, nv, self.ng)
         e, g = model.predict(self.xyz_val, self.p_learn is not None, self.g_learn is not None)
         total = 1.0
         if self.p_learn is not None:

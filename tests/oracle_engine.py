@@ -85,6 +85,32 @@ def install_oracle_engine(setattr_, oracle):
         return torch.from_numpy(oracle.hessian_kregf90(x_train.numpy(), a, sigma, nv, xte,
                                                        oracle.descriptors(xte, xeq.numpy())))
 
+    def kernel_block_ex(kind, xyz_a, xyz_b, xeq, sigma, nn=2, symmetric=False, lam=0.0):
+        xa, xb, q = xyz_a.numpy(), xyz_b.numpy(), xeq.numpy()
+        k = oracle.kernel_block_generic(kind, oracle.descriptors(xa, q), oracle.descriptors(xb, q), sigma, nn=nn)
+        if symmetric:
+            k[np.diag_indices_from(k)] = 1.0 + lam
+        return torch.from_numpy(k)
+
+    class FakeRadialModel:
+        def __init__(self, kind, nn, xyz_tr, xeq, alpha, sigma, prior):
+            self.kind, self.nn, self.sigma, self.prior, self.device = kind.lower(), int(nn), sigma, prior, torch.device("cpu")
+            self.xeq = xeq.numpy()
+            self.X = oracle.descriptors(xyz_tr.numpy(), self.xeq)
+            self.alpha = alpha.numpy().reshape(-1)
+
+        def predict(self, xyz, energy=True, gradient=True):
+            x = np.ascontiguousarray(xyz.numpy() if torch.is_tensor(xyz) else xyz)
+            e, g = oracle.predict_generic(self.kind, self.X, self.alpha, self.sigma, self.prior, x,
+                                          oracle.descriptors(x, self.xeq), nn=self.nn, calc_grad=gradient)
+            return (torch.from_numpy(e) if energy else None), (torch.from_numpy(g) if gradient else None)
+
+    from mlatom_b200 import kernels as KN
+
+    setattr_(KN, "RadialModel", FakeRadialModel)
+    setattr_(KN, "_dev", lambda t, device=None: torch.as_tensor(np.ascontiguousarray(
+        t.detach().cpu().numpy() if torch.is_tensor(t) else t, dtype=np.float64)))
+    setattr_(eng, "kernel_block_ex", kernel_block_ex)
     setattr_(eng, "hessian", hessian)
     setattr_(eng, "GraphPredictor", FakeGraph)
     setattr_(eng, "build_kernel_matrix", build)

@@ -182,6 +182,46 @@ def test_grid_search_fused_equals_pointwise(fake_engine, tmp_path):
     assert abs(res[0][2] - res[1][2]) <= 1e-9 * res[1][2]
 
 
+@pytest.mark.parametrize("kernel", ["Matern", "exponential", "Laplacian"])
+def test_grid_search_on_the_other_kernels_fused_equals_pointwise(fake_engine, tmp_path, kernel):
+    """Values-trained models on MLatomF's other kernel functions: the fused grid (K(sigma) once per sigma through
+    kernel_block_ex, lambda on the diagonal of a copy) visits the points and returns the winner and the loss of the
+    pointwise route, and the log2 grid runs on them too."""
+    nat = 5
+    sub, _, _, _ = make_db(D, nat, 12, 1)
+    val, _, _, _ = make_db(D, nat, 7, 3)
+    kw = dict(training_kwargs={"property_to_learn": "energy", "prior": "mean"},
+              prediction_kwargs={"property_to_predict": "estimated_energy"},
+              subtraining_molecular_database=sub, validation_molecular_database=val)
+    res = []
+    for fused in (True, False):
+        model = M.kreg(model_file=str(tmp_path / f"g{fused}"), ml_program="MLatomF")
+        model.additional_mlatomf_args = [f"kernel={kernel}", "nn=1"]
+        model.hyperparameters["lambda"].minval, model.hyperparameters["lambda"].maxval = 1e-8, 1e-2
+        model.hyperparameters["sigma"].minval, model.hyperparameters["sigma"].maxval = 0.3, 8.0
+        model.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="grid",
+                                       optimization_algorithm_kwargs={"grid_size": 3}, fused=fused, **kw)
+        assert type(model.kreg_api).__name__ == "RadialKREG" and model.kreg_api.nn == 1
+        res.append((model.hyperparameters["lambda"].value, model.hyperparameters["sigma"].value, model.validation_loss))
+        if fused:
+            assert len(model.grid_losses) == 9
+            assert abs(min(model.grid_losses.values()) - model.validation_loss) <= 1e-9 * model.validation_loss
+    assert res[0][:2] == res[1][:2]
+    assert abs(res[0][2] - res[1][2]) <= 1e-9 * res[1][2]
+    model = M.kreg(model_file=str(tmp_path / "lg"), ml_program="MLatomF")
+    model.additional_mlatomf_args = [f"kernel={kernel}", "nn=1"]
+    model.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="log2grid",
+                                   optimization_algorithm_kwargs={"depth": 2, "points": {"sigma": 5, "lambda": 3}}, **kw)
+    best = min(t[2] for t in model.grid_trace)
+    assert len(model.grid_trace) == 2 * 5 * 2 * 3 and abs(model.validation_loss - best) <= 1e-9 * best
+    with pytest.raises(NotImplementedError):  # gradient-trained models on these kernels are not built: fused or not
+        model.optimize_hyperparameters(
+            hyperparameters=["sigma"], optimization_algorithm="grid", optimization_algorithm_kwargs={"grid_size": 2},
+            training_kwargs={"property_to_learn": "energy", "xyz_derivative_property_to_learn": "energy_gradients"},
+            prediction_kwargs={"property_to_predict": "estimated_energy"},
+            subtraining_molecular_database=sub, validation_molecular_database=val)
+
+
 def test_log2_grid_search_follows_mlatomf_recursion(fake_engine, tmp_path):
     """optLog2Grid / optLambdaLog2Grid (A_KRR.f90:1049-1376): nested log2 grids, zoom +-1 step around the best,
     lgOptDepth levels, first minimum wins -- restated here with one train+predict per point."""

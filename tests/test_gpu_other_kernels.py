@@ -173,7 +173,7 @@ def test_model_class_routes_kernel_arguments(eng, oracle, tmp_path):
     assert type(m2.kreg_api).__name__ == "RadialKREG" and m2.kreg_api.nn == nn
     e2, g2 = m2.predict_xyz(xte)
     assert np.array_equal(e2, e) and np.array_equal(g2, g)
-    # hyper-parameter grid on this kernel: the pointwise route (the fused path is the Gaussian kernel's)
+    # hyper-parameter grid on this kernel (fused: K(sigma) from kreg_kernel_block_ex once per sigma)
     sub = data.molecular_database.from_arrays(z, xtr[:240], energy=etr[:240])
     val = data.molecular_database.from_arrays(z, xtr[240:], energy=etr[240:])
     m.optimize_hyperparameters(hyperparameters=["sigma"], training_kwargs={"property_to_learn": "energy", "prior": "mean"},
@@ -209,3 +209,44 @@ def test_radial_small_batches_take_the_split_path(eng, oracle, nat, n):
     assert np.abs(g_big.cpu().numpy()[:n] - g).max() <= 1e-12 * scale
     e_only, _ = model.predict(dev(xte[:n]), True, False)
     assert np.abs(e_only.cpu().numpy() - e).max() <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("kernel,nn", [("Matern", 2), ("exponential", 2), ("Laplacian", 2)])
+def test_grid_search_on_the_other_kernels_fused_equals_pointwise(eng, kernel, nn, tmp_path):
+    """The fused (lambda, sigma) grid -- K(sigma) assembled once per sigma, re-factorised per lambda, everything resident --
+    returns the winner and the loss the pointwise route (train + predict per point, as the reference does) returns; the
+    log2 grid of MLatomF runs on these kernels too and its winner retrains to the loss the search reported."""
+    from mlatom_b200 import data, models
+
+    nat, ntr = 7, 260
+    eq = S.equilibrium(nat)
+    z = np.array([6, 6, 8, 1, 1, 1, 1])
+    x = S.geometries(eq, ntr, 1)
+    e, _ = S.pair_potential(x, eq)
+    sub = data.molecular_database.from_arrays(z, x[:200], energy=e[:200])
+    val = data.molecular_database.from_arrays(z, x[200:], energy=e[200:])
+    kw = dict(training_kwargs={"property_to_learn": "energy", "prior": "mean"},
+              prediction_kwargs={"property_to_predict": "estimated_energy"},
+              subtraining_molecular_database=sub, validation_molecular_database=val)
+    res = []
+    for fused in (True, False):
+        m = models.kreg(model_file=str(tmp_path / f"g{fused}"), ml_program="MLatomF", equilibrium_molecule=data.molecule.from_arrays(z, eq))
+        m.additional_mlatomf_args = [f"kernel={kernel}", f"nn={nn}"]
+        m.hyperparameters["lambda"].minval, m.hyperparameters["lambda"].maxval = 1e-10, 1e-3
+        m.hyperparameters["sigma"].minval, m.hyperparameters["sigma"].maxval = 0.5, 64.0
+        m.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="grid",
+                                   optimization_algorithm_kwargs={"grid_size": 4}, fused=fused, **kw)
+        assert type(m.kreg_api).__name__ == "RadialKREG" and m.kreg_api.kernel.lower() == kernel.lower()
+        res.append((m.hyperparameters["lambda"].value, m.hyperparameters["sigma"].value, m.validation_loss))
+        if fused:
+            assert len(m.grid_losses) == 16 and abs(min(m.grid_losses.values()) - m.validation_loss) <= 1e-8 * m.validation_loss
+    assert res[0][:2] == res[1][:2]
+    assert abs(res[0][2] - res[1][2]) <= 1e-8 * res[1][2]
+    m = models.kreg(model_file=str(tmp_path / "lg"), ml_program="MLatomF", equilibrium_molecule=data.molecule.from_arrays(z, eq))
+    m.additional_mlatomf_args = [f"kernel={kernel}", f"nn={nn}"]
+    m.hyperparameters["lambda"].minval, m.hyperparameters["lambda"].maxval = 2.0 ** -30, 2.0 ** -10
+    m.hyperparameters["sigma"].minval, m.hyperparameters["sigma"].maxval = 0.5, 64.0
+    m.optimize_hyperparameters(hyperparameters=["lambda", "sigma"], optimization_algorithm="log2grid",
+                               optimization_algorithm_kwargs={"depth": 2, "points": {"sigma": 5, "lambda": 3}}, **kw)
+    best = min(t[2] for t in m.grid_trace)
+    assert len(m.grid_trace) == 2 * 5 * 2 * 3 and abs(m.validation_loss - best) <= 1e-8 * best
