@@ -153,7 +153,8 @@ int kreg_kernel_block_ex(int kind, int nn, int natoms, int64_t na, const double 
  * Matern of order nn >= 1: the reference's analytic derivative; exponential (and Matern nn = 0): the reference takes a
  * central difference of Kfunk in descriptor space (:1222-1230), here the analytic phi = k / (sigma r), 0 at r = 0;
  * KREG_KERNEL_GAUSSIAN is accepted too (the same numbers as kreg_predict through this path).  The Laplacian kernel
- * (L1 distance, no GEMM form) predicts energies through kreg_kernel_block_ex + kreg_block_dot. */
+ * (L1 distance, no GEMM form) predicts through kreg_kernel_block_ex + kreg_block_dot (energies) or
+ * kreg_laplacian_predict (energies and analytic gradients). */
 size_t kreg_radial_packed_model_bytes(int natoms, int64_t ntrain);
 /* Packs the model in the layout kreg_predict_radial streams for this molecule size (the kernel width does not enter):
  * `packed` must be 256-byte aligned, kreg_radial_packed_model_bytes long; center[D] is written. */
@@ -169,6 +170,15 @@ int kreg_predict_radial(int kind, int nn, int natoms, int64_t ntrain, const void
 /* E[i] = prior + sum_j K[i][j] alpha[j] for a materialised kernel block (row-major na x ldk): deterministic. */
 int kreg_block_dot(int64_t na, int64_t nb, const double *K, int64_t ldk, const double *alpha, double prior, double *E,
                    void *stream);
+/* Laplacian-kernel model: energies and ANALYTIC Cartesian gradients from the materialised block K[i][j] =
+ * exp(-|X_i - X_j|_1 / sigma) between `npoints` geometries and the training set (kreg_kernel_block_ex):
+ *   E[i] = prior + sum_j alpha_j K_ij,   dE/dX_id = -(1/sigma) sum_j alpha_j K_ij sign(X_id - X_jd),   G = J_i^T dE/dX_i.
+ * The reference has no closed form here: YgradXYZest_KRR (A_KRR_kernel.f90:731-744) reaches dKdXid's central difference of
+ * Kfunk in descriptor space (:1222-1230), which approximates this derivative (identical away from the kinks X_id == X_jd).
+ * X_train: DEVICE [ntrain][D] descriptors (kreg_descriptors); K row-major npoints x ldk. */
+int kreg_laplacian_predict(int natoms, int64_t ntrain, const double *X_train, const double *alpha, const double *xeq,
+                           double sigma, double prior, int64_t npoints, const double *xyz, const double *K, int64_t ldk,
+                           int flags, double *E, double *G, void *stream);
 
 /* Permutationally invariant kernel (values-trained models) --------------------------------------------------------
  * MLatomF `molDescrType=permuted permInvKernel` (A_KRR_kernel.f90:773-804 kernelFunction; descriptor calcX,

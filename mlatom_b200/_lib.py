@@ -68,6 +68,11 @@ PROTOTYPES = {
          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "kreg_block_dot": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p]),
+    "kreg_laplacian_predict": (
+        c_int,
+        [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_void_p, c_int64, c_int,
+         c_void_p, c_void_p, c_void_p],
+    ),
     "kreg_perm_descriptors": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "kreg_perm_self_terms": (
         c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),

@@ -8,8 +8,9 @@ Reference: ``Kfunk`` (MLatomF_src/A_KRR_kernel.f90:806-851, ``distance`` :2040-2
 
 Scope: models trained on VALUES.  Energies for all kernels; analytic gradients for the kernels of the Euclidean
 distance (Matern as the reference; exponential analytically where the reference takes central differences); the
-Laplacian kernel predicts energies only.  Everything runs in the CUDA kernels behind ``include/kreg_b200.h``
-(kreg_kernel_block_ex, kreg_solve, kreg_pack_model_radial, kreg_predict_radial, kreg_block_dot); no CPU fallback.
+Laplacian kernel (L1 distance, no GEMM form) predicts through its materialised kernel block.  Everything runs in the CUDA kernels behind ``include/kreg_b200.h``
+(kreg_kernel_block_ex, kreg_solve, kreg_pack_model_radial, kreg_predict_radial, kreg_block_dot, kreg_laplacian_predict);
+no CPU fallback.
 """
 from __future__ import annotations
 
@@ -40,6 +41,7 @@ class RadialModel:
         assert self.alpha.numel() == self.ntrain
         self.sigma, self.prior, self.xeq = float(sigma), float(prior), xeq_
         self.packed = self.center = None
+        self.x_tr = None  # training descriptors (Laplacian gradients only; built on first use)
         if self.kind != "laplacian":
             nbytes = _lib.load().kreg_radial_packed_model_bytes(self.natoms, self.ntrain)
             self.packed = torch.empty(nbytes, dtype=torch.uint8, device=xeq_.device)
@@ -57,17 +59,27 @@ class RadialModel:
         xyz = _dev(xyz, self.device)
         n = int(xyz.shape[0])
         if self.kind == "laplacian":
-            if gradient:
-                raise NotImplementedError("the Laplacian kernel (L1 distance) predicts energies only here; the reference "
-                                          "differentiates it numerically (A_KRR_kernel.f90:1222-1230)")
-            e = torch.empty(n, dtype=F64, device=xyz.device)
-            step = max(1, (256 << 20) // (8 * max(self.ntrain, 1)))  # kernel block in slabs of at most 256 MB
+            # L1 distance: no GEMM form.  The kernel block goes through HBM in slabs of at most 256 MB; energies are its
+            # product with alpha, gradients the analytic sign form (the reference differentiates this kernel numerically,
+            # A_KRR_kernel.f90:1222-1230)
+            e = torch.empty(n, dtype=F64, device=xyz.device) if energy or not gradient else None
+            g = torch.empty((n, self.natoms, 3), dtype=F64, device=xyz.device) if gradient else None
+            if gradient and self.x_tr is None:
+                self.x_tr = engine.descriptors(self.xyz_tr, self.xeq)
+            step = max(1, (256 << 20) // (8 * max(self.ntrain, 1)))
             for lo in range(0, n, step):
-                kt = engine.kernel_block_ex("laplacian", xyz[lo:lo + step], self.xyz_tr, self.xeq, self.sigma)
+                x = xyz[lo:lo + step]
+                kt = engine.kernel_block_ex("laplacian", x, self.xyz_tr, self.xeq, self.sigma)
                 with _on(xyz):
-                    call("kreg_block_dot", kt.shape[0], kt.shape[1], _ptr(kt), kt.stride(0), _ptr(self.alpha), self.prior,
-                         _ptr(e[lo:lo + step]), _stream(xyz.device))
-            return (e if energy else None), None
+                    if gradient:
+                        flags = PREDICT_GRADIENT | (PREDICT_ENERGY if energy else 0)
+                        call("kreg_laplacian_predict", self.natoms, self.ntrain, _ptr(self.x_tr), _ptr(self.alpha),
+                             _ptr(self.xeq), self.sigma, self.prior, kt.shape[0], _ptr(x), _ptr(kt), kt.stride(0), flags,
+                             _ptr(e[lo:lo + step]) if energy else None, _ptr(g[lo:lo + step]), _stream(xyz.device))
+                    else:
+                        call("kreg_block_dot", kt.shape[0], kt.shape[1], _ptr(kt), kt.stride(0), _ptr(self.alpha), self.prior,
+                             _ptr(e[lo:lo + step]), _stream(xyz.device))
+            return (e if energy else None), g
         e = torch.empty(n, dtype=F64, device=xyz.device) if energy else None
         g = torch.empty((n, self.natoms, 3), dtype=F64, device=xyz.device) if gradient else None
         if n == 0:

@@ -119,21 +119,48 @@ def test_radial_gaussian_path_equals_the_fused_kernels(eng):
     assert float((e1 - e2).abs().max()) <= 1e-13 * scale and float((g1 - g2).abs().max()) <= 1e-12 * scale
 
 
-def test_laplacian_model_predicts_energies_only(eng, oracle):
+@pytest.mark.parametrize("nat,ntr,nte", [(9, 120, 77), (2, 9, 9), (5, 64, 70), (21, 130, 65), (24, 70, 19), (30, 37, 29),
+                                         (45, 30, 11)])
+def test_laplacian_model_energies_and_analytic_gradients(eng, oracle, nat, ntr, nte):
+    """Laplacian kernel (L1 distance): energies from the materialised kernel block; gradients in the analytic sign form
+    (kreg_laplacian_predict).  The reference differentiates this kernel numerically (central difference of Kfunk in
+    descriptor space, A_KRR_kernel.f90:1222-1230), which the oracle restates: the two agree to the error of that
+    difference.  24 / 30 / 45 atoms: the three CTA shapes of the kernel."""
     from mlatom_b200 import kernels
 
-    nat, ntr, nte, sigma = 9, 120, 77, 3.0
+    sigma = 3.0 * max(1.0, nat / 9.0)
     eq = S.equilibrium(nat)
     xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, nte, 2)
     xeq = oracle.xeq(eq)
     alpha = np.random.default_rng(6).standard_normal(ntr)
     model = kernels.RadialModel("laplacian", 0, dev(xtr), dev(xeq), dev(alpha), sigma, 7.0)
     e, g = model.predict(dev(xte), True, False)
-    e_ref, _ = oracle.predict_generic("laplacian", oracle.descriptors(xtr, xeq), alpha, sigma, 7.0, xte,
-                                      oracle.descriptors(xte, xeq), calc_grad=False)
+    e_ref, g_ref = oracle.predict_generic("laplacian", oracle.descriptors(xtr, xeq), alpha, sigma, 7.0, xte,
+                                          oracle.descriptors(xte, xeq))
     assert g is None and np.abs(e.cpu().numpy() - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
-    with pytest.raises(NotImplementedError):
-        model.predict(dev(xte), True, True)
+    e2, g2 = model.predict(dev(xte), True, True)
+    assert np.abs(e2.cpu().numpy() - e_ref).max() <= 1e-10 * np.abs(e_ref).max()
+    # a central difference that straddles a kink X_id == X_jd of the L1 distance (step sqrt(eps) X_id) is not a derivative:
+    # geometries with such a pair are compared with the closed form only (below)
+    Xtr, Xte = oracle.descriptors(xtr, xeq), oracle.descriptors(xte, xeq)
+    h = np.sqrt(np.finfo(float).eps) * np.abs(Xte)
+    smooth = ~(np.abs(Xte[:, None, :] - Xtr[None, :, :]) < 2.0 * h[:, None, :]).any(axis=(1, 2))
+    assert smooth.sum() >= nte // 2
+    dg = np.abs(g2.cpu().numpy() - g_ref)[smooth].max()
+    assert dg <= 2e-6 * max(1.0, np.abs(g_ref).max()), float(dg)
+    e3, g3 = model.predict(dev(xte), False, True)
+    assert e3 is None and np.array_equal(g3.cpu().numpy(), g2.cpu().numpy())
+    # the same numbers from the closed form on the host
+    w = np.exp(-np.abs(Xte[:, None, :] - Xtr[None, :, :]).sum(-1) / sigma) * alpha[None, :]
+    gd = -np.einsum("ij,ijd->id", w, np.sign(Xte[:, None, :] - Xtr[None, :, :])) / sigma
+    want = np.zeros_like(xte)
+    for a in range(nat):
+        for c in range(nat):
+            if c != a:
+                d = (2 * nat - min(a, c) - 1) * min(a, c) // 2 + abs(c - a) - 1
+                diff = xte[:, a] - xte[:, c]
+                want[:, a] += (gd[:, d] * -Xte[:, d] / (diff ** 2).sum(-1))[:, None] * diff
+    assert np.abs(g2.cpu().numpy() - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
 
 
 def test_model_class_routes_kernel_arguments(eng, oracle, tmp_path):
