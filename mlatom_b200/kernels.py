@@ -54,8 +54,19 @@ class RadialModel:
     def device(self):
         return self.xeq.device
 
-    def predict(self, xyz: torch.Tensor, energy: bool = True, gradient: bool = True):
-        """xyz (N, Nat, 3) cuda fp64 -> (E (N,) or None, dE/dxyz (N, Nat, 3) or None)."""
+    def workspace(self, n: int) -> Optional[torch.Tensor]:
+        """Scratch of a batch of n geometries (the small-batch split launch; the tiled path above 24 atoms), for a caller
+        that must own it -- a CUDA graph keeps the raw pointer (engine.GraphPredictor)."""
+        if self.kind == "laplacian":
+            return None
+        with _on(self.xeq):
+            nbytes = int(_lib.load().kreg_predict_radial_workspace_bytes(self.natoms, self.ntrain, int(n)))
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+
+    def predict(self, xyz: torch.Tensor, energy: bool = True, gradient: bool = True, out_e: Optional[torch.Tensor] = None,
+                out_g: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None):
+        """xyz (N, Nat, 3) cuda fp64 -> (E (N,) or None, dE/dxyz (N, Nat, 3) or None).  out_e / out_g / ws: caller-owned
+        result and scratch buffers (the Euclidean-distance kernels; the same protocol as engine.PackedModel.predict)."""
         xyz = _dev(xyz, self.device)
         n = int(xyz.shape[0])
         if self.kind == "laplacian":
@@ -80,14 +91,17 @@ class RadialModel:
                         call("kreg_block_dot", kt.shape[0], kt.shape[1], _ptr(kt), kt.stride(0), _ptr(self.alpha), self.prior,
                              _ptr(e[lo:lo + step]), _stream(xyz.device))
             return (e if energy else None), g
-        e = torch.empty(n, dtype=F64, device=xyz.device) if energy else None
-        g = torch.empty((n, self.natoms, 3), dtype=F64, device=xyz.device) if gradient else None
+        e = (out_e if out_e is not None else torch.empty(n, dtype=F64, device=xyz.device)) if energy else None
+        g = (out_g if out_g is not None else torch.empty((n, self.natoms, 3), dtype=F64, device=xyz.device)) if gradient else None
         if n == 0:
             return e, g
         flags = (PREDICT_ENERGY if energy else 0) | (PREDICT_GRADIENT if gradient else 0)
         with _on(xyz):
-            ws_bytes = int(_lib.load().kreg_predict_radial_workspace_bytes(self.natoms, self.ntrain, n))
-            ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=xyz.device)
+            if ws is not None:
+                ws_bytes = ws.numel()
+            else:
+                ws_bytes = int(_lib.load().kreg_predict_radial_workspace_bytes(self.natoms, self.ntrain, n))
+                ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=xyz.device)
             call("kreg_predict_radial", KERNEL_KINDS[self.kind], self.nn, self.natoms, self.ntrain, _ptr(self.packed),
                  _ptr(self.center), _ptr(self.xeq), self.sigma, self.prior, n, _ptr(xyz), flags, _ptr(e), _ptr(g), _ptr(ws),
                  ws_bytes, _stream(xyz.device))
@@ -163,6 +177,17 @@ class RadialKREG(KREG_API):
     def predict_arrays(self, xyz, calculate_energy=True, calculate_energy_gradients=True):
         model = self._ensure_model()
         on_device = torch.is_tensor(xyz) and xyz.is_cuda
+        if not on_device and model.kind != "laplacian" and model.device.type == "cuda":
+            n = int(np.shape(xyz)[0])
+            if 0 < n <= self.graph_batch_limit:
+                # MD / geometry optimisation: the same small batch every step -> replay a captured CUDA graph, as the
+                # Gaussian model does (KREG_API.predict_arrays)
+                key = (n, bool(calculate_energy), bool(calculate_energy_gradients))
+                gp = self._graphs.get(key)
+                if gp is None or gp.model is not model:
+                    gp = self._graphs[key] = engine.GraphPredictor(model, n, calculate_energy, calculate_energy_gradients)
+                e, g = gp(np.asarray(xyz.detach().cpu().numpy() if torch.is_tensor(xyz) else xyz, dtype=np.float64))
+                return (None if e is None else e.copy()), (None if g is None else g.copy())
         e, g = model.predict(_dev(xyz, model.device), calculate_energy, calculate_energy_gradients)
         if on_device:
             return e, g

@@ -277,3 +277,38 @@ def test_grid_search_on_the_other_kernels_fused_equals_pointwise(eng, kernel, nn
                                optimization_algorithm_kwargs={"depth": 2, "points": {"sigma": 5, "lambda": 3}}, **kw)
     best = min(t[2] for t in m.grid_trace)
     assert len(m.grid_trace) == 2 * 5 * 2 * 3 and abs(m.validation_loss - best) <= 1e-8 * best
+
+
+@pytest.mark.parametrize("nat", [9, 26])
+def test_radial_small_host_batches_replay_a_graph(eng, oracle, nat):
+    """MD / geometry-optimisation steps on a Matern model: small numpy batches go through a captured CUDA graph (as the
+    Gaussian model's do); the numbers are the eager device path's, and a larger batch in between (which allocates its own
+    scratch) does not disturb the graph's."""
+    from mlatom_b200 import kernels
+
+    ntr, sigma = 500, 1.4
+    eq = S.equilibrium(nat)
+    xtr, xte = S.geometries(eq, ntr, 1), S.geometries(eq, 400, 2)
+    etr, _ = S.pair_potential(xtr, eq)
+    api = kernels.RadialKREG("Matern", 2)
+    api.train_arrays(sigma, 1e-6, 0.0, xtr, eq, y=etr, prior="mean")
+    e_dev, g_dev = api.predict_arrays(dev(xte))
+    e_dev, g_dev = e_dev.cpu().numpy(), g_dev.cpu().numpy()
+    # batches of different sizes split the training set differently: same sums in another order
+    tol_e, tol_g = 1e-13 * np.abs(api.alpha).sum(), 1e-12 * np.abs(api.alpha).sum()
+    first = {}
+    for n in (1, 3, 1):
+        e, g = api.predict_arrays(xte[:n])
+        assert isinstance(e, np.ndarray) and np.abs(e - e_dev[:n]).max() <= tol_e and np.abs(g - g_dev[:n]).max() <= tol_g
+        if n in first:  # a replay of the same graph on the same input: the same bits
+            assert np.array_equal(e, first[n][0]) and np.array_equal(g, first[n][1])
+        first[n] = (e, g)
+    assert set(k[0] for k in api._graphs) == {1, 3}
+    e_big, g_big = api.predict_arrays(xte)  # eager, its own scratch
+    assert np.array_equal(e_big, e_dev) and np.array_equal(g_big, g_dev)
+    e, g = api.predict_arrays(xte[:1])
+    assert np.array_equal(e, first[1][0]) and np.array_equal(g, first[1][1])
+    e, g = api.predict_arrays(xte[5:6])
+    assert np.abs(e - e_dev[5:6]).max() <= tol_e and np.abs(g - g_dev[5:6]).max() <= tol_g
+    e_only, none = api.predict_arrays(xte[:1], True, False)
+    assert none is None and np.abs(e_only - e_dev[:1]).max() <= tol_e
