@@ -222,6 +222,30 @@ def test_grid_search_on_the_other_kernels_fused_equals_pointwise(fake_engine, tm
             subtraining_molecular_database=sub, validation_molecular_database=val)
 
 
+@pytest.mark.parametrize("kernel", ["Matern", "Laplacian"])
+def test_other_kernel_models_through_the_class(fake_engine, oracle, tmp_path, kernel):
+    """kreg(ml_program='MLatomF') + additional_mlatomf_args=['kernel=...'] (mlatom/models.py:494-495): train on values,
+    predict energies and gradients into the molecules, reload from the .npz file (KREG_API keys + kernel, nn)."""
+    nat = 5
+    db, xyz, e, _ = make_db(D, nat, 16, 1)
+    model = M.kreg(model_file=str(tmp_path / "m"), ml_program="MLatomF", hyperparameters={"sigma": 2.0, "lambda": 1e-6})
+    model.additional_mlatomf_args = [f"kernel={kernel}", "nn=1"]
+    model.train(molecular_database=db, property_to_learn="energy", prior="mean")
+    assert type(model.kreg_api).__name__ == "RadialKREG" and model.model_file.endswith(".npz") and os.path.exists(model.model_file)
+    tdb, xte, _, _ = make_db(D, nat, 6, 2, with_labels=False)
+    model.predict(molecular_database=tdb, calculate_energy=True, calculate_energy_gradients=True)
+    xeq = oracle.xeq(np.asarray(model.kreg_api.Req))  # no equilibrium molecule given: the lowest-energy training geometry
+    a = np.asarray(model.kreg_api.alpha).reshape(-1)
+    e_ref, g_ref = oracle.predict_generic(kernel.lower(), oracle.descriptors(xyz, xeq), a, 2.0, float(e.mean()), xte,
+                                          oracle.descriptors(xte, xeq), nn=1)
+    assert np.abs(tdb.get_properties("energy") - e_ref).max() <= 1e-12 * np.abs(e_ref).max()
+    assert np.abs(tdb.get_xyz_vectorial_properties("energy_gradients") - g_ref).max() <= 1e-12 * max(1.0, np.abs(g_ref).max())
+    again = M.kreg(model_file=model.model_file, ml_program="MLatomF")
+    assert type(again.kreg_api).__name__ == "RadialKREG" and again.kreg_api.kernel == kernel and again.kreg_api.nn == 1
+    e2, g2 = again.predict_xyz(xte)
+    assert np.array_equal(e2, tdb.get_properties("energy"))
+
+
 def test_log2_grid_search_follows_mlatomf_recursion(fake_engine, tmp_path):
     """optLog2Grid / optLambdaLog2Grid (A_KRR.f90:1049-1376): nested log2 grids, zoom +-1 step around the best,
     lgOptDepth levels, first minimum wins -- restated here with one train+predict per point."""
